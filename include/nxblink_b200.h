@@ -1,0 +1,127 @@
+/* nxblink_b200 -- C-ABI of the B200 Rao-Teh blink-model sweep engine.
+ *
+ * The reference (argriffing/nxblink) is pure Python and has no FFI; its boundary
+ * for this path is the Python call surface listed in SURVEY.md section 8(b).  The
+ * entry points below are what a ctypes binding of that surface needs; each one
+ * cites the reference code whose work it replaces (paths relative to the reference
+ * root).  All pointers are plain host pointers unless the name says `dev`; the
+ * caller owns every buffer; every function returns 0 on success or an NXB_ERR_*
+ * code, with a message available from nxb_last_error().  A handle is bound to one
+ * CUDA device and is not re-entrant.  There is no CPU fallback: every call fails
+ * with NXB_ERR_CUDA if no device is usable.
+ */
+#ifndef NXBLINK_B200_H
+#define NXBLINK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nxb_handle nxb_handle;
+
+/* Integer-indexed model tables.
+ * Replaces the `model` duck type read by nxblink/raoteh.py:59-119
+ * (get_T_and_root, get_edge_to_blen, get_edge_to_rate, get_primary_to_tol,
+ * get_Q_primary, get_primary_distn, get_rate_on, get_rate_off).
+ * Nodes are numbered so that parent[v] < v and node 0 is the root; edge e is the
+ * edge into node e+1.  q_* is the primary rate matrix in CSR form ALREADY divided
+ * by its expected rate (raoteh.py:90-102). */
+typedef struct {
+    int32_t n_nodes;
+    int32_t n_states;        /* P <= 64 */
+    int32_t n_classes;       /* K <= 32 */
+    int32_t nnz;
+    const int32_t* parent;   /* [n_nodes], parent[0] = -1 */
+    const double* blen;      /* [n_nodes], branch length of the edge into v (blen[0] unused) */
+    const double* rate;      /* [n_nodes], rate scaling factor of the edge into v */
+    const int32_t* q_ptr;    /* [n_states + 1] */
+    const int32_t* q_col;    /* [nnz] */
+    const double* q_val;     /* [nnz] */
+    const int32_t* state_class; /* [n_states], tolerance class of each primary state */
+    const double* prior;     /* [n_states], root prior of the primary process */
+    double rate_on;          /* blink off -> on */
+    double rate_off;         /* blink on -> off */
+    int32_t diameter;        /* directed diameter of Q (raoteh.py:351) */
+    int32_t msg_f64;         /* 1: chunk messages stored as f64, 0: f32 */
+    double cap_scale;        /* scales every per-unit capacity; 0 or 1.0 = default */
+    int32_t validate;        /* 1: check trajectory invariants after every phase */
+    int32_t max_warps;       /* 0 = auto */
+} nxb_model_desc;
+
+/* Sizes of the flat statistic buffers (see nxb_summary_read). */
+typedef struct {
+    int32_t n_counts, n_dwell;
+    int32_t c_root_pri, c_root_on, c_root_off, c_root_on_cls, c_pri_trans,
+            c_off_on, c_on_off, c_nsamples;
+    int32_t d_T, d_off;
+} nxb_summary_layout;
+
+typedef struct {
+    int64_t n_units;
+    int64_t state_bytes_used;    /* sum over units of the live slab bytes */
+    int64_t n_pri_events;        /* retained primary events, all units */
+    int64_t n_blk_events;        /* retained blink events, all units */
+    int64_t data_bytes;          /* per-site constraint bytes held on the device */
+    int32_t warps_per_cta, n_ctas, smem_bytes, n_tiers;
+    int32_t capP, capB, capF, capC;
+    int64_t deferred_units;      /* units that needed a higher capacity tier so far */
+    int64_t kernel_launches;     /* sweep-kernel launches so far */
+} nxb_stats;
+
+int nxb_device_count(void);
+
+/* Build device tables for one model on `device`. */
+int nxb_create(const nxb_model_desc* desc, int device, nxb_handle** out);
+int nxb_destroy(nxb_handle* h);
+const char* nxb_last_error(const nxb_handle* h);   /* h may be NULL: last create error */
+
+/* Per-site data constraints; replaces the `data` duck type of raoteh.py:45-52,61
+ * after the zero-length pooling of raoteh.py:160-184 (done by the caller).
+ * pri_ok[s*N+v]: bit i set iff primary state i is allowed at node v.
+ * tol_true_ok / tol_false_ok: bit k set iff class k may be ON / OFF at node v.
+ * Host buffers; copied to the device. */
+int nxb_set_data(nxb_handle* h, int64_t n_sites, const uint64_t* pri_ok,
+                 const uint32_t* tol_true_ok, const uint32_t* tol_false_ok);
+
+/* Allocate `chains` independent chains per site and draw the initial feasible
+ * trajectories (raoteh.py:337-361 init_tracks).  `unit_offset` is the global index
+ * of this device's first unit: random streams are keyed by global unit index. */
+int nxb_init_chains(nxb_handle* h, int32_t chains, uint64_t seed, int64_t unit_offset);
+
+/* n_sweeps full Gibbs sweeps (raoteh.py:392-435) of every unit.  If `accumulate`
+ * the sufficient statistics of every sweep are added to the device summary
+ * (nxblink/summary.py:190-243 Summary.on_sample). */
+int nxb_sweep(nxb_handle* h, int32_t n_sweeps, int32_t accumulate);
+
+int nxb_summary_layout_get(const nxb_handle* h, nxb_summary_layout* out);
+int nxb_summary_reset(nxb_handle* h);
+/* Copies the statistics to host buffers: counts[n_counts] (u64), dwell[n_dwell] (f64). */
+int nxb_summary_read(nxb_handle* h, uint64_t* counts, double* dwell);
+/* Device pointers of the same two buffers, for an in-place NCCL all-reduce. */
+int nxb_summary_device_ptrs(nxb_handle* h, void** counts_dev, void** dwell_dev);
+/* Recompute the statistics of the CURRENT trajectories with an independent
+ * kernel (not fused with the sweep) and add them to the device summary. */
+int nxb_summarize_current(nxb_handle* h);
+
+/* Export one unit's trajectory (the tracks yielded by raoteh.py:435).
+ * node_pri[N], node_tol[N]; events: up to cap entries each, returns counts.
+ * Primary: time, edge, sa, sb.  Blink: time, edge, track, new state. */
+int nxb_export_unit(nxb_handle* h, int64_t unit, int32_t* node_pri, uint32_t* node_tol,
+                    int32_t cap, int32_t* n_pri, double* pri_time, int32_t* pri_edge,
+                    int32_t* pri_sa, int32_t* pri_sb,
+                    int32_t* n_blk, double* blk_time, int32_t* blk_edge,
+                    int32_t* blk_track, int32_t* blk_state);
+
+int nxb_get_stats(nxb_handle* h, nxb_stats* out);
+/* Last sweep-kernel launch times (ms, CUDA events on the launching stream). */
+int nxb_last_kernel_ms(nxb_handle* h, float* total_ms, int32_t* n_launches);
+
+/* Known-answer hook for the counter-based generator (host code path). */
+void nxb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,974 @@
+// C-ABI of the sweep engine (include/nxblink_b200.h) and the persistent kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/nxblink_b200.h"
+#include "sweep_kernel.cuh"
+
+#define NXB_MAX_THREADS 512
+
+namespace nxb {
+
+// ---------------------------------------------------------------------------
+// persistent sweep kernel: one CTA per SM, one warp per unit
+// ---------------------------------------------------------------------------
+template <typename MSG>
+__global__ void __launch_bounds__(NXB_MAX_THREADS, 1)
+sweep_kernel(const __grid_constant__ NxbSweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const NxbModelLayout& ml = p.ml;
+    const NxbWarpLayout& wl = p.wl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid * 16; i < ml.bytes; i += blockDim.x * 16)
+        *(uint4*)(smem + i) = *(const uint4*)(p.blob + i);
+    unsigned long long* stats = (unsigned long long*)(smem + ml.off_stats);
+    for (int i = tid; i < ml.stats_words; i += blockDim.x) stats[i] = 0ull;
+    __syncthreads();
+
+    Ctx c;
+    c.p = &p;
+    c.N = ml.N; c.E = ml.E; c.P = ml.P; c.K = ml.K; c.lane = lane;
+    c.parent = (const int*)(smem + ml.off_parent);
+    c.slot = (const int*)(smem + ml.off_slot);
+    c.tma = (const double*)(smem + ml.off_tma);
+    c.len = (const double*)(smem + ml.off_len);
+    c.rate = (const double*)(smem + ml.off_rate);
+    c.lam_pri = (const double*)(smem + ml.off_lam_pri);
+    c.p0_pri = (const double*)(smem + ml.off_p0_pri);
+    c.lam_blk = (const double*)(smem + ml.off_lam_blk);
+    c.p0_blk = (const double*)(smem + ml.off_p0_blk);
+    c.qval = (const double*)(smem + ml.off_qval);
+    c.qinfo = (const unsigned short*)(smem + ml.off_qinfo);
+    c.qptr = (const unsigned short*)(smem + ml.off_qptr);
+    c.cls = (const unsigned char*)(smem + ml.off_cls);
+    c.pi = (const double*)(smem + ml.off_pi);
+    c.qm = (const double*)(smem + ml.off_qm);
+    c.clsmask = (const unsigned long long*)(smem + ml.off_clsmask);
+    c.s_off_on = stats;
+    c.s_on_off = stats + ml.E;
+    c.s_root_pri = stats + 2 * ml.E;
+    c.s_root_misc = stats + 2 * ml.E + ml.P;
+    c.s_root_on_cls = stats + 2 * ml.E + ml.P + 4;
+    c.wbase = smem + p.smem_warp0 + (size_t)warp * wl.bytes;
+    c.node_tol = (unsigned*)(c.wbase + wl.off_node_tol);
+    c.node_pri = (unsigned char*)(c.wbase + wl.off_node_pri);
+    c.ptm = (double*)(c.wbase + wl.off_ptm);
+    c.pcode = (unsigned*)(c.wbase + wl.off_pcode);
+    c.btm = (double*)(c.wbase + wl.off_btm);
+    c.bcode = (unsigned*)(c.wbase + wl.off_bcode);
+    c.boff = (int*)(c.wbase + wl.off_boff);
+    c.poff = (int*)(c.wbase + wl.off_poff);
+    c.tmpa = (int*)(c.wbase + wl.off_tmpa);
+    c.tmpb = (int*)(c.wbase + wl.off_tmpb);
+    c.tmpc = (int*)(c.wbase + wl.off_tmpc);
+    unsigned long long* d_pri = (unsigned long long*)(c.wbase + wl.off_dpri);
+    unsigned* d_tt = (unsigned*)(c.wbase + wl.off_dtt);
+    unsigned* d_tf = (unsigned*)(c.wbase + wl.off_dtf);
+    c.pri_ok = d_pri; c.tt_ok = d_tt; c.tf_ok = d_tf;
+    c.k0 = (unsigned)(p.seed & 0xffffffffull);
+    c.k1 = (unsigned)(p.seed >> 32);
+    const int N = ml.N;
+    const long long n_work = p.unit_list ? (long long)p.n_list : p.n_units;
+
+    while (true) {
+        unsigned long long widx = 0;
+        if (lane == 0) widx = atomicAdd(p.work_counter, 1ull);
+        widx = __shfl_sync(FULL, widx, 0);
+        if ((long long)widx >= n_work) break;
+        const long long u = p.unit_list ? (long long)p.unit_list[widx] : (long long)widx;
+        c.unit = u;
+        c.unit32 = (unsigned)(p.unit_offset + u);
+        unsigned char* slab = p.state + u * p.state_stride;
+        NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;
+        if (p.init) { hdr.sweeps_done = 0; hdr.n_pri = 0; hdr.n_blk = 0; hdr.phase = NXB_PHASE_INIT; hdr.pad = 0; }
+        int rc = RC_OK;
+        if ((int)hdr.n_pri > wl.capP || (int)hdr.n_blk > wl.capB) {
+            // does not fit this tier's shared-memory arrays: untouched, next tier
+            if (lane == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)u;
+            continue;
+        }
+        // ---- load the unit (coalesced; only the live part of the slab is read) ----
+        {
+            const long long site = u / p.chains;
+            const unsigned long long* g_pri = p.pri_ok + site * N;
+            const unsigned* g_tt = p.tol_true_ok + site * N;
+            const unsigned* g_tf = p.tol_false_ok + site * N;
+            for (int v = lane; v < N; v += 32) { d_pri[v] = g_pri[v]; d_tt[v] = g_tt[v]; d_tf[v] = g_tf[v]; }
+            c.nP = hdr.n_pri; c.nB = hdr.n_blk;
+            if (hdr.phase != NXB_PHASE_INIT) {
+                const unsigned* g_tol = (const unsigned*)(slab + p.so_tol);
+                const unsigned* g_npri = (const unsigned*)(slab + p.so_pri);
+                for (int v = lane; v < N; v += 32) c.node_tol[v] = g_tol[v];
+                for (int v = lane; v < (N + 3) / 4; v += 32) ((unsigned*)c.node_pri)[v] = g_npri[v];
+                const double* g_ptm = (const double*)(slab + p.so_ptm);
+                const unsigned* g_pcode = (const unsigned*)(slab + p.so_pcode);
+                for (int i = lane; i < c.nP; i += 32) { c.ptm[i] = g_ptm[i]; c.pcode[i] = g_pcode[i]; }
+                const double* g_btm = (const double*)(slab + p.so_btm);
+                const unsigned* g_bcode = (const unsigned*)(slab + p.so_bcode);
+                for (int i = lane; i < c.nB; i += 32) { c.btm[i] = g_btm[i]; c.bcode[i] = g_bcode[i]; }
+            }
+            __syncwarp();
+        }
+        bool spilled = false;
+        while (rc == RC_OK && (hdr.phase == NXB_PHASE_INIT || hdr.sweeps_done < p.target_sweeps)) {
+            if (hdr.phase == NXB_PHASE_INIT) {
+                c.sweep = NXB_SWEEP_INIT;
+                rc = init_blink(c);
+                if (rc) break;
+                rc = primary_phase<MSG>(c, true, false);
+                if (rc) break;
+                hdr.phase = NXB_PHASE_PRIMARY;
+                if (p.validate) rc = validate_unit(c);
+                continue;
+            }
+            c.sweep = hdr.sweeps_done;
+            const bool accum = hdr.sweeps_done >= p.accum_from;
+            if (hdr.phase == NXB_PHASE_PRIMARY) {
+                rc = primary_phase<MSG>(c, false, accum);
+                if (rc) break;
+                hdr.phase = NXB_PHASE_BLINK;
+                if (p.validate) { rc = validate_unit(c); if (rc) break; }
+            }
+            rc = blink_phase(c, accum);
+            if (rc == RC_DEFER && c.nB < 0) {     // sweep complete, blink list spilled to HBM
+                hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
+                spilled = true;
+                break;
+            }
+            if (rc) break;
+            hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
+            if (p.validate) rc = validate_unit(c);
+        }
+        if (rc == RC_ERROR) continue;
+        if (c.nP > p.gcapP || (!spilled && c.nB > p.gcapB)) {
+            fail(c, NXB_ERR_STATE_CAP, c.nP > p.gcapP ? c.nP : c.nB);
+            continue;
+        }
+        // ---- store the unit ----
+        {
+            __syncwarp();
+            hdr.n_pri = (uint16_t)c.nP;
+            hdr.n_blk = (uint16_t)(spilled ? -c.nB : c.nB);
+            if (lane == 0) *(NxbUnitHeader*)slab = hdr;
+            if (hdr.phase != NXB_PHASE_INIT) {
+                unsigned* g_tol = (unsigned*)(slab + p.so_tol);
+                unsigned* g_npri = (unsigned*)(slab + p.so_pri);
+                for (int v = lane; v < N; v += 32) g_tol[v] = c.node_tol[v];
+                for (int v = lane; v < (N + 3) / 4; v += 32) g_npri[v] = ((unsigned*)c.node_pri)[v];
+                double* g_ptm = (double*)(slab + p.so_ptm);
+                unsigned* g_pcode = (unsigned*)(slab + p.so_pcode);
+                for (int i = lane; i < c.nP; i += 32) { g_ptm[i] = c.ptm[i]; g_pcode[i] = c.pcode[i]; }
+                if (!spilled) {
+                    double* g_btm = (double*)(slab + p.so_btm);
+                    unsigned* g_bcode = (unsigned*)(slab + p.so_bcode);
+                    for (int i = lane; i < c.nB; i += 32) { g_btm[i] = c.btm[i]; g_bcode[i] = c.bcode[i]; }
+                }
+            }
+            if (rc == RC_DEFER && lane == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)u;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- flush the CTA's statistic partials ----
+    const NxbSummaryLayout& sl = p.sl;
+    for (int i = tid; i < ml.E; i += blockDim.x) {
+        if (stats[i]) atomicAdd(p.counts + sl.c_off_on + i, stats[i]);
+        if (stats[ml.E + i]) atomicAdd(p.counts + sl.c_on_off + i, stats[ml.E + i]);
+    }
+    for (int i = tid; i < ml.P; i += blockDim.x)
+        if (c.s_root_pri[i]) atomicAdd(p.counts + sl.c_root_pri + i, c.s_root_pri[i]);
+    for (int i = tid; i < ml.K; i += blockDim.x)
+        if (c.s_root_on_cls[i]) atomicAdd(p.counts + sl.c_root_on_cls + i, c.s_root_on_cls[i]);
+    if (tid == 0) {
+        if (c.s_root_misc[0]) atomicAdd(p.counts + sl.c_root_on, c.s_root_misc[0]);
+        if (c.s_root_misc[1]) atomicAdd(p.counts + sl.c_root_off, c.s_root_misc[1]);
+        if (c.s_root_misc[2]) atomicAdd(p.counts + sl.c_nsamples, c.s_root_misc[2]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// independent (non-fused) statistics of the stored trajectories: one warp per unit,
+// lanes over edges, straight from the HBM slabs.  Restates summary.py:190-243 directly
+// (segment by segment, as navigation.py:14-46 gen_segments) and is used to cross-check
+// the statistics fused into the sweep.
+// ---------------------------------------------------------------------------
+__global__ void summarize_kernel(const __grid_constant__ NxbSweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const NxbModelLayout& ml = p.ml;
+    for (int i = threadIdx.x * 16; i < ml.bytes; i += blockDim.x * 16)
+        *(uint4*)(smem + i) = *(const uint4*)(p.blob + i);
+    __syncthreads();
+    const int* parent = (const int*)(smem + ml.off_parent);
+    const double* tma = (const double*)(smem + ml.off_tma);
+    const double* len = (const double*)(smem + ml.off_len);
+    const unsigned short* qinfo = (const unsigned short*)(smem + ml.off_qinfo);
+    const unsigned short* qptr = (const unsigned short*)(smem + ml.off_qptr);
+    const unsigned char* cls = (const unsigned char*)(smem + ml.off_cls);
+    const NxbSummaryLayout& sl = p.sl;
+    const int lane = threadIdx.x & 31;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int E = ml.E, P = ml.P, K = ml.K;
+    for (long long u = wid; u < p.n_units; u += nw) {
+        const unsigned char* slab = p.state + u * p.state_stride;
+        const NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;
+        const unsigned* g_tol = (const unsigned*)(slab + p.so_tol);
+        const unsigned char* g_npri = (const unsigned char*)(slab + p.so_pri);
+        const double* g_ptm = (const double*)(slab + p.so_ptm);
+        const unsigned* g_pcode = (const unsigned*)(slab + p.so_pcode);
+        const double* g_btm = (const double*)(slab + p.so_btm);
+        const unsigned* g_bcode = (const unsigned*)(slab + p.so_bcode);
+        if (lane == 0) {
+            int s0 = g_npri[0];
+            int on = __popc(g_tol[0]);
+            atomicAdd(p.counts + sl.c_root_pri + s0, 1ull);
+            atomicAdd(p.counts + sl.c_root_on, (unsigned long long)on);
+            atomicAdd(p.counts + sl.c_root_off, (unsigned long long)(K - on));
+            atomicAdd(p.counts + sl.c_root_on_cls + cls[s0], (unsigned long long)on);
+            atomicAdd(p.counts + sl.c_nsamples, 1ull);
+        }
+        for (int e = lane; e < E; e += 32) {
+            int s = g_npri[parent[e]];
+            unsigned mask = g_tol[parent[e]];
+            double t = tma[e];
+            const double tend = tma[e] + len[e];
+            while (true) {
+                // next event on this edge strictly after t
+                double best = NXB_INF; int which = -1; bool is_pri = false;
+                for (int i = 0; i < hdr.n_pri; ++i)
+                    if ((int)(g_pcode[i] & 0xffffu) == e && g_ptm[i] > t && g_ptm[i] < best) {
+                        best = g_ptm[i]; which = i; is_pri = true;
+                    }
+                for (int i = 0; i < hdr.n_blk; ++i)
+                    if ((int)(g_bcode[i] & 0xffffu) == e && g_btm[i] > t && g_btm[i] < best) {
+                        best = g_btm[i]; which = i; is_pri = false;
+                    }
+                double tn = (which < 0) ? tend : best;
+                double dt = tn - t;
+                atomicAdd(p.dwell + sl.d_T + e * P + s, dt);
+                for (int k = 0; k < K; ++k)
+                    if (!((mask >> k) & 1u))
+                        atomicAdd(p.dwell + sl.d_off + ((long long)e * P + s) * K + k, dt);
+                if (which < 0) break;
+                if (is_pri) {
+                    int sb = (g_pcode[which] >> 24) & 0xffu;
+                    int idx = qptr[s];
+                    while ((qinfo[idx] & 0xffu) != (unsigned)sb) ++idx;
+                    atomicAdd(p.counts + sl.c_pri_trans + (long long)e * ml.nnz + idx, 1ull);
+                    s = sb;
+                } else {
+                    unsigned code = g_bcode[which];
+                    if (code >> 31) atomicAdd(p.counts + sl.c_off_on + e, 1ull);
+                    else atomicAdd(p.counts + sl.c_on_off + e, 1ull);
+                    mask ^= 1u << ((code >> 16) & 0xffu);
+                }
+                t = tn;
+            }
+        }
+    }
+}
+
+// rmax_tab[mask] = max_s sum_{b: class(b) in mask} q[s][b]
+__global__ void rmax_table_kernel(double* tab, unsigned n_masks, int P, const int* q_ptr,
+                                  const int* q_cls, const double* q_val) {
+    unsigned m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_masks) return;
+    double best = 0.0;
+    for (int s = 0; s < P; ++s) {
+        double acc = 0.0;
+        for (int i = q_ptr[s]; i < q_ptr[s + 1]; ++i)
+            if ((m >> q_cls[i]) & 1u) acc += q_val[i];
+        best = fmax(best, acc);
+    }
+    tab[m] = best;
+}
+
+__global__ void unit_stats_kernel(const unsigned char* state, long long stride, long long n,
+                                  unsigned long long* out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long a = 0, b = 0;
+    if (i < n) {
+        const NxbUnitHeader* h = (const NxbUnitHeader*)(state + i * stride);
+        a = h->n_pri; b = h->n_blk;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(FULL, a, o);
+        b += __shfl_xor_sync(FULL, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); }
+}
+
+}  // namespace nxb
+
+// ===========================================================================
+// host side
+// ===========================================================================
+using namespace nxb;
+
+struct Tier {
+    NxbWarpLayout wl;
+    int warps;
+    int smem_warp0;
+    size_t smem;
+};
+
+struct nxb_handle {
+    int device = 0;
+    int num_sms = 0;
+    int max_smem = 0;
+    bool msg_f64 = false;
+    int validate = 0;
+    NxbModelLayout ml;
+    NxbSummaryLayout sl;
+    std::vector<Tier> tiers;
+    int gcapP = 0, gcapB = 0;
+    int so_tol = 0, so_pri = 0, so_ptm = 0, so_pcode = 0, so_btm = 0, so_bcode = 0;
+    long long stride = 0;
+    unsigned char* d_blob = nullptr;
+    double* d_rmax = nullptr;
+    unsigned long long* d_pri_ok = nullptr;
+    unsigned* d_tt = nullptr;
+    unsigned* d_tf = nullptr;
+    long long n_sites = 0;
+    unsigned char* d_state = nullptr;
+    long long n_units = 0;
+    int chains = 0;
+    long long unit_offset = 0;
+    unsigned long long seed = 0;
+    unsigned sweeps = 0;
+    unsigned long long* d_counts = nullptr;
+    double* d_dwell = nullptr;
+    int* d_status = nullptr;
+    unsigned long long* d_work = nullptr;
+    int* d_defer[2] = {nullptr, nullptr};
+    int* d_defer_count = nullptr;
+    unsigned long long* d_scratch = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    int last_launches = 0;
+    long long deferred_total = 0, launches_total = 0;
+    std::string err;
+};
+
+static std::string g_create_err;
+
+static int set_err(nxb_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, call)                                                        \
+    do {                                                                         \
+        cudaError_t e_ = (call);                                                 \
+        if (e_ != cudaSuccess)                                                   \
+            return set_err(h, NXB_ERR_CUDA, std::string(#call) + ": " +          \
+                                                cudaGetErrorString(e_));         \
+    } while (0)
+
+static int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, int capB,
+                              int capR, int capF, int capC, NxbWarpLayout* wl) {
+    const int N = ml.N, E = ml.E, K = ml.K;
+    int o = 0;
+    auto take = [&](int bytes, int al) { o = align_up(o, al); int r = o; o += bytes; return r; };
+    wl->capP = capP; wl->capB = capB; wl->capR = capR; wl->capF = capF; wl->capC = capC;
+    wl->off_node_tol = take(4 * N, 4);
+    wl->off_node_pri = take(align_up(N, 4), 4);
+    wl->off_ptm = take(8 * capP, 8);
+    wl->off_pcode = take(4 * capP, 4);
+    wl->off_btm = take(8 * capB, 8);
+    wl->off_bcode = take(4 * capB, 4);
+    wl->off_dpri = take(8 * N, 8);
+    wl->off_dtt = take(4 * N, 4);
+    wl->off_dtf = take(4 * N, 4);
+    wl->off_boff = take(4 * (E + 1), 4);
+    wl->off_poff = take(4 * (E + 1), 4);
+    wl->off_tmpa = take(4 * (E + 1), 4);
+    wl->off_tmpb = take(4 * (E + 1), 4);
+    wl->off_tmpc = take(4 * (E + 1), 4);
+    const int scratch0 = align_up(o, 16);
+    // primary-phase scratch
+    o = scratch0;
+    wl->off_bord = take(2 * capB, 2);
+    wl->off_rtm = take(8 * capR, 8);
+    wl->off_rmask = take(4 * capR, 4);
+    wl->off_ftm = take(8 * capF, 8);
+    wl->off_fmask = take(4 * capF, 4);
+    wl->off_fedge = take(2 * capF, 2);
+    wl->off_nchunk = take(4 * N, 4);
+    wl->off_jump = take(4 * N, 4);
+    wl->off_par = take(2 * (capF + 1), 2);
+    wl->off_toland = take(4 * (capF + 1), 4);
+    wl->off_callow = take(8 * (capF + 1), 8);
+    wl->off_cstate = take(capF + 1, 1);
+    wl->off_msg = take((msg_f64 ? 8 : 4) * (capF + 1) * NXB_PPAD, 16);
+    const int end_pri = o;
+    // blink-phase scratch (aliases the primary-phase scratch)
+    o = scratch0;
+    wl->off_ctm = take(8 * capC, 8);
+    wl->off_cell = take(4 * capC, 4);
+    wl->off_cedge = take(2 * capC, 2);
+    wl->off_cflag = take(capC, 1);
+    wl->off_toff = take(4 * (K + 1), 4);
+    wl->off_acc = take(8 * 3 * K * ml.nslots, 8);
+    wl->off_newtol = take(4 * N, 4);
+    // validate_unit needs bord while the persistent state is live; it is only called
+    // between phases, when either scratch is dead.
+    const int end_blk = o;
+    wl->bytes = align_up(std::max(end_pri, end_blk), 16);
+}
+
+extern "C" int nxb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" const char* nxb_last_error(const nxb_handle* h) {
+    return h ? h->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" void nxb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    NxbU4 r = nxb_philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out) {
+    if (!d || !out) return set_err(nullptr, NXB_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    const int N = d->n_nodes, P = d->n_states, K = d->n_classes, nnz = d->nnz, E = N - 1;
+    if (N < 2 || N > 65535) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 2 <= n_nodes <= 65535");
+    if (P < 1 || P > NXB_MAX_STATES) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 1 <= n_states <= 64");
+    if (K < 1 || K > NXB_MAX_CLASSES) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 1 <= n_classes <= 32");
+    if (!(d->rate_on > 0.0) || !(d->rate_off > 0.0))
+        return set_err(nullptr, NXB_ERR_BAD_ARG, "blink rates must be positive");
+    if (d->parent[0] != -1) return set_err(nullptr, NXB_ERR_BAD_ARG, "parent[0] must be -1 (root)");
+    for (int v = 1; v < N; ++v)
+        if (d->parent[v] < 0 || d->parent[v] >= v)
+            return set_err(nullptr, NXB_ERR_BAD_ARG, "nodes must be numbered so that parent[v] < v");
+    for (int v = 1; v < N; ++v)
+        if (!(d->blen[v] >= 0.0) || !(d->rate[v] >= 0.0))
+            return set_err(nullptr, NXB_ERR_BAD_ARG, "branch lengths and rates must be >= 0");
+    if (d->q_ptr[0] != 0 || d->q_ptr[P] != nnz) return set_err(nullptr, NXB_ERR_BAD_ARG, "bad q_ptr");
+    for (int s = 0; s < P; ++s) {
+        if (d->state_class[s] < 0 || d->state_class[s] >= K)
+            return set_err(nullptr, NXB_ERR_BAD_ARG, "state_class out of range");
+        if (d->q_ptr[s + 1] - d->q_ptr[s] > 63)
+            return set_err(nullptr, NXB_ERR_BAD_ARG, "at most 63 transitions per primary state");
+        for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i) {
+            if (d->q_col[i] < 0 || d->q_col[i] >= P || d->q_col[i] == s || !(d->q_val[i] > 0.0))
+                return set_err(nullptr, NXB_ERR_BAD_ARG, "bad primary rate matrix entry");
+        }
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return set_err(nullptr, NXB_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err(nullptr, NXB_ERR_BAD_ARG, "bad device index");
+
+    nxb_handle* h = new nxb_handle();
+    h->device = device;
+    h->msg_f64 = d->msg_f64 != 0;
+    h->validate = d->validate;
+#define CUDA_TRY_C(call)                                                                  \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            set_err(nullptr, NXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+            delete h;                                                                     \
+            return NXB_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+    CUDA_TRY_C(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY_C(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    CUDA_TRY_C(cudaStreamCreate(&h->stream));
+    CUDA_TRY_C(cudaEventCreate(&h->ev0));
+    CUDA_TRY_C(cudaEventCreate(&h->ev1));
+
+    // ---- derived model quantities ----
+    NxbModelLayout& ml = h->ml;
+    memset(&ml, 0, sizeof(ml));
+    ml.N = N; ml.E = E; ml.P = P; ml.K = K; ml.nnz = nnz; ml.diameter = d->diameter;
+    ml.rate_on = d->rate_on; ml.rate_off = d->rate_off;
+    std::vector<double> tm(N, 0.0);
+    for (int v = 1; v < N; ++v) tm[v] = tm[d->parent[v]] + d->blen[v];
+    // accumulator slots for the upward blink pass (edges in descending index)
+    std::vector<int> slot(N, -1);
+    {
+        std::vector<int> free_slots;
+        int next = 0;
+        for (int e = E - 1; e >= 0; --e) {
+            int vb = e + 1, va = d->parent[vb];
+            if (slot[va] < 0) {
+                if (!free_slots.empty()) {
+                    auto it = std::min_element(free_slots.begin(), free_slots.end());
+                    slot[va] = *it; free_slots.erase(it);
+                } else slot[va] = next++;
+            }
+            if (slot[vb] >= 0) free_slots.push_back(slot[vb]);
+        }
+        ml.nslots = std::max(next, 1);
+        if (ml.nslots > 32) {
+            set_err(nullptr, NXB_ERR_BAD_ARG, "tree needs more than 32 live accumulators; renumber nodes depth-first");
+            delete h; return NXB_ERR_BAD_ARG;
+        }
+    }
+    // rates: total out-rate per state with every class on, and its maximum
+    double rmax_all = 0.0;
+    for (int s = 0; s < P; ++s) {
+        double acc = 0.0;
+        for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i) acc += d->q_val[i];
+        rmax_all = std::max(rmax_all, acc);
+    }
+    if (!(rmax_all > 0.0)) { set_err(nullptr, NXB_ERR_BAD_ARG, "empty rate matrix"); delete h; return NXB_ERR_BAD_ARG; }
+    ml.inv_omega_pri = 1.0 / (2.0 * rmax_all);
+    const double M = std::max(d->rate_on, d->rate_off);
+    ml.a_on = d->rate_on / (2.0 * M);
+    ml.a_off = d->rate_off / (2.0 * M);
+    ml.acc_blk[0] = (2.0 * M - d->rate_on) / (2.0 * M);   // other class, track OFF
+    ml.acc_blk[1] = (2.0 * M - d->rate_off) / (2.0 * M);  // other class, track ON
+    ml.acc_blk[2] = d->rate_on / (2.0 * M);               // own class, OFF (infeasible state)
+    ml.acc_blk[3] = d->rate_on / M;                       // own class, ON
+    ml.p_on = d->rate_on / (d->rate_on + d->rate_off);
+    ml.p_off = d->rate_off / (d->rate_on + d->rate_off);
+
+    // ---- model blob ----
+    std::vector<unsigned char> blob;
+    auto put = [&](const void* src, int bytes, int al) {
+        int o = align_up((int)blob.size(), al);
+        blob.resize(o + bytes);
+        memcpy(blob.data() + o, src, bytes);
+        return o;
+    };
+    double sum_rt = 0.0, lam_pri_sum = 0.0, lam_blk_sum = 0.0;
+    {
+        std::vector<int> parent(E);
+        std::vector<double> tma(E), len(E), rate(E), lam_pri(E), p0_pri(E), lam_blk(E), p0_blk(E);
+        for (int e = 0; e < E; ++e) {
+            parent[e] = d->parent[e + 1];
+            tma[e] = tm[parent[e]];
+            len[e] = d->blen[e + 1];
+            rate[e] = d->rate[e + 1];
+            lam_pri[e] = 2.0 * rmax_all * rate[e] * len[e];
+            lam_blk[e] = 2.0 * M * rate[e] * len[e];
+            p0_pri[e] = exp(-lam_pri[e]);
+            p0_blk[e] = exp(-lam_blk[e]);
+            sum_rt += rate[e] * len[e];
+            lam_pri_sum += lam_pri[e];
+            lam_blk_sum += lam_blk[e];
+            if (lam_pri[e] > 600.0 || lam_blk[e] > 600.0) {
+                set_err(nullptr, NXB_ERR_BAD_ARG, "edge rate * length too large for the tabulated Poisson inversion");
+                delete h; return NXB_ERR_BAD_ARG;
+            }
+        }
+        ml.off_parent = put(parent.data(), 4 * E, 4);
+        ml.off_slot = put(slot.data(), 4 * N, 4);
+        ml.off_tma = put(tma.data(), 8 * E, 8);
+        ml.off_len = put(len.data(), 8 * E, 8);
+        ml.off_rate = put(rate.data(), 8 * E, 8);
+        ml.off_lam_pri = put(lam_pri.data(), 8 * E, 8);
+        ml.off_p0_pri = put(p0_pri.data(), 8 * E, 8);
+        ml.off_lam_blk = put(lam_blk.data(), 8 * E, 8);
+        ml.off_p0_blk = put(p0_blk.data(), 8 * E, 8);
+        ml.off_qval = put(d->q_val, 8 * nnz, 8);
+        std::vector<unsigned short> qinfo(nnz), qptr(P + 1);
+        for (int i = 0; i < nnz; ++i)
+            qinfo[i] = (unsigned short)(d->q_col[i] | (d->state_class[d->q_col[i]] << 8));
+        for (int s = 0; s <= P; ++s) qptr[s] = (unsigned short)d->q_ptr[s];
+        ml.off_qinfo = put(qinfo.data(), 2 * nnz, 2);
+        ml.off_qptr = put(qptr.data(), 2 * (P + 1), 2);
+        std::vector<unsigned char> cls(P);
+        for (int s = 0; s < P; ++s) cls[s] = (unsigned char)d->state_class[s];
+        ml.off_cls = put(cls.data(), P, 1);
+        ml.off_pi = put(d->prior, 8 * P, 8);
+        std::vector<double> qm((size_t)P * K, 0.0);
+        for (int s = 0; s < P; ++s)
+            for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i)
+                qm[(size_t)s * K + d->state_class[d->q_col[i]]] += d->q_val[i];
+        ml.off_qm = put(qm.data(), 8 * P * K, 8);
+        std::vector<unsigned long long> clsmask(K, 0ull);
+        for (int s = 0; s < P; ++s) clsmask[d->state_class[s]] |= 1ull << s;
+        ml.off_clsmask = put(clsmask.data(), 8 * K, 8);
+        blob.resize(align_up((int)blob.size(), 16));
+        ml.bytes = (int)blob.size();
+        ml.off_stats = ml.bytes;
+        ml.stats_words = 2 * E + P + 4 + K;
+    }
+    CUDA_TRY_C(cudaMalloc(&h->d_blob, blob.size()));
+    CUDA_TRY_C(cudaMemcpy(h->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    {
+        double inv_n[64];
+        inv_n[0] = 0.0;
+        for (int i = 1; i < 64; ++i) inv_n[i] = 1.0 / (double)i;
+        CUDA_TRY_C(cudaMemcpyToSymbol(c_inv_n, inv_n, sizeof(inv_n)));
+    }
+    // ---- L2-resident table of uniformization rates, one entry per tolerance mask ----
+    ml.table_bits = 0;
+    if (K <= 22) {
+        ml.table_bits = K;
+        const unsigned n_masks = 1u << K;
+        int *dq_ptr, *dq_cls; double* dq_val;
+        std::vector<int> qcls(nnz);
+        for (int i = 0; i < nnz; ++i) qcls[i] = d->state_class[d->q_col[i]];
+        CUDA_TRY_C(cudaMalloc(&h->d_rmax, sizeof(double) * n_masks));
+        CUDA_TRY_C(cudaMalloc(&dq_ptr, 4 * (P + 1)));
+        CUDA_TRY_C(cudaMalloc(&dq_cls, 4 * std::max(nnz, 1)));
+        CUDA_TRY_C(cudaMalloc(&dq_val, 8 * std::max(nnz, 1)));
+        CUDA_TRY_C(cudaMemcpy(dq_ptr, d->q_ptr, 4 * (P + 1), cudaMemcpyHostToDevice));
+        CUDA_TRY_C(cudaMemcpy(dq_cls, qcls.data(), 4 * nnz, cudaMemcpyHostToDevice));
+        CUDA_TRY_C(cudaMemcpy(dq_val, d->q_val, 8 * nnz, cudaMemcpyHostToDevice));
+        rmax_table_kernel<<<(n_masks + 255) / 256, 256, 0, h->stream>>>(h->d_rmax, n_masks, P, dq_ptr, dq_cls, dq_val);
+        CUDA_TRY_C(cudaGetLastError());
+        CUDA_TRY_C(cudaStreamSynchronize(h->stream));
+        cudaFree(dq_ptr); cudaFree(dq_cls); cudaFree(dq_val);
+    }
+    // ---- statistics ----
+    {
+        NxbSummaryLayout& sl = h->sl;
+        int o = 0;
+        sl.c_root_pri = o; o += P;
+        sl.c_root_on = o; o += 1;
+        sl.c_root_off = o; o += 1;
+        sl.c_root_on_cls = o; o += K;
+        sl.c_pri_trans = o; o += E * nnz;
+        sl.c_off_on = o; o += E;
+        sl.c_on_off = o; o += E;
+        sl.c_nsamples = o; o += 1;
+        sl.n_counts = o;
+        o = 0;
+        sl.d_T = o; o += E * P;
+        sl.d_off = o; o += E * P * K;
+        sl.n_dwell = o;
+        CUDA_TRY_C(cudaMalloc(&h->d_counts, 8 * (size_t)sl.n_counts));
+        CUDA_TRY_C(cudaMalloc(&h->d_dwell, 8 * (size_t)sl.n_dwell));
+        CUDA_TRY_C(cudaMemset(h->d_counts, 0, 8 * (size_t)sl.n_counts));
+        CUDA_TRY_C(cudaMemset(h->d_dwell, 0, 8 * (size_t)sl.n_dwell));
+    }
+    CUDA_TRY_C(cudaMalloc(&h->d_status, 4 * sizeof(int)));
+    CUDA_TRY_C(cudaMemset(h->d_status, 0, 4 * sizeof(int)));
+    CUDA_TRY_C(cudaMalloc(&h->d_work, 8));
+    CUDA_TRY_C(cudaMalloc(&h->d_defer_count, 4));
+    CUDA_TRY_C(cudaMalloc(&h->d_scratch, 64));
+
+    // ---- capacity tiers ----
+    {
+        const double scale = (d->cap_scale > 0.0) ? d->cap_scale : 1.0;
+        const double on = d->rate_on, off = d->rate_off;
+        const double mean_blk = K * sum_rt * 2.0 * on * off / (on + off);
+        const double mean_pri = sum_rt;
+        const double cand_pri = lam_pri_sum, cand_blk = K * lam_blk_sum;
+        auto cap = [&](double mean, double nsig, double slack) {
+            return align_up((int)ceil(scale * (mean + nsig * sqrt(std::max(mean, 1.0)) + slack)), 8);
+        };
+        int capP = cap(mean_pri, 4.0, 8.0);
+        int capB = cap(mean_blk, 4.0, 2.0 * E < 32 ? 2.0 * E * K : 16.0);
+        // the initial trajectory holds up to two blink events per (track, active edge)
+        // for tracks that the data force off (raoteh.py:205-229)
+        int capF = cap(mean_pri + 0.75 * cand_pri + (double)d->diameter * 0, 4.0, 8.0);
+        int capR = cap(mean_pri + cand_pri, 4.0, 8.0) + capP;
+        int capC = cap(mean_blk + cand_blk, 4.0, 16.0);
+        h->gcapP = std::min(65535, align_up(4 * capP + 32, 8));
+        h->gcapB = std::min(65535, align_up(4 * capB + 64, 8));
+        const int stats_bytes = align_up(8 * ml.stats_words, 16);
+        const int fixed = ml.bytes + stats_bytes;
+        const int max_warps = (d->max_warps > 0) ? std::min(d->max_warps, NXB_MAX_THREADS / 32)
+                                                 : NXB_MAX_THREADS / 32;
+        for (int t = 0; t < 8; ++t) {
+            Tier tier;
+            const int f = 1 << t;
+            int init_f = std::max(capF * f, E * d->diameter + 8);   // init pass: diameter events per edge
+            int init_r = std::max(capR * f, E * d->diameter + 8);
+            build_warp_layout(ml, h->msg_f64, std::min(capP * f, h->gcapP), std::min(capB * f, h->gcapB),
+                              init_r, init_f, capC * f, &tier.wl);
+            tier.smem_warp0 = fixed;
+            int w = (h->max_smem - fixed) / tier.wl.bytes;
+            if (w < 1) break;
+            tier.warps = std::min(w, max_warps);
+            tier.smem = (size_t)fixed + (size_t)tier.warps * tier.wl.bytes;
+            h->tiers.push_back(tier);
+        }
+        if (h->tiers.empty()) {
+            set_err(nullptr, NXB_ERR_BAD_ARG, "model too large: one unit does not fit in shared memory");
+            nxb_destroy(h); return NXB_ERR_BAD_ARG;
+        }
+        // slab layout
+        int o = (int)sizeof(NxbUnitHeader);
+        h->so_tol = o; o += 4 * N;
+        h->so_pri = o; o += align_up(N, 4);
+        o = align_up(o, 8);
+        h->so_ptm = o; o += 8 * h->gcapP;
+        h->so_pcode = o; o += 4 * h->gcapP;
+        o = align_up(o, 8);
+        h->so_btm = o; o += 8 * h->gcapB;
+        h->so_bcode = o; o += 4 * h->gcapB;
+        h->stride = align_up(o, 16);
+    }
+    for (auto& t : h->tiers) {
+        cudaError_t e1 = h->msg_f64
+            ? cudaFuncSetAttribute(sweep_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
+            : cudaFuncSetAttribute(sweep_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+        (void)t;
+        if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }
+        break;
+    }
+    cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+    *out = h;
+    return NXB_OK;
+}
+
+extern "C" int nxb_destroy(nxb_handle* h) {
+    if (!h) return NXB_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_blob); cudaFree(h->d_rmax); cudaFree(h->d_pri_ok); cudaFree(h->d_tt); cudaFree(h->d_tf);
+    cudaFree(h->d_state); cudaFree(h->d_counts); cudaFree(h->d_dwell); cudaFree(h->d_status);
+    cudaFree(h->d_work); cudaFree(h->d_defer[0]); cudaFree(h->d_defer[1]); cudaFree(h->d_defer_count);
+    cudaFree(h->d_scratch);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return NXB_OK;
+}
+
+extern "C" int nxb_set_data(nxb_handle* h, int64_t n_sites, const uint64_t* pri_ok,
+                            const uint32_t* tt, const uint32_t* tf) {
+    if (!h || n_sites <= 0 || !pri_ok || !tt || !tf) return set_err(h, NXB_ERR_BAD_ARG, "bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)n_sites * h->ml.N;
+    if (n_sites != h->n_sites) {
+        cudaFree(h->d_pri_ok); cudaFree(h->d_tt); cudaFree(h->d_tf);
+        h->d_pri_ok = nullptr; h->d_tt = nullptr; h->d_tf = nullptr;
+        CUDA_TRY(h, cudaMalloc(&h->d_pri_ok, 8 * n));
+        CUDA_TRY(h, cudaMalloc(&h->d_tt, 4 * n));
+        CUDA_TRY(h, cudaMalloc(&h->d_tf, 4 * n));
+        h->n_sites = n_sites;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pri_ok, pri_ok, 8 * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_tt, tt, 4 * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_tf, tf, 4 * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NXB_OK;
+}
+
+static const char* status_text(int code) {
+    switch (code) {
+        case NXB_ERR_INFEASIBLE: return "infeasible data: the forward-filtering pass met an all-zero message";
+        case NXB_ERR_ZERO_RATE: return "zero max rate";
+        case NXB_ERR_STATE_CAP: return "a unit outgrew its HBM slab; re-create the handle with a larger cap_scale";
+        case NXB_ERR_INVARIANT: return "trajectory invariant violated";
+        case NXB_ERR_SCRATCH_CAP: return "scratch overflow at the largest shared-memory tier; increase cap_scale";
+        default: return "error";
+    }
+}
+
+// Run every unit up to `target` sweeps, escalating overflowing units through the tiers.
+static int run_tiers(nxb_handle* h, unsigned target, unsigned accum_from, int init) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int* list = nullptr;
+    int n_list = 0;
+    h->last_ms = 0.f; h->last_launches = 0;
+    for (size_t t = 0; t < h->tiers.size(); ++t) {
+        const Tier& tier = h->tiers[t];
+        NxbSweepParams p;
+        memset(&p, 0, sizeof(p));
+        p.ml = h->ml; p.wl = tier.wl; p.sl = h->sl;
+        p.smem_warp0 = tier.smem_warp0;
+        p.blob = h->d_blob; p.rmax_tab = h->d_rmax;
+        p.pri_ok = h->d_pri_ok; p.tol_true_ok = h->d_tt; p.tol_false_ok = h->d_tf;
+        p.state = h->d_state; p.state_stride = h->stride;
+        p.gcapP = h->gcapP; p.gcapB = h->gcapB;
+        p.so_tol = h->so_tol; p.so_pri = h->so_pri; p.so_ptm = h->so_ptm; p.so_pcode = h->so_pcode;
+        p.so_btm = h->so_btm; p.so_bcode = h->so_bcode;
+        p.n_units = h->n_units; p.unit_offset = h->unit_offset; p.chains = h->chains;
+        p.unit_list = list; p.n_list = n_list;
+        p.defer_list = h->d_defer[t & 1]; p.defer_count = h->d_defer_count;
+        p.seed = h->seed; p.target_sweeps = target; p.accum_from = accum_from;
+        p.init = (init && t == 0) ? 1 : 0;
+        p.validate = h->validate;
+        p.counts = h->d_counts; p.dwell = h->d_dwell; p.status = h->d_status;
+        p.work_counter = h->d_work;
+        CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
+        const long long n_work = list ? n_list : h->n_units;
+        int grid = (int)std::min<long long>(h->num_sms, (n_work + tier.warps - 1) / tier.warps);
+        grid = std::max(grid, 1);
+        CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        if (h->msg_f64) sweep_kernel<double><<<grid, tier.warps * 32, tier.smem, h->stream>>>(p);
+        else sweep_kernel<float><<<grid, tier.warps * 32, tier.smem, h->stream>>>(p);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        int hs[5];
+        CUDA_TRY(h, cudaMemcpyAsync(hs, h->d_status, 16, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(hs + 4, h->d_defer_count, 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        h->last_ms += ms; h->last_launches++; h->launches_total++;
+        if (hs[0] != 0) {
+            char buf[256];
+            snprintf(buf, sizeof(buf), "%s (code %d, unit %d, detail %d, sweep %d)", status_text(hs[0]),
+                     hs[0], hs[1], hs[2], hs[3]);
+            cudaMemsetAsync(h->d_status, 0, 16, h->stream);
+            return set_err(h, hs[0], buf);
+        }
+        if (hs[4] == 0) return NXB_OK;
+        h->deferred_total += hs[4];
+        list = h->d_defer[t & 1];
+        n_list = hs[4];
+    }
+    return set_err(h, NXB_ERR_SCRATCH_CAP, status_text(NXB_ERR_SCRATCH_CAP));
+}
+
+extern "C" int nxb_init_chains(nxb_handle* h, int32_t chains, uint64_t seed, int64_t unit_offset) {
+    if (!h || chains <= 0) return set_err(h, NXB_ERR_BAD_ARG, "bad argument");
+    if (!h->d_pri_ok) return set_err(h, NXB_ERR_BAD_ARG, "call nxb_set_data first");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const long long n_units = h->n_sites * chains;
+    if (n_units > 0x7fffffffLL) return set_err(h, NXB_ERR_BAD_ARG, "too many units for one device");
+    if (n_units != h->n_units) {
+        cudaFree(h->d_state); cudaFree(h->d_defer[0]); cudaFree(h->d_defer[1]);
+        h->d_state = nullptr; h->d_defer[0] = h->d_defer[1] = nullptr;
+        CUDA_TRY(h, cudaMalloc(&h->d_state, (size_t)n_units * h->stride));
+        CUDA_TRY(h, cudaMalloc(&h->d_defer[0], 4 * (size_t)n_units));
+        CUDA_TRY(h, cudaMalloc(&h->d_defer[1], 4 * (size_t)n_units));
+    }
+    h->n_units = n_units; h->chains = chains; h->seed = seed; h->unit_offset = unit_offset;
+    h->sweeps = 0;
+    return run_tiers(h, 0u, 0xffffffffu, 1);
+}
+
+extern "C" int nxb_sweep(nxb_handle* h, int32_t n_sweeps, int32_t accumulate) {
+    if (!h || n_sweeps < 0) return set_err(h, NXB_ERR_BAD_ARG, "bad argument");
+    if (!h->d_state) return set_err(h, NXB_ERR_BAD_ARG, "call nxb_init_chains first");
+    if (n_sweeps == 0) return NXB_OK;
+    const unsigned target = h->sweeps + (unsigned)n_sweeps;
+    int rc = run_tiers(h, target, accumulate ? h->sweeps : 0xffffffffu, 0);
+    if (rc == NXB_OK) h->sweeps = target;
+    return rc;
+}
+
+extern "C" int nxb_summary_layout_get(const nxb_handle* h, nxb_summary_layout* o) {
+    if (!h || !o) return NXB_ERR_BAD_ARG;
+    const NxbSummaryLayout& s = h->sl;
+    o->n_counts = s.n_counts; o->n_dwell = s.n_dwell;
+    o->c_root_pri = s.c_root_pri; o->c_root_on = s.c_root_on; o->c_root_off = s.c_root_off;
+    o->c_root_on_cls = s.c_root_on_cls; o->c_pri_trans = s.c_pri_trans; o->c_off_on = s.c_off_on;
+    o->c_on_off = s.c_on_off; o->c_nsamples = s.c_nsamples; o->d_T = s.d_T; o->d_off = s.d_off;
+    return NXB_OK;
+}
+
+extern "C" int nxb_summary_reset(nxb_handle* h) {
+    if (!h) return NXB_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counts, 0, 8 * (size_t)h->sl.n_counts, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_dwell, 0, 8 * (size_t)h->sl.n_dwell, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NXB_OK;
+}
+
+extern "C" int nxb_summary_read(nxb_handle* h, uint64_t* counts, double* dwell) {
+    if (!h || !counts || !dwell) return set_err(h, NXB_ERR_BAD_ARG, "bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(counts, h->d_counts, 8 * (size_t)h->sl.n_counts, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(dwell, h->d_dwell, 8 * (size_t)h->sl.n_dwell, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NXB_OK;
+}
+
+extern "C" int nxb_summary_device_ptrs(nxb_handle* h, void** c, void** d) {
+    if (!h || !c || !d) return NXB_ERR_BAD_ARG;
+    *c = h->d_counts; *d = h->d_dwell;
+    return NXB_OK;
+}
+
+extern "C" int nxb_summarize_current(nxb_handle* h) {
+    if (!h || !h->d_state) return set_err(h, NXB_ERR_BAD_ARG, "no chains");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    NxbSweepParams p;
+    memset(&p, 0, sizeof(p));
+    p.ml = h->ml; p.sl = h->sl; p.blob = h->d_blob;
+    p.state = h->d_state; p.state_stride = h->stride;
+    p.so_tol = h->so_tol; p.so_pri = h->so_pri; p.so_ptm = h->so_ptm; p.so_pcode = h->so_pcode;
+    p.so_btm = h->so_btm; p.so_bcode = h->so_bcode;
+    p.n_units = h->n_units; p.counts = h->d_counts; p.dwell = h->d_dwell;
+    const int threads = 128;
+    long long warps = h->n_units;
+    int grid = (int)std::min<long long>((warps * 32 + threads - 1) / threads, 148LL * 16);
+    summarize_kernel<<<grid, threads, h->ml.bytes, h->stream>>>(p);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NXB_OK;
+}
+
+extern "C" int nxb_export_unit(nxb_handle* h, int64_t unit, int32_t* node_pri, uint32_t* node_tol,
+                               int32_t cap, int32_t* n_pri, double* pt, int32_t* pe, int32_t* psa,
+                               int32_t* psb, int32_t* n_blk, double* bt, int32_t* be, int32_t* bk,
+                               int32_t* bs) {
+    if (!h || !h->d_state || unit < 0 || unit >= h->n_units) return set_err(h, NXB_ERR_BAD_ARG, "bad unit");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    std::vector<unsigned char> slab(h->stride);
+    CUDA_TRY(h, cudaMemcpy(slab.data(), h->d_state + unit * h->stride, h->stride, cudaMemcpyDeviceToHost));
+    const NxbUnitHeader* hdr = (const NxbUnitHeader*)slab.data();
+    const int N = h->ml.N;
+    const unsigned* tol = (const unsigned*)(slab.data() + h->so_tol);
+    const unsigned char* pri = slab.data() + h->so_pri;
+    for (int v = 0; v < N; ++v) { node_pri[v] = pri[v]; node_tol[v] = tol[v]; }
+    *n_pri = hdr->n_pri; *n_blk = hdr->n_blk;
+    if (hdr->n_pri > cap || hdr->n_blk > cap) return set_err(h, NXB_ERR_BAD_ARG, "export buffers too small");
+    const double* g_ptm = (const double*)(slab.data() + h->so_ptm);
+    const unsigned* g_pcode = (const unsigned*)(slab.data() + h->so_pcode);
+    for (int i = 0; i < hdr->n_pri; ++i) {
+        pt[i] = g_ptm[i]; pe[i] = g_pcode[i] & 0xffffu;
+        psa[i] = (g_pcode[i] >> 16) & 0xffu; psb[i] = (g_pcode[i] >> 24) & 0xffu;
+    }
+    const double* g_btm = (const double*)(slab.data() + h->so_btm);
+    const unsigned* g_bcode = (const unsigned*)(slab.data() + h->so_bcode);
+    for (int i = 0; i < hdr->n_blk; ++i) {
+        bt[i] = g_btm[i]; be[i] = g_bcode[i] & 0xffffu;
+        bk[i] = (g_bcode[i] >> 16) & 0xffu; bs[i] = g_bcode[i] >> 31;
+    }
+    return NXB_OK;
+}
+
+extern "C" int nxb_get_stats(nxb_handle* h, nxb_stats* o) {
+    if (!h || !o) return NXB_ERR_BAD_ARG;
+    memset(o, 0, sizeof(*o));
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    o->n_units = h->n_units;
+    if (h->d_state && h->n_units > 0) {
+        CUDA_TRY(h, cudaMemsetAsync(h->d_scratch, 0, 16, h->stream));
+        unit_stats_kernel<<<(unsigned)((h->n_units + 255) / 256), 256, 0, h->stream>>>(
+            h->d_state, h->stride, h->n_units, h->d_scratch);
+        unsigned long long r[2];
+        CUDA_TRY(h, cudaMemcpyAsync(r, h->d_scratch, 16, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        o->n_pri_events = (int64_t)r[0]; o->n_blk_events = (int64_t)r[1];
+        const int N = h->ml.N;
+        o->state_bytes_used = h->n_units * (int64_t)(sizeof(NxbUnitHeader) + 4 * N + N) + 12 * (int64_t)(r[0] + r[1]);
+    }
+    o->data_bytes = h->n_sites * (int64_t)h->ml.N * 16;
+    const Tier& t0 = h->tiers[0];
+    o->warps_per_cta = t0.warps; o->n_ctas = h->num_sms; o->smem_bytes = (int32_t)t0.smem;
+    o->n_tiers = (int32_t)h->tiers.size();
+    o->capP = t0.wl.capP; o->capB = t0.wl.capB; o->capF = t0.wl.capF; o->capC = t0.wl.capC;
+    o->deferred_units = h->deferred_total; o->kernel_launches = h->launches_total;
+    return NXB_OK;
+}
+
+extern "C" int nxb_last_kernel_ms(nxb_handle* h, float* ms, int32_t* n) {
+    if (!h) return NXB_ERR_BAD_ARG;
+    if (ms) *ms = h->last_ms;
+    if (n) *n = h->last_launches;
+    return NXB_OK;
+}

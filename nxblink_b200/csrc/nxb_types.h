@@ -1,0 +1,138 @@
+// Shared host/device types for the nxblink_b200 sweep engine.
+//
+// Vocabulary follows the reference (nxblink): a *unit* is one (site, chain);
+// a *track* is the primary process or one tolerance ("blink") process; an
+// *event* is a point on a tree edge where a track changes state; a *chunk* is
+// a maximal region of the tree on which the foreground track cannot change
+// (nxblink/chunking.py:1-12).
+#pragma once
+#include <stdint.h>
+
+#define NXB_MAX_STATES 64    // primary states P  (bitmask in one u64)
+#define NXB_MAX_CLASSES 32   // tolerance classes K (bitmask in one u32; one lane per track)
+#define NXB_PPAD 64          // padded row length of a chunk message
+
+// unit status codes written to the per-handle status word
+enum {
+    NXB_OK = 0,
+    NXB_ERR_INFEASIBLE = 1,      // FFBS met an all-zero message (raoteh.py:178-180,201)
+    NXB_ERR_ZERO_RATE = 2,       // util.py:15-16 'zero max rate'
+    NXB_ERR_STATE_CAP = 3,       // unit no longer fits its HBM slab
+    NXB_ERR_INVARIANT = 4,       // navigation.py:40,122-142 style consistency check
+    NXB_ERR_BAD_ARG = 5,
+    NXB_ERR_CUDA = 6,
+    NXB_ERR_SCRATCH_CAP = 7,     // scratch overflow even at the largest shared-memory tier
+};
+
+// where a deferred unit resumes (see DESIGN.md "capacity tiers")
+enum { NXB_PHASE_PRIMARY = 0, NXB_PHASE_BLINK = 1, NXB_PHASE_INIT = 2 };
+
+// Per-unit slab header in HBM (16 bytes).
+struct NxbUnitHeader {
+    uint32_t sweeps_done;   // absolute number of completed sweeps
+    uint16_t n_pri;         // retained primary events
+    uint16_t n_blk;         // retained blink events
+    uint32_t phase;         // NXB_PHASE_*: PRIMARY = at a sweep boundary
+    uint32_t pad;
+};
+
+// Offsets (bytes) of the model tables inside the model blob that every CTA
+// stages into shared memory once.
+struct NxbModelLayout {
+    int N, E, P, K, nnz, nslots, diameter, table_bits;
+    int off_stats;      // CTA-level statistic partials (u64), zeroed per launch
+    int stats_words;
+    int off_parent;     // int32  [E]   parent node of node e+1
+    int off_slot;       // int32  [N]   accumulator slot of internal nodes, -1 for leaves
+    int off_tma;        // f64    [E]   time at the rootward end of edge e
+    int off_len;        // f64    [E]   branch length (time units)
+    int off_rate;       // f64    [E]   edge rate scaling factor
+    int off_lam_pri;    // f64    [E]   dominating Poisson mean, primary track
+    int off_p0_pri;     // f64    [E]   exp(-lam_pri)
+    int off_lam_blk;    // f64    [E]   dominating Poisson mean, one blink track
+    int off_p0_blk;     // f64    [E]   exp(-lam_blk)
+    int off_qval;       // f64    [nnz] normalised primary rates (CSR values)
+    int off_qinfo;      // u16    [nnz] column | class(column) << 8
+    int off_qptr;       // u16    [P+1]
+    int off_cls;        // u8     [P]
+    int off_pi;         // f64    [P]
+    int off_qm;         // f64    [P*K] dense Q_meta (model.py:93-106)
+    int off_clsmask;    // u64    [K]   states belonging to class k
+    int bytes;
+    double rate_on, rate_off;
+    double inv_omega_pri;   // 1 / (2 * Rmax(all classes on))
+    double acc_blk[4];      // thinning acceptance [own][fg state]
+    double a_on, a_off;     // off-diagonal entries of the uniformized 2x2 blink matrix
+    double p_on, p_off;     // blink prior at the root
+};
+
+// Per-warp shared-memory layout (bytes from the warp's base), chosen by the host
+// for a capacity tier.
+struct NxbWarpLayout {
+    int capP, capB;         // retained primary / blink events held in shared memory
+    int capR, capF;         // primary phase: pre-thinning region, foreground events
+    int capC;               // blink phase: candidate pool
+    // persistent
+    int off_node_tol, off_node_pri, off_ptm, off_pcode, off_btm, off_bcode;
+    int off_dpri, off_dtt, off_dtf;   // this unit's site constraints
+    // small index arrays (live in both phases)
+    int off_boff, off_poff, off_tmpa, off_tmpb, off_tmpc;
+    // primary-phase scratch
+    int off_bord, off_rtm, off_rmask, off_ftm, off_fmask, off_fedge,
+        off_nchunk, off_jump, off_par, off_toland, off_callow, off_cstate, off_msg;
+    // blink-phase scratch
+    int off_ctm, off_cell, off_cedge, off_cflag, off_toff, off_acc, off_newtol;
+    int bytes;
+};
+
+struct NxbSummaryLayout {
+    // counts (u64)
+    int c_root_pri;     // [P]
+    int c_root_on;      // [1] total ON tolerance tracks at the root
+    int c_root_off;     // [1]
+    int c_root_on_cls;  // [K] ON tracks at the root, summed over samples whose root state is in class k
+    int c_pri_trans;    // [E*nnz]
+    int c_off_on;       // [E] off->on blink transitions
+    int c_on_off;       // [E]
+    int c_nsamples;     // [1]
+    int n_counts;
+    // dwell (f64)
+    int d_T;            // [E*P]   time on edge e in primary state s
+    int d_off;          // [E*P*K] time on edge e in state s with class k OFF
+    int n_dwell;
+};
+
+struct NxbSweepParams {
+    NxbModelLayout ml;
+    NxbWarpLayout wl;
+    NxbSummaryLayout sl;
+    int smem_warp0;                     // byte offset of warp 0's region in shared memory
+    const unsigned char* blob;          // model blob (global)
+    const double* rmax_tab;             // [2^K] max_s sum_{c in mask} Qmeta[s][c]
+    // per-site data constraints
+    const unsigned long long* pri_ok;   // [S][N] allowed primary states
+    const unsigned* tol_true_ok;        // [S][N] bit k: class k may be ON
+    const unsigned* tol_false_ok;       // [S][N] bit k: class k may be OFF
+    // unit slabs
+    unsigned char* state;
+    long long state_stride;
+    int gcapP, gcapB;                   // slab capacities
+    int so_tol, so_pri, so_ptm, so_pcode, so_btm, so_bcode;   // byte offsets inside a slab
+    long long n_units;                  // units on this device
+    long long unit_offset;              // global id of local unit 0 (RNG key)
+    int chains;                         // chains per site
+    const int* unit_list;               // optional: deferred units to process
+    int n_list;
+    int* defer_list;                    // out: units that overflowed this tier
+    int* defer_count;
+    unsigned long long seed;
+    unsigned target_sweeps;             // run every unit up to this absolute sweep count
+    unsigned accum_from;                // accumulate statistics for sweeps >= this
+    int init;                           // 1: initialise trajectories (raoteh.py:337-361)
+    int validate;                       // 1: check trajectory invariants after every phase
+    unsigned long long* counts;
+    double* dwell;
+    int* status;                        // [4]: code, unit, detail, detail
+    unsigned long long* work_counter;
+    unsigned long long* perf;           // [8] optional counters (events, candidates, bytes)
+};

@@ -1,0 +1,961 @@
+// The Rao-Teh uniformization Gibbs sweep of the blink model, one warp per unit.
+//
+// Replaces, for a batch of independent (site, chain) units, the body of
+// nxblink/raoteh.py:392-435 (_gen_samples) and everything it calls:
+//   nxblink/poisson.py:53-131        candidate ("Poisson") events
+//   nxblink/navigation.py:49-148     background-constant context segments
+//   nxblink/chunking.py:39-261       chunk trees
+//   nxblink/chunking.py:264-289      resample_using_chunk_tree -> sample_history (FFBS)
+//   nxblink/summary.py:190-243       Summary.on_sample
+// and nxblink/raoteh.py:187-361 (init_tracks) in `init` mode.
+//
+// B200 mapping:
+//   * persistent grid, one CTA per SM, W warps per CTA, one warp per unit; the
+//     unit's whole trajectory lives in shared memory for the duration of its sweeps;
+//   * primary update: lanes over edges for candidate generation/thinning, lanes over
+//     the (<=64) primary states for the chunk-tree FFBS mat-vecs;
+//   * tolerance updates: the K tracks are conditionally independent given the primary
+//     track (chunking.py:39-107 reads only the primary track), so all K are updated
+//     concurrently, one lane per track, edge-synchronously;
+//   * candidate events are drawn by thinning one dominating Poisson process per
+//     (track, edge) whose exp(-lambda) is tabulated per edge -- no transcendental in the
+//     candidate path; the uniformization rate 2*max_s(rate) of poisson.py:88-90 is a
+//     table lookup in an L2-resident 2^K-entry table;
+//   * sufficient statistics are reduced on device (shared-memory partials per CTA,
+//     fp64/u64 atomics to L2 for the big tables).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "nxb_types.h"
+#include "philox.cuh"
+
+#define FULL 0xffffffffu
+#define NXB_INF (__longlong_as_double(0x7ff0000000000000LL))
+#define FLAG_OLD 1
+#define FLAG_DEAD 2
+
+namespace nxb {
+
+enum { RC_OK = 0, RC_DEFER = 1, RC_ERROR = 2 };
+
+__constant__ double c_inv_n[64];
+
+struct Ctx {
+    const NxbSweepParams* p;
+    int N, E, P, K, lane;
+    // model tables (shared memory)
+    const int* parent; const int* slot;
+    const double *tma, *len, *rate, *lam_pri, *p0_pri, *lam_blk, *p0_blk, *qval, *pi, *qm;
+    const unsigned short *qinfo, *qptr;
+    const unsigned char* cls;
+    const unsigned long long* clsmask;
+    // CTA-level statistic partials (shared memory)
+    unsigned long long *s_off_on, *s_on_off, *s_root_pri, *s_root_misc, *s_root_on_cls;
+    // per-warp persistent state (shared memory)
+    unsigned char* wbase;
+    unsigned* node_tol; unsigned char* node_pri;
+    double* ptm; unsigned* pcode; double* btm; unsigned* bcode;
+    int nP, nB;
+    int *boff, *poff, *tmpa, *tmpb, *tmpc;
+    // site data
+    const unsigned long long* pri_ok; const unsigned* tt_ok; const unsigned* tf_ok;
+    // rng
+    unsigned k0, k1, unit32, sweep;
+    long long unit;       // local unit index
+};
+
+__device__ __forceinline__ NxbU4 rng(const Ctx& c, unsigned stream, unsigned block) {
+    return nxb_philox4x32_10(c.unit32, c.sweep, stream, block, c.k0, c.k1);
+}
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    total = __shfl_sync(FULL, x, 31);
+    return x - v;
+}
+__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        double y = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += y;
+    }
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Draw an index from 64 non-negative weights, two per lane (items lane, lane+32).
+// Returns -1 if all weights are zero.  u in (0,1).
+__device__ __forceinline__ int warp_sample64(double w_lo, double w_hi, double u, int lane) {
+    double s_lo = warp_incl_scan(w_lo, lane);
+    double tot_lo = __shfl_sync(FULL, s_lo, 31);
+    double s_hi = warp_incl_scan(w_hi, lane) + tot_lo;
+    double total = __shfl_sync(FULL, s_hi, 31);
+    if (!(total > 0.0)) return -1;
+    double target = u * total;
+    unsigned b_lo = __ballot_sync(FULL, s_lo > target);
+    if (b_lo) return __ffs(b_lo) - 1;
+    unsigned b_hi = __ballot_sync(FULL, s_hi > target);
+    if (b_hi) return 32 + __ffs(b_hi) - 1;
+    // rounding: target == total; take the last item with positive weight
+    unsigned p_hi = __ballot_sync(FULL, w_hi > 0.0);
+    if (p_hi) return 32 + (31 - __clz(p_hi));
+    unsigned p_lo = __ballot_sync(FULL, w_lo > 0.0);
+    return 31 - __clz(p_lo);
+}
+
+__device__ __forceinline__ int poisson_inv(double u, double p0, double lam) {
+    int n = 0;
+    double pr = p0, cdf = p0;
+    while (u > cdf && n < 1000) {
+        ++n;
+        pr *= lam * (n < 64 ? c_inv_n[n] : 1.0 / (double)n);
+        cdf += pr;
+    }
+    return n;
+}
+
+// sum_{b : class(b) in mask} q[s][b]   (util.py:24-48 restricted as in poisson.py:83-86)
+__device__ __forceinline__ double rsum_masked(const Ctx& c, int s, unsigned mask) {
+    double acc = 0.0;
+    for (int idx = c.qptr[s]; idx < c.qptr[s + 1]; ++idx) {
+        unsigned info = c.qinfo[idx];
+        if ((mask >> (info >> 8)) & 1u) acc += c.qval[idx];
+    }
+    return acc;
+}
+
+// max over ALL source states (poisson.py:88-90 / util.py:13-17)
+__device__ __forceinline__ double rmax_lookup(const Ctx& c, unsigned mask) {
+    if (c.p->rmax_tab) return __ldg(c.p->rmax_tab + mask);
+    double m = 0.0;
+    for (int s = 0; s < c.P; ++s) m = fmax(m, rsum_masked(c, s, mask));
+    return m;
+}
+
+__device__ __forceinline__ void fail(const Ctx& c, int code, int detail) {
+    if (c.lane == 0) {
+        if (atomicCAS(c.p->status, 0, code) == 0) {
+            c.p->status[1] = (int)c.unit;
+            c.p->status[2] = detail;
+            c.p->status[3] = (int)c.sweep;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// index helpers shared by both phases
+// ---------------------------------------------------------------------------
+
+// poff[e] = first retained primary event on edge e (events are sorted by edge, time)
+__device__ void build_poff(Ctx& c) {
+    const int E = c.E, lane = c.lane;
+    for (int e = lane; e <= E; e += 32) c.tmpa[e] = 0;
+    __syncwarp();
+    for (int i = lane; i < c.nP; i += 32) atomicAdd(&c.tmpa[c.pcode[i] & 0xffffu], 1);
+    __syncwarp();
+    int run = 0;
+    for (int b = 0; b <= E; b += 32) {
+        int e = b + lane;
+        int v = (e < E) ? c.tmpa[e] : 0;
+        int tot;
+        int ex = warp_excl_scan(v, lane, tot);
+        if (e <= E) c.poff[e] = run + ex;
+        run += tot;
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// PRIMARY TRACK UPDATE  (raoteh.py:394-411; init: raoteh.py:350-361)
+// ---------------------------------------------------------------------------
+template <typename MSG>
+__device__ int primary_phase(Ctx& c, bool init, bool accumulate) {
+    const NxbSweepParams& p = *c.p;
+    const NxbWarpLayout& wl = p.wl;
+    const int E = c.E, N = c.N, P = c.P, K = c.K, lane = c.lane;
+    const unsigned ALLK = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
+
+    unsigned short* bord = (unsigned short*)(c.wbase + wl.off_bord);
+    double* rtm = (double*)(c.wbase + wl.off_rtm);
+    unsigned* rmask = (unsigned*)(c.wbase + wl.off_rmask);
+    double* ftm = (double*)(c.wbase + wl.off_ftm);
+    unsigned* fmask = (unsigned*)(c.wbase + wl.off_fmask);
+    unsigned short* fedge = (unsigned short*)(c.wbase + wl.off_fedge);
+    int* nchunk = (int*)(c.wbase + wl.off_nchunk);
+    int* jump = (int*)(c.wbase + wl.off_jump);
+    unsigned short* par = (unsigned short*)(c.wbase + wl.off_par);
+    unsigned* toland = (unsigned*)(c.wbase + wl.off_toland);
+    unsigned long long* callow = (unsigned long long*)(c.wbase + wl.off_callow);
+    unsigned char* cstate = (unsigned char*)(c.wbase + wl.off_cstate);
+    MSG* msg = (MSG*)(c.wbase + wl.off_msg);
+    int* boff = c.boff; int* poff = c.poff;
+    int* mE = c.tmpa; int* rbase = c.tmpb; int* foff = c.tmpc;
+
+    // ---- P0: edge-major, time-sorted view of the retained blink events ----------
+    for (int e = lane; e <= E; e += 32) { c.tmpa[e] = 0; c.tmpb[e] = 0; }
+    __syncwarp();
+    for (int i = lane; i < c.nB; i += 32) atomicAdd(&c.tmpa[c.bcode[i] & 0xffffu], 1);
+    __syncwarp();
+    {
+        int run = 0;
+        for (int b = 0; b <= E; b += 32) {
+            int e = b + lane;
+            int v = (e < E) ? c.tmpa[e] : 0;
+            int tot;
+            int ex = warp_excl_scan(v, lane, tot);
+            if (e <= E) boff[e] = run + ex;
+            run += tot;
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < c.nB; i += 32) {
+        int e = c.bcode[i] & 0xffffu;
+        int pos = atomicAdd(&c.tmpb[e], 1);
+        bord[boff[e] + pos] = (unsigned short)i;
+    }
+    __syncwarp();
+    for (int e = lane; e < E; e += 32) {
+        int a = boff[e], b = boff[e + 1];
+        for (int i = a + 1; i < b; ++i) {
+            unsigned short id = bord[i];
+            double t = c.btm[id];
+            int j = i - 1;
+            while (j >= a && c.btm[bord[j]] > t) { bord[j + 1] = bord[j]; --j; }
+            bord[j + 1] = id;
+        }
+    }
+    __syncwarp();
+    build_poff(c);   // uses tmpa
+
+    // ---- P1: candidates by thinning, merged walk, foreground event regions ------
+    int run = 0;
+    for (int b = 0; b < E; b += 32) {
+        const int e = b + lane;
+        const bool valid = e < E;
+        int n_ret = 0, n_cand = 0;
+        bool active = false;
+        if (valid) {
+            n_ret = poff[e + 1] - poff[e];
+            active = (c.len[e] > 0.0) && (c.rate[e] > 0.0);
+            if (active) {
+                if (init) n_cand = p.ml.diameter;
+                else {
+                    NxbU4 r = rng(c, NXB_STREAM_PRI_EDGE | (unsigned)e, 0u);
+                    n_cand = poisson_inv(nxb_u32(r.x), c.p0_pri[e], c.lam_pri[e]);
+                }
+            }
+        }
+        int size = n_ret + n_cand, tot;
+        int base = run + warp_excl_scan(size, lane, tot);
+        run += tot;
+        if (run > wl.capR) return RC_DEFER;          // uniform
+        int m = 0;
+        if (valid) {
+            const int c0 = base + n_ret;
+            const double tma = c.tma[e], len = c.len[e];
+            for (int i = 0; i < n_cand; ++i) {
+                NxbU4 r = rng(c, NXB_STREAM_PRI_EDGE | (unsigned)e, 1u + (unsigned)i);
+                double u = nxb_u53(r.x, r.y);
+                double t = init ? tma + len * ((1.0 + u) * (1.0 / 3.0)) : tma + len * u;
+                // insertion sort, carrying the thinning uniform
+                int j = c0 + i - 1;
+                while (j >= c0 && rtm[j] > t) { rtm[j + 1] = rtm[j]; rmask[j + 1] = rmask[j]; --j; }
+                rtm[j + 1] = t; rmask[j + 1] = r.z;
+            }
+            // merged walk: blink events (background), retained + candidate events (foreground)
+            const int va = c.parent[e];
+            unsigned mask = c.node_tol[va];
+            int s = init ? 0 : c.node_pri[va];
+            int ib = boff[e], ibe = boff[e + 1];
+            int ip = poff[e], ipe = poff[e + 1];
+            int ic = c0, ice = base + size;
+            int w = base;
+            while (true) {
+                double tb = (ib < ibe) ? c.btm[bord[ib]] : NXB_INF;
+                double tp = (ip < ipe) ? c.ptm[ip] : NXB_INF;
+                double tc = (ic < ice) ? rtm[ic] : NXB_INF;
+                if (tb == NXB_INF && tp == NXB_INF && tc == NXB_INF) break;
+                if (tb < tp && tb < tc) {
+                    mask ^= 1u << ((c.bcode[bord[ib]] >> 16) & 0xffu);
+                    ++ib;
+                } else if (tp < tc) {
+                    // retained foreground transition: always a chunk boundary
+                    rtm[w] = tp; rmask[w] = mask; ++w;
+                    s = (c.pcode[ip] >> 24) & 0xffu;
+                    ++ip;
+                } else {
+                    unsigned uth = rmask[ic];
+                    ++ic;
+                    bool keep = true;
+                    unsigned pm = mask;
+                    if (init) pm = ALLK;    // raoteh.py:271-276: full-Q uniformization
+                    else {
+                        // poisson.py:111-116: local rate = omega_ctx - r_s, thinned from the
+                        // dominating rate 2*Rmax(all on)
+                        double a = (2.0 * rmax_lookup(c, mask) - rsum_masked(c, s, mask))
+                                   * p.ml.inv_omega_pri;
+                        keep = nxb_u32(uth) < a;
+                    }
+                    if (keep) { rtm[w] = tc; rmask[w] = pm; ++w; }
+                }
+            }
+            m = w - base;
+            mE[e] = m; rbase[e] = base;
+        }
+    }
+    __syncwarp();
+    int F = 0;
+    {
+        int acc = 0;
+        for (int b = 0; b <= E; b += 32) {
+            int e = b + lane;
+            int v = (e < E) ? mE[e] : 0;
+            int tot;
+            int ex = warp_excl_scan(v, lane, tot);
+            if (e <= E) foff[e] = acc + ex;
+            acc += tot;
+        }
+        F = acc;
+    }
+    if (F > wl.capF) return RC_DEFER;
+    __syncwarp();
+    for (int e = lane; e < E; e += 32) {
+        int src = rbase[e], dst = foff[e], m = mE[e];
+        for (int i = 0; i < m; ++i) {
+            ftm[dst + i] = rtm[src + i];
+            fmask[dst + i] = rmask[src + i];
+            fedge[dst + i] = (unsigned short)e;
+        }
+    }
+    // ---- P2: chunk structure (chunking.py:158-261) --------------------------------
+    // chunk 0 holds the root; foreground event j opens chunk j+1.
+    for (int v = lane; v < N; v += 32) {
+        int own = -1;
+        if (v == 0) own = 0;
+        else if (mE[v - 1] > 0) own = foff[v - 1] + mE[v - 1];   // id of the last event on the edge
+        nchunk[v] = own;
+        jump[v] = (v == 0) ? 0 : c.parent[v - 1];
+    }
+    __syncwarp();
+    for (int it = 0; it < 32; ++it) {
+        bool pending = false;
+        for (int v = lane; v < N; v += 32) {
+            if (nchunk[v] < 0) {
+                int a = jump[v];
+                int ca = nchunk[a];
+                if (ca >= 0) nchunk[v] = ca;
+                else { jump[v] = jump[a]; pending = true; }
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(FULL, pending)) break;
+    }
+    for (int j = lane; j <= F; j += 32) { toland[j] = ALLK; callow[j] = ~0ull; }
+    for (int j = lane; j < F; j += 32) {
+        int e = fedge[j];
+        par[j + 1] = (unsigned short)((j == foff[e]) ? nchunk[c.parent[e]] : j);
+    }
+    __syncwarp();
+    for (int e = lane; e < E; e += 32) {
+        const int va = c.parent[e];
+        int cur = nchunk[va];
+        unsigned mask = c.node_tol[va];
+        unsigned acc = mask;
+        int ib = boff[e], ibe = boff[e + 1];
+        int j = foff[e], je = foff[e] + mE[e];
+        while (ib < ibe || j < je) {
+            double tb = (ib < ibe) ? c.btm[bord[ib]] : NXB_INF;
+            double tf = (j < je) ? ftm[j] : NXB_INF;
+            if (tb < tf) {
+                mask ^= 1u << ((c.bcode[bord[ib]] >> 16) & 0xffu);
+                acc &= mask;
+                ++ib;
+            } else {
+                atomicAnd(&toland[cur], acc);
+                cur = j + 1; acc = mask; ++j;
+            }
+        }
+        atomicAnd(&toland[cur], acc);
+        atomicAnd(&callow[cur], c.pri_ok[e + 1]);
+    }
+    if (lane == 0) atomicAnd(&callow[0], c.pri_ok[0]);
+    __syncwarp();
+    for (int j = lane; j <= F; j += 32) {
+        unsigned tm = toland[j];
+        unsigned long long ok = 0ull;
+        for (int k = 0; k < K; ++k) if ((tm >> k) & 1u) ok |= c.clsmask[k];
+        callow[j] &= ok;
+    }
+    // ---- P3: upward pass over the chunk tree ------------------------------------------
+    for (int i = lane; i < (F + 1) * NXB_PPAD; i += 32) msg[i] = (MSG)1.0;
+    __syncwarp();
+    for (int j = F - 1; j >= 0; --j) {
+        const int ci = j + 1, pi_ = par[ci];
+        const unsigned fm = fmask[j];
+        const unsigned long long allow = callow[ci];
+        const double rm = rmax_lookup(c, fm);
+        if (!(rm > 0.0)) { fail(c, NXB_ERR_ZERO_RATE, j); return RC_ERROR; }
+        const double inv = 0.5 / rm;
+        MSG* mc = msg + ci * NXB_PPAD;
+        MSG* mp = msg + pi_ * NXB_PPAD;
+        double v0 = (lane < P && ((allow >> lane) & 1ull)) ? (double)mc[lane] : 0.0;
+        double v1 = (lane + 32 < P && ((allow >> (lane + 32)) & 1ull)) ? (double)mc[lane + 32] : 0.0;
+        double mx = warp_max(fmax(v0, v1));
+        if (!(mx > 0.0)) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
+        double sc = 1.0 / mx;
+        mc[lane] = (MSG)(v0 * sc);
+        mc[lane + 32] = (MSG)(v1 * sc);
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int a = lane + 32 * half;
+            if (a < P) {
+                double aq = 0.0, am = 0.0;
+                for (int idx = c.qptr[a]; idx < c.qptr[a + 1]; ++idx) {
+                    unsigned info = c.qinfo[idx];
+                    if ((fm >> (info >> 8)) & 1u) {
+                        double q = c.qval[idx];
+                        aq += q;
+                        am += q * (double)mc[info & 0xffu];
+                    }
+                }
+                double self = (double)mc[a];
+                double up = self + inv * (am - aq * self);
+                mp[a] = (MSG)((double)mp[a] * up);
+            }
+        }
+        __syncwarp();
+    }
+    // ---- P4: root draw and downward sampling ----------------------------------------------
+    {
+        const unsigned long long allow = callow[0];
+        double w0 = (lane < P && ((allow >> lane) & 1ull)) ? (double)msg[lane] * c.pi[lane] : 0.0;
+        double w1 = (lane + 32 < P && ((allow >> (lane + 32)) & 1ull))
+                    ? (double)msg[lane + 32] * c.pi[lane + 32] : 0.0;
+        NxbU4 r = rng(c, NXB_STREAM_PRI_FFBS, 0u);
+        int s0 = warp_sample64(w0, w1, nxb_u53(r.x, r.y), lane);
+        if (s0 < 0) { fail(c, NXB_ERR_INFEASIBLE, -1); return RC_ERROR; }
+        if (lane == 0) cstate[0] = (unsigned char)s0;
+    }
+    __syncwarp();
+    for (int j = 0; j < F; ++j) {
+        const int ci = j + 1;
+        const int a = cstate[par[ci]];
+        const unsigned fm = fmask[j];
+        const double inv = 0.5 / rmax_lookup(c, fm);
+        const MSG* mc = msg + ci * NXB_PPAD;
+        const int q0 = c.qptr[a], deg = c.qptr[a + 1] - q0;
+        // items: 0 = stay in a (diagonal of the uniformized matrix), i>=1 = neighbour i-1
+        double q_lo = 0.0, q_hi = 0.0; int b_lo = a, b_hi = a;
+        if (lane >= 1 && lane <= deg) {
+            unsigned info = c.qinfo[q0 + lane - 1];
+            if ((fm >> (info >> 8)) & 1u) q_lo = c.qval[q0 + lane - 1];
+            b_lo = info & 0xffu;
+        }
+        if (lane + 32 <= deg) {
+            unsigned info = c.qinfo[q0 + lane + 31];
+            if ((fm >> (info >> 8)) & 1u) q_hi = c.qval[q0 + lane + 31];
+            b_hi = info & 0xffu;
+        }
+        double ra = warp_sum(q_lo + q_hi);
+        double w_lo = (lane == 0) ? (1.0 - inv * ra) * (double)mc[a] : inv * q_lo * (double)mc[b_lo];
+        double w_hi = inv * q_hi * (double)mc[b_hi];
+        NxbU4 r = rng(c, NXB_STREAM_PRI_FFBS, (unsigned)ci);
+        int item = warp_sample64(w_lo, w_hi, nxb_u53(r.x, r.y), lane);
+        if (item < 0) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
+        int bsel = (item < 32) ? __shfl_sync(FULL, b_lo, item) : __shfl_sync(FULL, b_hi, item - 32);
+        if (lane == 0) cstate[ci] = (unsigned char)bsel;
+        __syncwarp();
+    }
+    // ---- P5: write back, dropping self transitions (raoteh.py:411) ------------------------------
+    int nkeep = 0;
+    for (int b = 0; b < F; b += 32) {
+        int j = b + lane;
+        bool keep = (j < F) && (cstate[par[j + 1]] != cstate[j + 1]);
+        nkeep += __popc(__ballot_sync(FULL, keep));
+    }
+    if (nkeep > wl.capP) return RC_DEFER;     // nothing persistent has been modified yet
+    nkeep = 0;
+    for (int b = 0; b < F; b += 32) {
+        int j = b + lane;
+        int sa = 0, sb = 0;
+        bool keep = false;
+        if (j < F) { sa = cstate[par[j + 1]]; sb = cstate[j + 1]; keep = sa != sb; }
+        unsigned bal = __ballot_sync(FULL, keep);
+        if (keep) {
+            int pos = nkeep + __popc(bal & ((1u << lane) - 1u));
+            c.ptm[pos] = ftm[j];
+            c.pcode[pos] = (unsigned)fedge[j] | ((unsigned)sa << 16) | ((unsigned)sb << 24);
+        }
+        nkeep += __popc(bal);
+    }
+    c.nP = nkeep;
+    for (int v = lane; v < N; v += 32) c.node_pri[v] = cstate[nchunk[v]];
+    __syncwarp();
+
+    // ---- primary-track statistics (summary.py:214-232 and the primary half of :111-121) ----------
+    if (accumulate) {
+        build_poff(c);
+        const NxbSummaryLayout& sl = p.sl;
+        for (int e = lane; e < E; e += 32) {
+            double t = c.tma[e];
+            int s = c.node_pri[c.parent[e]];
+            for (int i = poff[e]; i < poff[e + 1]; ++i) {
+                double te = c.ptm[i];
+                atomicAdd(p.dwell + sl.d_T + e * P + s, te - t);
+                int sb = (c.pcode[i] >> 24) & 0xffu;
+                int idx = c.qptr[s];
+                while ((c.qinfo[idx] & 0xffu) != (unsigned)sb) ++idx;
+                atomicAdd(p.counts + sl.c_pri_trans + (long long)e * p.ml.nnz + idx, 1ull);
+                s = sb; t = te;
+            }
+            atomicAdd(p.dwell + sl.d_T + e * P + s, c.tma[e] + c.len[e] - t);
+        }
+        if (lane == 0) atomicAdd(&c.s_root_pri[c.node_pri[0]], 1ull);
+    }
+    return RC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, lane k = track k
+// ---------------------------------------------------------------------------
+__device__ int blink_phase(Ctx& c, bool accumulate) {
+    const NxbSweepParams& p = *c.p;
+    const NxbWarpLayout& wl = p.wl;
+    const NxbModelLayout& ml = p.ml;
+    const int E = c.E, N = c.N, P = c.P, K = c.K, lane = c.lane;
+
+    double* ctm = (double*)(c.wbase + wl.off_ctm);
+    unsigned* cell = (unsigned*)(c.wbase + wl.off_cell);       // thinning uniform, then float l
+    unsigned short* cedge = (unsigned short*)(c.wbase + wl.off_cedge);
+    unsigned char* cflag = (unsigned char*)(c.wbase + wl.off_cflag);
+    int* toff = (int*)(c.wbase + wl.off_toff);
+    double* acc = (double*)(c.wbase + wl.off_acc);              // [slot][K][3]: u0, u1, penalty
+    unsigned* newtol = (unsigned*)(c.wbase + wl.off_newtol);
+    int* poff = c.poff;
+
+    build_poff(c);
+
+    // ---- B0: candidate pool, (track, edge)-major, time-sorted; lanes over pairs ------------
+    const int npairs = K * E;
+    int run = 0, cur = 0;
+    for (int b = 0; b < npairs; b += 32) {
+        const int pr = b + lane;
+        const bool valid = pr < npairs;
+        int k = 0, e = 0;
+        if (valid) { k = pr / E; e = pr - k * E; }
+        const unsigned mykey = ((unsigned)k << 16) | (unsigned)e;
+        int lastp = min(b + 31, npairs - 1);
+        int lk = lastp / E;
+        const unsigned lastkey = ((unsigned)lk << 16) | (unsigned)(lastp - lk * E);
+        int n_old = 0, first = 0;
+        int i = cur;
+        while (i < c.nB) {
+            unsigned key = c.bcode[i] & 0x00ffffffu;
+            if (key > lastkey) break;
+            if (valid && key == mykey) { if (n_old == 0) first = i; ++n_old; }
+            ++i;
+        }
+        cur = i;
+        int n_new = 0;
+        bool active = valid && (c.len[e] > 0.0) && (c.rate[e] > 0.0);
+        if (active) {
+            NxbU4 r = rng(c, NXB_STREAM_BLK_PAIR | mykey, 0u);
+            n_new = poisson_inv(nxb_u32(r.x), c.p0_blk[e], c.lam_blk[e]);
+        }
+        int size = n_old + n_new, tot;
+        int base = run + warp_excl_scan(size, lane, tot);
+        run += tot;
+        if (run > wl.capC) return RC_DEFER;
+        if (valid) {
+            if (e == 0) toff[k] = base;
+            for (int q = 0; q < n_old; ++q) {
+                ctm[base + q] = c.btm[first + q];
+                cflag[base + q] = FLAG_OLD;
+                cell[base + q] = 0u;
+                cedge[base + q] = (unsigned short)e;
+            }
+            const double tma = c.tma[e], len = c.len[e];
+            for (int q = 0; q < n_new; ++q) {
+                NxbU4 r = rng(c, NXB_STREAM_BLK_PAIR | mykey, 1u + (unsigned)q);
+                double t = tma + len * nxb_u53(r.x, r.y);
+                int j = base + n_old + q - 1;
+                while (j >= base && ctm[j] > t) {
+                    ctm[j + 1] = ctm[j]; cflag[j + 1] = cflag[j]; cell[j + 1] = cell[j]; --j;
+                }
+                ctm[j + 1] = t; cflag[j + 1] = 0; cell[j + 1] = r.z;
+                cedge[base + n_old + q] = (unsigned short)e;
+            }
+        }
+    }
+    if (lane == 0) toff[K] = run;
+    __syncwarp();
+
+    const bool trk = lane < K;
+    const int k = trk ? lane : 0;
+    const int t_lo = trk ? toff[k] : 0;
+    const int t_hi = trk ? toff[k + 1] : 0;
+    int rc_lane = 0;     // per-lane infeasibility flag, reduced after the loops
+
+    // ---- B1: upward pass, edges in descending index (children before parents) -----------------
+    {
+        int ic = t_hi;                 // this lane's pool cursor (exclusive upper end)
+        unsigned inited = 0u;          // uniform bitmask of live accumulator slots
+        for (int e = E - 1; e >= 0; --e) {
+            const int vb = e + 1, va = c.parent[e];
+            const int sb_slot = c.slot[vb], sa_slot = c.slot[va];
+            const double tma = c.tma[e], rate = c.rate[e];
+            double u0 = 1.0, u1 = 1.0, pen = 0.0;
+            if (trk) {
+                if (sb_slot >= 0 && ((inited >> sb_slot) & 1u)) {
+                    const double* a = acc + (sb_slot * K + k) * 3;
+                    u0 = a[0]; u1 = a[1]; pen = a[2];
+                }
+                if (!((c.tt_ok[vb] >> k) & 1u)) u1 = 0.0;
+                if (!((c.tf_ok[vb] >> k) & 1u)) u0 = 0.0;
+                int s = c.node_pri[vb];
+                unsigned xold = (c.node_tol[vb] >> k) & 1u;
+                int ip = poff[e + 1] - 1;
+                const int ip0 = poff[e];
+                double tcur = tma + c.len[e];
+                while (true) {
+                    double tp = (ip >= ip0) ? c.ptm[ip] : -NXB_INF;
+                    bool hasc = (ic > t_lo) && (cedge[ic - 1] == (unsigned short)e);
+                    double tc = hasc ? ctm[ic - 1] : -NXB_INF;
+                    double tnext = fmax(fmax(tp, tc), tma);
+                    const bool own = (c.cls[s] == k);
+                    // chunking.py:67-79: own class forces ON; ON pays the rate into class k
+                    pen += c.qm[s * K + k] * rate * (tcur - tnext);
+                    if (own) u0 = 0.0;
+                    if (tp == -NXB_INF && tc == -NXB_INF) break;
+                    if (tc > tp) {
+                        const int id = ic - 1;
+                        --ic;
+                        bool live = true;
+                        if (cflag[id] & FLAG_OLD) xold ^= 1u;
+                        else {
+                            double a = ml.acc_blk[(own ? 2 : 0) + (int)xold];
+                            live = nxb_u32(cell[id]) < a;
+                            if (!live) cflag[id] = FLAG_DEAD;
+                        }
+                        if (live) {
+                            u1 *= exp(-pen); pen = 0.0;
+                            double ssum = u0 + u1;
+                            if (!(ssum > 0.0)) { rc_lane = 1; ssum = 1.0; }
+                            double l1 = u1 / ssum, l0 = u0 / ssum;
+                            cell[id] = __float_as_uint((float)l1);
+                            // uniformized 2x2 matrix of this context (poisson.py:92-96)
+                            if (own) { u0 = 0.5 * l0 + 0.5 * l1; u1 = l1; }
+                            else {
+                                double n0 = (1.0 - ml.a_on) * l0 + ml.a_on * l1;
+                                double n1 = ml.a_off * l0 + (1.0 - ml.a_off) * l1;
+                                u0 = n0; u1 = n1;
+                            }
+                        }
+                    } else {
+                        s = (c.pcode[ip] >> 16) & 0xffu;     // going rootward: state before the event
+                        --ip;
+                    }
+                    tcur = tnext;
+                }
+                // fold into the parent's accumulator
+                double mx = fmax(u0, u1);
+                if (!(mx > 0.0)) { rc_lane = 1; mx = 1.0; }
+                u0 /= mx; u1 /= mx;
+                double* a = acc + (sa_slot * K + k) * 3;
+                if ((inited >> sa_slot) & 1u) {
+                    double n0 = a[0] * u0, n1 = a[1] * u1;
+                    double m2 = fmax(n0, n1);
+                    if (!(m2 > 0.0)) {
+                        // the two factors may only be compatible after their penalties are
+                        // applied; both are max-normalised so a zero product is a true zero
+                        rc_lane = 1; m2 = 1.0;
+                    }
+                    a[0] = n0 / m2; a[1] = n1 / m2; a[2] += pen;
+                } else { a[0] = u0; a[1] = u1; a[2] = pen; }
+            }
+            inited |= 1u << sa_slot;
+            if (sb_slot >= 0) inited &= ~(1u << sb_slot);
+        }
+    }
+    __syncwarp();
+    // ---- root draw (prior: toymodel.py:17-27 get_blink_distn) ----------------------------------------
+    unsigned x = 0u;
+    if (trk) {
+        const double* a = acc + (c.slot[0] * K + k) * 3;
+        double w1 = a[1] * exp(-a[2]) * ml.p_on;
+        double w0 = a[0] * ml.p_off;
+        if (!((c.tt_ok[0] >> k) & 1u)) w1 = 0.0;
+        if (!((c.tf_ok[0] >> k) & 1u)) w0 = 0.0;
+        if (c.cls[c.node_pri[0]] == k) w0 = 0.0;
+        if (!(w0 + w1 > 0.0)) rc_lane = 1;
+        NxbU4 r = rng(c, NXB_STREAM_BLK_FFBS | ((unsigned)k << 16), 0xffffffffu);
+        x = (nxb_u53(r.x, r.y) * (w0 + w1) < w1) ? 1u : 0u;
+    }
+    if (__any_sync(FULL, rc_lane)) { fail(c, NXB_ERR_INFEASIBLE, -2); return RC_ERROR; }
+    {
+        unsigned bal = __ballot_sync(FULL, x);
+        if (lane == 0) newtol[0] = bal;
+    }
+    __syncwarp();
+
+    // ---- B2: downward sampling, edges in ascending index; statistics fused in ------------------------
+    const NxbSummaryLayout& sl = p.sl;
+    int w = t_lo, ic = t_lo;
+    for (int e = 0; e < E; ++e) {
+        const int vb = e + 1, va = c.parent[e];
+        if (trk) {
+            x = (newtol[va] >> k) & 1u;
+            int s = c.node_pri[va];
+            int ip = poff[e];
+            const int ipe = poff[e + 1];
+            const double tmb = c.tma[e] + c.len[e];
+            double tcur = c.tma[e];
+            double offtime = 0.0;
+            int n_on = 0, n_off = 0;
+            while (true) {
+                double tp = (ip < ipe) ? c.ptm[ip] : NXB_INF;
+                bool hasc = (ic < t_hi) && (cedge[ic] == (unsigned short)e);
+                double tc = hasc ? ctm[ic] : NXB_INF;
+                double tnext = fmin(fmin(tp, tc), tmb);
+                if (!x) offtime += tnext - tcur;
+                tcur = tnext;
+                if (tp == NXB_INF && tc == NXB_INF) {
+                    if (accumulate && offtime > 0.0)
+                        atomicAdd(p.dwell + sl.d_off + ((long long)e * P + s) * K + k, offtime);
+                    break;
+                }
+                if (tc < tp) {
+                    const int id = ic;
+                    ++ic;
+                    if (!(cflag[id] & FLAG_DEAD)) {
+                        const bool own = (c.cls[s] == k);
+                        double l1 = (double)__uint_as_float(cell[id]);
+                        double p1 = own ? (x ? 1.0 : 0.5) : (x ? 1.0 - ml.a_off : ml.a_on);
+                        double w1 = p1 * l1, w0 = (1.0 - p1) * (1.0 - l1);
+                        NxbU4 r = rng(c, NXB_STREAM_BLK_FFBS | ((unsigned)k << 16), (unsigned)id);
+                        unsigned xn = (nxb_u32(r.x) * (w0 + w1) < w1) ? 1u : 0u;
+                        if (!(w0 + w1 > 0.0)) rc_lane = 1;
+                        if (xn != x) {
+                            ctm[w] = tc; cedge[w] = (unsigned short)e; cflag[w] = (unsigned char)xn;
+                            ++w;
+                            if (xn) ++n_on; else ++n_off;
+                            x = xn;
+                        }
+                    }
+                } else {
+                    if (accumulate && offtime > 0.0)
+                        atomicAdd(p.dwell + sl.d_off + ((long long)e * P + s) * K + k, offtime);
+                    offtime = 0.0;
+                    s = (c.pcode[ip] >> 24) & 0xffu;
+                    ++ip;
+                }
+            }
+            if (accumulate) {
+                if (n_on) atomicAdd(&c.s_off_on[e], (unsigned long long)n_on);
+                if (n_off) atomicAdd(&c.s_on_off[e], (unsigned long long)n_off);
+            }
+        }
+        unsigned bal = __ballot_sync(FULL, trk && x);
+        if (lane == 0) newtol[vb] = bal;
+        __syncwarp();
+    }
+    if (__any_sync(FULL, rc_lane)) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
+
+    // ---- write back: new retained blink events, (track, edge, time) order -----------------------------
+    int n_mine = trk ? (w - t_lo) : 0, total;
+    int dst = warp_excl_scan(n_mine, lane, total);
+    for (int v = lane; v < N; v += 32) c.node_tol[v] = newtol[v];
+    if (accumulate && lane == 0) {
+        int on = __popc(newtol[0]);
+        atomicAdd(&c.s_root_misc[0], (unsigned long long)on);
+        atomicAdd(&c.s_root_misc[1], (unsigned long long)(K - on));
+        atomicAdd(&c.s_root_on_cls[c.cls[c.node_pri[0]]], (unsigned long long)on);
+        atomicAdd(&c.s_root_misc[2], 1ull);
+    }
+    if (total > wl.capB) {
+        // The sweep is complete and its statistics are booked; only the shared-memory
+        // arrays are too small.  Spill the new blink list straight to the HBM slab and
+        // let the next capacity tier pick the unit up at the next sweep boundary.
+        if (total > p.gcapB) { fail(c, NXB_ERR_STATE_CAP, total); return RC_ERROR; }
+        unsigned char* slab = p.state + c.unit * p.state_stride;
+        double* gbtm = (double*)(slab + p.so_btm);
+        unsigned* gbcode = (unsigned*)(slab + p.so_bcode);
+        for (int q = 0; q < n_mine; ++q) {
+            gbtm[dst + q] = ctm[t_lo + q];
+            gbcode[dst + q] = (unsigned)cedge[t_lo + q] | ((unsigned)k << 16)
+                              | ((unsigned)cflag[t_lo + q] << 31);
+        }
+        c.nB = -total;      // negative: already in HBM
+        __syncwarp();
+        return RC_DEFER;
+    }
+    for (int q = 0; q < n_mine; ++q) {
+        c.btm[dst + q] = ctm[t_lo + q];
+        c.bcode[dst + q] = (unsigned)cedge[t_lo + q] | ((unsigned)k << 16)
+                           | ((unsigned)cflag[t_lo + q] << 31);
+    }
+    c.nB = total;
+    __syncwarp();
+    return RC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// initial tolerance histories  (raoteh.py:187-229)
+// ---------------------------------------------------------------------------
+__device__ int init_blink(Ctx& c) {
+    const int E = c.E, N = c.N, K = c.K, lane = c.lane;
+    const unsigned ALLK = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
+    int bad = 0;
+    for (int v = lane; v < N; v += 32) {
+        unsigned t = c.tt_ok[v] & ALLK, f = c.tf_ok[v] & ALLK;
+        if ((t | f) != ALLK) bad = 1;          // raoteh.py:201
+        c.node_tol[v] = t;                     // ON wherever the data allow it
+    }
+    if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_INFEASIBLE, -4); return RC_ERROR; }
+    __syncwarp();
+    const bool trk = lane < K;
+    int cnt = 0;
+    if (trk) for (int e = 0; e < E; ++e) {
+        if (!(c.len[e] > 0.0 && c.rate[e] > 0.0)) continue;
+        cnt += !((c.node_tol[c.parent[e]] >> lane) & 1u);
+        cnt += !((c.node_tol[e + 1] >> lane) & 1u);
+    }
+    int total;
+    int dst = warp_excl_scan(cnt, lane, total);
+    if (total > c.p->wl.capB) return RC_DEFER;
+    if (trk) for (int e = 0; e < E; ++e) {
+        if (!(c.len[e] > 0.0 && c.rate[e] > 0.0)) continue;
+        unsigned sa = (c.node_tol[c.parent[e]] >> lane) & 1u;
+        unsigned sb = (c.node_tol[e + 1] >> lane) & 1u;
+        if (sa && sb) continue;
+        NxbU4 r = rng(c, NXB_STREAM_INIT_BLK | ((unsigned)lane << 16) | (unsigned)e, 0u);
+        if (!sa) {
+            c.btm[dst] = c.tma[e] + c.len[e] * (nxb_u53(r.x, r.y) * (1.0 / 3.0));
+            c.bcode[dst] = (unsigned)e | ((unsigned)lane << 16) | (1u << 31);
+            ++dst;
+        }
+        if (!sb) {
+            c.btm[dst] = c.tma[e] + c.len[e] * ((2.0 + nxb_u53(r.z, r.w)) * (1.0 / 3.0));
+            c.bcode[dst] = (unsigned)e | ((unsigned)lane << 16);
+            ++dst;
+        }
+    }
+    c.nB = total;
+    c.nP = 0;
+    __syncwarp();
+    return RC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// trajectory invariants (the checks of navigation.py:39-44,121-135, chunking.py:96-100,
+// summary.py:243, plus the model constraints of nxblink/compound.py:23-40)
+// ---------------------------------------------------------------------------
+__device__ int validate_unit(Ctx& c) {
+    const int E = c.E, N = c.N, K = c.K, lane = c.lane;
+    unsigned short* bord = (unsigned short*)(c.wbase + c.p->wl.off_bord);
+    int bad = 0;
+    // primary events sorted by (edge, time); blink events by (track, edge, time)
+    for (int i = lane; i + 1 < c.nP; i += 32) {
+        unsigned ea = c.pcode[i] & 0xffffu, eb = c.pcode[i + 1] & 0xffffu;
+        if (ea > eb || (ea == eb && !(c.ptm[i] < c.ptm[i + 1]))) bad = 1;
+    }
+    for (int i = lane; i + 1 < c.nB; i += 32) {
+        unsigned ka = c.bcode[i] & 0xffffffu, kb = c.bcode[i + 1] & 0xffffffu;
+        if (ka > kb || (ka == kb && !(c.btm[i] < c.btm[i + 1]))) bad = 2;
+    }
+    if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_INVARIANT, __reduce_max_sync(FULL, bad)); return RC_ERROR; }
+    // edge-major view of the blink events
+    for (int e = lane; e <= E; e += 32) { c.tmpa[e] = 0; c.tmpb[e] = 0; }
+    __syncwarp();
+    for (int i = lane; i < c.nB; i += 32) atomicAdd(&c.tmpa[c.bcode[i] & 0xffffu], 1);
+    __syncwarp();
+    {
+        int run = 0;
+        for (int b = 0; b <= E; b += 32) {
+            int e = b + lane, tot;
+            int v = (e < E) ? c.tmpa[e] : 0;
+            int ex = warp_excl_scan(v, lane, tot);
+            if (e <= E) c.boff[e] = run + ex;
+            run += tot;
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < c.nB; i += 32) {
+        int e = c.bcode[i] & 0xffffu;
+        bord[c.boff[e] + atomicAdd(&c.tmpb[e], 1)] = (unsigned short)i;
+    }
+    __syncwarp();
+    for (int e = lane; e < E; e += 32) {
+        int a = c.boff[e], b = c.boff[e + 1];
+        for (int i = a + 1; i < b; ++i) {
+            unsigned short id = bord[i];
+            double t = c.btm[id];
+            int j = i - 1;
+            while (j >= a && c.btm[bord[j]] > t) { bord[j + 1] = bord[j]; --j; }
+            bord[j + 1] = id;
+        }
+    }
+    __syncwarp();
+    build_poff(c);
+    for (int v = lane; v < N; v += 32) {
+        int s = c.node_pri[v];
+        unsigned m = c.node_tol[v];
+        if (!((c.pri_ok[v] >> s) & 1ull)) bad = 3;
+        if ((m & ~c.tt_ok[v]) || (~m & ((K == 32) ? ~0u : ((1u << K) - 1u)) & ~c.tf_ok[v])) bad = 4;
+        if (!((m >> c.cls[s]) & 1u)) bad = 5;
+    }
+    for (int e = lane; e < E; e += 32) {
+        const int va = c.parent[e];
+        const double t0 = c.tma[e], t1 = t0 + c.len[e];
+        unsigned mask = c.node_tol[va];
+        int s = c.node_pri[va];
+        int ib = c.boff[e], ibe = c.boff[e + 1], ip = c.poff[e], ipe = c.poff[e + 1];
+        if ((ib < ibe || ip < ipe) && !(c.len[e] > 0.0 && c.rate[e] > 0.0)) bad = 6;
+        while (ib < ibe || ip < ipe) {
+            double tb = (ib < ibe) ? c.btm[bord[ib]] : NXB_INF;
+            double tp = (ip < ipe) ? c.ptm[ip] : NXB_INF;
+            double t = fmin(tb, tp);
+            if (!(t > t0 && t < t1)) bad = 7;
+            if (tb < tp) {
+                unsigned code = c.bcode[bord[ib]];
+                unsigned k = (code >> 16) & 0xffu, ns = code >> 31;
+                if (((mask >> k) & 1u) == ns) bad = 8;            // self / incompatible transition
+                if (!ns && c.cls[s] == k) bad = 9;                 // own class may not switch off
+                mask ^= 1u << k;
+                ++ib;
+            } else {
+                unsigned code = c.pcode[ip];
+                int sa = (code >> 16) & 0xffu, sb = (code >> 24) & 0xffu;
+                if (sa != s || sa == sb) bad = 10;
+                if (!((mask >> c.cls[sb]) & 1u)) bad = 11;         // target class must be ON
+                bool found = false;
+                for (int idx = c.qptr[sa]; idx < c.qptr[sa + 1]; ++idx)
+                    if ((c.qinfo[idx] & 0xffu) == (unsigned)sb) found = true;
+                if (!found) bad = 12;
+                s = sb;
+                ++ip;
+            }
+        }
+        if (s != c.node_pri[e + 1]) bad = 13;
+        if (mask != c.node_tol[e + 1]) bad = 14;
+    }
+    if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_INVARIANT, __reduce_max_sync(FULL, bad)); return RC_ERROR; }
+    return RC_OK;
+}
+
+}  // namespace nxb

@@ -1,0 +1,168 @@
+"""Batched Rao-Teh sampler: the host-side handle around the C-ABI.
+
+``BlinkSampler`` runs the Gibbs sweep of nxblink/raoteh.py:364-435 for a whole
+batch of alignment sites x independent chains on one B200 and reduces the
+sufficient statistics of nxblink/summary.py on the device.  There is no CPU
+path: constructing it without the CUDA library or without a device raises.
+"""
+from __future__ import division, print_function
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import NxbError
+from .packing import PackedModel, PackedData, pack_data
+from .summary import Summary
+
+
+class Event(object):
+    """Same fields as ``nxctmctree.trajectory.Event`` (track, tm, sa, sb)."""
+    __slots__ = ('track', 'tm', 'sa', 'sb')
+
+    def __init__(self, track=None, tm=None, sa=None, sb=None):
+        self.track, self.tm, self.sa, self.sb = track, tm, sa, sb
+
+    def __repr__(self):
+        return 'Event(%r, %r, %r, %r)' % (
+                getattr(self.track, 'name', None), self.tm, self.sa, self.sb)
+
+
+class Track(object):
+    """What ``gen_samples`` yields per track: name, history, events (trajectory.py:17-50)."""
+
+    def __init__(self, name):
+        self.name = name
+        self.history = {}
+        self.events = {}
+
+
+class BlinkSampler(object):
+    def __init__(self, model, device=0, msg_f64=False, cap_scale=1.0,
+            validate=False, max_warps=0):
+        self.lib = _lib.load()
+        self.pm = model if isinstance(model, PackedModel) else PackedModel(model)
+        self._h = C.c_void_p()
+        desc = self.pm.desc(msg_f64=msg_f64, cap_scale=cap_scale,
+                validate=validate, max_warps=max_warps)
+        rc = self.lib.nxb_create(C.byref(desc), int(device), C.byref(self._h))
+        if rc:
+            msg = self.lib.nxb_last_error(None).decode()
+            self._h = None
+            raise NxbError(rc, msg)
+        self.layout = _lib.SummaryLayout()
+        self._check(self.lib.nxb_summary_layout_get(self._h, C.byref(self.layout)))
+        self.data = None
+        self.chains = 0
+        self.n_units = 0
+
+    def _check(self, rc):
+        if rc:
+            raise NxbError(rc, self.lib.nxb_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.nxb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    def set_data(self, data):
+        """``data``: PackedData, or a sequence of reference-style data objects."""
+        if not isinstance(data, PackedData):
+            data = pack_data(self.pm, list(data))
+        self.data = data
+        self._check(self.lib.nxb_set_data(self._h, data.n_sites,
+            data.pri_ok.ctypes.data, data.tol_true_ok.ctypes.data,
+            data.tol_false_ok.ctypes.data))
+
+    def init_chains(self, chains=1, seed=0, unit_offset=0):
+        self._check(self.lib.nxb_init_chains(self._h, int(chains), int(seed),
+            int(unit_offset)))
+        self.chains = int(chains)
+        self.n_units = self.data.n_sites * self.chains
+
+    def sweep(self, n_sweeps=1, accumulate=True):
+        self._check(self.lib.nxb_sweep(self._h, int(n_sweeps), 1 if accumulate else 0))
+
+    def reset_summary(self):
+        self._check(self.lib.nxb_summary_reset(self._h))
+
+    def summarize_current(self):
+        self._check(self.lib.nxb_summarize_current(self._h))
+
+    def read_summary(self):
+        counts = np.zeros(self.layout.n_counts, dtype=np.uint64)
+        dwell = np.zeros(self.layout.n_dwell, dtype=np.float64)
+        self._check(self.lib.nxb_summary_read(self._h, counts.ctypes.data, dwell.ctypes.data))
+        return counts, dwell
+
+    def summary_device_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.nxb_summary_device_ptrs(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def summary(self, counts=None, dwell=None, Q_primary=None):
+        if counts is None:
+            counts, dwell = self.read_summary()
+        return Summary.from_device(self.pm, self.layout, counts, dwell, Q_primary)
+
+    def stats(self):
+        st = _lib.Stats()
+        self._check(self.lib.nxb_get_stats(self._h, C.byref(st)))
+        return dict((f, getattr(st, f)) for f, _ in st._fields_)
+
+    def last_kernel_ms(self):
+        ms, n = C.c_float(), C.c_int32()
+        self._check(self.lib.nxb_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # ------------------------------------------------------------------
+    def export_unit(self, unit, cap=4096):
+        """Raw integer-indexed trajectory of one unit."""
+        N = self.pm.n_nodes
+        node_pri = np.zeros(N, dtype=np.int32)
+        node_tol = np.zeros(N, dtype=np.uint32)
+        n_pri, n_blk = C.c_int32(), C.c_int32()
+        pt = np.zeros(cap); pe = np.zeros(cap, np.int32)
+        psa = np.zeros(cap, np.int32); psb = np.zeros(cap, np.int32)
+        bt = np.zeros(cap); be = np.zeros(cap, np.int32)
+        bk = np.zeros(cap, np.int32); bs = np.zeros(cap, np.int32)
+        self._check(self.lib.nxb_export_unit(self._h, int(unit),
+            node_pri.ctypes.data, node_tol.ctypes.data, cap,
+            C.addressof(n_pri), pt.ctypes.data, pe.ctypes.data, psa.ctypes.data,
+            psb.ctypes.data, C.addressof(n_blk), bt.ctypes.data, be.ctypes.data,
+            bk.ctypes.data, bs.ctypes.data))
+        a, b = n_pri.value, n_blk.value
+        return dict(node_pri=node_pri, node_tol=node_tol,
+                pri=(pt[:a], pe[:a], psa[:a], psb[:a]),
+                blk=(bt[:b], be[:b], bk[:b], bs[:b]))
+
+    def export_tracks(self, unit):
+        """(primary_track, tolerance_tracks) in the reference's object format
+        (what nxblink/raoteh.py:435 yields)."""
+        pm = self.pm
+        raw = self.export_unit(unit)
+        pri = Track('PRIMARY')
+        tols = [Track(name) for name in pm.tols]
+        for v, node in enumerate(pm.nodes):
+            pri.history[node] = pm.states[raw['node_pri'][v]]
+            for k, t in enumerate(tols):
+                t.history[node] = bool((int(raw['node_tol'][v]) >> k) & 1)
+        for edge in pm.edges:
+            pri.events[edge] = []
+            for t in tols:
+                t.events[edge] = []
+        for tm, e, sa, sb in zip(*raw['pri']):
+            pri.events[pm.edges[e]].append(
+                    Event(pri, float(tm), pm.states[sa], pm.states[sb]))
+        for tm, e, k, ns in zip(*raw['blk']):
+            t = tols[k]
+            t.events[pm.edges[e]].append(Event(t, float(tm), not bool(ns), bool(ns)))
+        return pri, tols
