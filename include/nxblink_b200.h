@@ -118,6 +118,12 @@ int nxb_get_stats(nxb_handle* h, nxb_stats* out);
 /* Last sweep-kernel launch times (ms, CUDA events on the launching stream). */
 int nxb_last_kernel_ms(nxb_handle* h, float* total_ms, int32_t* n_launches);
 
+/* Per-phase cycle counters of the sweep kernel (lane 0 of every warp, summed):
+ * load, P0..P5 (primary update), B0..B2 + write-back (tolerance updates), store.
+ * `enable` switches collection on/off; if cycles12 is non-NULL the 12 counters are
+ * copied out and cleared.  Diagnostic only. */
+int nxb_profile(nxb_handle* h, int32_t enable, uint64_t* cycles12);
+
 /* Known-answer hook for the counter-based generator (host code path). */
 void nxb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

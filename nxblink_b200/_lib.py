@@ -61,7 +61,7 @@ EXPORTS = (
     'nxb_set_data', 'nxb_init_chains', 'nxb_sweep', 'nxb_summary_layout_get',
     'nxb_summary_reset', 'nxb_summary_read', 'nxb_summary_device_ptrs',
     'nxb_summarize_current', 'nxb_export_unit', 'nxb_get_stats',
-    'nxb_last_kernel_ms', 'nxb_philox4x32_10',
+    'nxb_last_kernel_ms', 'nxb_profile', 'nxb_philox4x32_10',
 )
 
 _lib = None
@@ -95,6 +95,7 @@ def load():
     lib.nxb_export_unit.argtypes = [H, C.c_int64] + [C.c_void_p] * 2 + [C.c_int32] + [C.c_void_p] * 10
     lib.nxb_get_stats.argtypes = [H, C.POINTER(Stats)]
     lib.nxb_last_kernel_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    lib.nxb_profile.argtypes = [H, C.c_int32, C.c_void_p]
     lib.nxb_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nxb_philox4x32_10.restype = None
     for name in EXPORTS:

@@ -76,6 +76,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     c.k1 = (unsigned)(p.seed >> 32);
     const int N = ml.N;
     const long long n_work = p.unit_list ? (long long)p.n_list : p.n_units;
+    c.t_last = clock64();
 
     while (true) {
         unsigned long long widx = 0;
@@ -116,6 +117,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             }
             __syncwarp();
         }
+        tick(c, T_LOAD);
         bool spilled = false;
         while (rc == RC_OK && (hdr.phase == NXB_PHASE_INIT || hdr.sweeps_done < p.target_sweeps)) {
             if (hdr.phase == NXB_PHASE_INIT) {
@@ -174,6 +176,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             if (rc == RC_DEFER && lane == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)u;
             __syncwarp();
         }
+        tick(c, T_STORE);
     }
     __syncthreads();
     // ---- flush the CTA's statistic partials ----
@@ -327,7 +330,10 @@ struct nxb_handle {
     int validate = 0;
     NxbModelLayout ml;
     NxbSummaryLayout sl;
-    std::vector<Tier> tiers;
+    std::vector<Tier> tiers;        // steady-state sweeps
+    std::vector<Tier> init_tiers;   // initial trajectories (raoteh.py:337-361) hold far more events
+    unsigned long long* d_perf = nullptr;
+    int profile = 0;
     int gcapP = 0, gcapB = 0;
     int so_tol = 0, so_pri = 0, so_ptm = 0, so_pcode = 0, so_btm = 0, so_bcode = 0;
     long long stride = 0;
@@ -660,6 +666,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     CUDA_TRY_C(cudaMalloc(&h->d_work, 8));
     CUDA_TRY_C(cudaMalloc(&h->d_defer_count, 4));
     CUDA_TRY_C(cudaMalloc(&h->d_scratch, 64));
+    CUDA_TRY_C(cudaMalloc(&h->d_perf, 16 * 8));
+    CUDA_TRY_C(cudaMemset(h->d_perf, 0, 16 * 8));
 
     // ---- capacity tiers ----
     {
@@ -684,21 +692,29 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         const int fixed = ml.bytes + stats_bytes;
         const int max_warps = (d->max_warps > 0) ? std::min(d->max_warps, NXB_MAX_THREADS / 32)
                                                  : NXB_MAX_THREADS / 32;
-        for (int t = 0; t < 8; ++t) {
-            Tier tier;
-            const int f = 1 << t;
-            int init_f = std::max(capF * f, E * d->diameter + 8);   // init pass: diameter events per edge
-            int init_r = std::max(capR * f, E * d->diameter + 8);
-            build_warp_layout(ml, h->msg_f64, std::min(capP * f, h->gcapP), std::min(capB * f, h->gcapB),
-                              init_r, init_f, capC * f, &tier.wl);
-            tier.smem_warp0 = fixed;
-            int w = (h->max_smem - fixed) / tier.wl.bytes;
-            if (w < 1) break;
-            tier.warps = std::min(w, max_warps);
-            tier.smem = (size_t)fixed + (size_t)tier.warps * tier.wl.bytes;
-            h->tiers.push_back(tier);
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int t = 0; t < 8; ++t) {
+                Tier tier;
+                const int f = 1 << t;
+                int cP = capP * f, cB = capB * f, cR = capR * f, cF = capF * f, cC = capC * f;
+                if (pass == 1) {
+                    // init pass: `diameter` forced events on every edge, all of which may
+                    // survive; up to two blink events per (track, edge)
+                    cF = std::max(cF, E * d->diameter + 8);
+                    cR = std::max(cR, E * d->diameter + 8);
+                    cP = std::max(cP, std::min(E * d->diameter + 8, 4 * capP + 32));
+                }
+                build_warp_layout(ml, h->msg_f64, std::min(cP, h->gcapP), std::min(cB, h->gcapB),
+                                  cR, cF, cC, &tier.wl);
+                tier.smem_warp0 = fixed;
+                int w = (h->max_smem - fixed) / tier.wl.bytes;
+                if (w < 1) break;
+                tier.warps = std::min(w, max_warps);
+                tier.smem = (size_t)fixed + (size_t)tier.warps * tier.wl.bytes;
+                (pass == 0 ? h->tiers : h->init_tiers).push_back(tier);
+            }
         }
-        if (h->tiers.empty()) {
+        if (h->tiers.empty() || h->init_tiers.empty()) {
             set_err(nullptr, NXB_ERR_BAD_ARG, "model too large: one unit does not fit in shared memory");
             nxb_destroy(h); return NXB_ERR_BAD_ARG;
         }
@@ -733,7 +749,7 @@ extern "C" int nxb_destroy(nxb_handle* h) {
     cudaFree(h->d_blob); cudaFree(h->d_rmax); cudaFree(h->d_pri_ok); cudaFree(h->d_tt); cudaFree(h->d_tf);
     cudaFree(h->d_state); cudaFree(h->d_counts); cudaFree(h->d_dwell); cudaFree(h->d_status);
     cudaFree(h->d_work); cudaFree(h->d_defer[0]); cudaFree(h->d_defer[1]); cudaFree(h->d_defer_count);
-    cudaFree(h->d_scratch);
+    cudaFree(h->d_scratch); cudaFree(h->d_perf);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -778,8 +794,9 @@ static int run_tiers(nxb_handle* h, unsigned target, unsigned accum_from, int in
     const int* list = nullptr;
     int n_list = 0;
     h->last_ms = 0.f; h->last_launches = 0;
-    for (size_t t = 0; t < h->tiers.size(); ++t) {
-        const Tier& tier = h->tiers[t];
+    const std::vector<Tier>& tiers = init ? h->init_tiers : h->tiers;
+    for (size_t t = 0; t < tiers.size(); ++t) {
+        const Tier& tier = tiers[t];
         NxbSweepParams p;
         memset(&p, 0, sizeof(p));
         p.ml = h->ml; p.wl = tier.wl; p.sl = h->sl;
@@ -798,6 +815,7 @@ static int run_tiers(nxb_handle* h, unsigned target, unsigned accum_from, int in
         p.validate = h->validate;
         p.counts = h->d_counts; p.dwell = h->d_dwell; p.status = h->d_status;
         p.work_counter = h->d_work;
+        p.perf = h->profile ? h->d_perf : nullptr;
         CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
         CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
         const long long n_work = list ? n_list : h->n_units;
@@ -970,5 +988,16 @@ extern "C" int nxb_last_kernel_ms(nxb_handle* h, float* ms, int32_t* n) {
     if (!h) return NXB_ERR_BAD_ARG;
     if (ms) *ms = h->last_ms;
     if (n) *n = h->last_launches;
+    return NXB_OK;
+}
+
+extern "C" int nxb_profile(nxb_handle* h, int32_t enable, uint64_t* cycles12) {
+    if (!h) return NXB_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (cycles12) {
+        CUDA_TRY(h, cudaMemcpy(cycles12, h->d_perf, 12 * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(h, cudaMemset(h->d_perf, 0, 16 * 8));
+    }
+    h->profile = enable;
     return NXB_OK;
 }

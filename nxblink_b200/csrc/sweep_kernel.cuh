@@ -62,7 +62,19 @@ struct Ctx {
     // rng
     unsigned k0, k1, unit32, sweep;
     long long unit;       // local unit index
+    // phase timers (cycles, lane 0)
+    long long t_last;
 };
+
+enum { T_LOAD = 0, T_P0, T_P1, T_P2, T_P3, T_P4, T_P5, T_B0, T_B1, T_B2, T_BW, T_STORE };
+
+__device__ __forceinline__ void tick(Ctx& c, int which) {
+    if (c.p->perf) {
+        long long now = clock64();
+        if (c.lane == 0) atomicAdd(c.p->perf + which, (unsigned long long)(now - c.t_last));
+        c.t_last = now;
+    }
+}
 
 __device__ __forceinline__ NxbU4 rng(const Ctx& c, unsigned stream, unsigned block) {
     return nxb_philox4x32_10(c.unit32, c.sweep, stream, block, c.k0, c.k1);
@@ -240,6 +252,7 @@ __device__ int primary_phase(Ctx& c, bool init, bool accumulate) {
     }
     __syncwarp();
     build_poff(c);   // uses tmpa
+    tick(c, T_P0);
 
     // ---- P1: candidates by thinning, merged walk, foreground event regions ------
     int run = 0;
@@ -333,6 +346,7 @@ __device__ int primary_phase(Ctx& c, bool init, bool accumulate) {
     }
     if (F > wl.capF) return RC_DEFER;
     __syncwarp();
+    tick(c, T_P1);
     for (int e = lane; e < E; e += 32) {
         int src = rbase[e], dst = foff[e], m = mE[e];
         for (int i = 0; i < m; ++i) {
@@ -400,6 +414,7 @@ __device__ int primary_phase(Ctx& c, bool init, bool accumulate) {
         for (int k = 0; k < K; ++k) if ((tm >> k) & 1u) ok |= c.clsmask[k];
         callow[j] &= ok;
     }
+    tick(c, T_P2);
     // ---- P3: upward pass over the chunk tree ------------------------------------------
     for (int i = lane; i < (F + 1) * NXB_PPAD; i += 32) msg[i] = (MSG)1.0;
     __syncwarp();
@@ -440,6 +455,7 @@ __device__ int primary_phase(Ctx& c, bool init, bool accumulate) {
         }
         __syncwarp();
     }
+    tick(c, T_P3);
     // ---- P4: root draw and downward sampling ----------------------------------------------
     {
         const unsigned long long allow = callow[0];
@@ -481,6 +497,7 @@ __device__ int primary_phase(Ctx& c, bool init, bool accumulate) {
         if (lane == 0) cstate[ci] = (unsigned char)bsel;
         __syncwarp();
     }
+    tick(c, T_P4);
     // ---- P5: write back, dropping self transitions (raoteh.py:411) ------------------------------
     int nkeep = 0;
     for (int b = 0; b < F; b += 32) {
@@ -527,6 +544,7 @@ __device__ int primary_phase(Ctx& c, bool init, bool accumulate) {
         }
         if (lane == 0) atomicAdd(&c.s_root_pri[c.node_pri[0]], 1ull);
     }
+    tick(c, T_P5);
     return RC_OK;
 }
 
@@ -604,6 +622,7 @@ __device__ int blink_phase(Ctx& c, bool accumulate) {
     }
     if (lane == 0) toff[K] = run;
     __syncwarp();
+    tick(c, T_B0);
 
     const bool trk = lane < K;
     const int k = trk ? lane : 0;
@@ -693,6 +712,7 @@ __device__ int blink_phase(Ctx& c, bool accumulate) {
         }
     }
     __syncwarp();
+    tick(c, T_B1);
     // ---- root draw (prior: toymodel.py:17-27 get_blink_distn) ----------------------------------------
     unsigned x = 0u;
     if (trk) {
@@ -776,6 +796,7 @@ __device__ int blink_phase(Ctx& c, bool accumulate) {
     }
     if (__any_sync(FULL, rc_lane)) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
 
+    tick(c, T_B2);
     // ---- write back: new retained blink events, (track, edge, time) order -----------------------------
     int n_mine = trk ? (w - t_lo) : 0, total;
     int dst = warp_excl_scan(n_mine, lane, total);
@@ -811,6 +832,7 @@ __device__ int blink_phase(Ctx& c, bool accumulate) {
     }
     c.nB = total;
     __syncwarp();
+    tick(c, T_BW);
     return RC_OK;
 }
 

@@ -123,6 +123,16 @@ class BlinkSampler(object):
         self._check(self.lib.nxb_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    PHASES = ('load', 'P0 edge-major view', 'P1 candidates', 'P2 chunks', 'P3 upward',
+            'P4 downward', 'P5 writeback+stats', 'B0 pool', 'B1 upward', 'B2 downward+stats',
+            'BW writeback', 'store')
+
+    def profile(self, enable=True):
+        """Switch the per-phase cycle counters on/off; returns the counters so far."""
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(self.lib.nxb_profile(self._h, 1 if enable else 0, out.ctypes.data))
+        return dict(zip(self.PHASES, out.tolist()))
+
     # ------------------------------------------------------------------
     def export_unit(self, unit, cap=4096):
         """Raw integer-indexed trajectory of one unit."""

@@ -1,0 +1,96 @@
+"""Determinism and partition invariance of the CUDA sweep.
+
+Random streams are keyed by (seed, global unit, sweep, stream, block), so integer
+statistics must be bit-identical regardless of launch geometry, shared-memory
+capacity tier (deferral path), message precision of the blink path, or how units
+are sharded over handles.  Dwell sums are fp64
+atomics: equal up to summation order (rtol 1e-11)."""
+import numpy as np
+import pytest
+
+from nxblink_b200 import toymodel, toydata, p53, packing
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(nb, model, data, chains=64, seed=5, sweeps=6, unit_offset=0, **kw):
+    s = nb.BlinkSampler(model, **kw)
+    s.set_data(data)
+    s.init_chains(chains=chains, seed=seed, unit_offset=unit_offset)
+    s.sweep(3, accumulate=False)
+    s.sweep(sweeps, accumulate=True)
+    c, d = s.read_summary()
+    st = s.stats()
+    s.close()
+    return c, d, st
+
+
+def _p53_inputs(n_sites):
+    m = p53.p53_model()
+    pm = packing.PackedModel(m)
+    leaf = pm.node_index[m.name_to_leaf['Has']]
+    ls, tt, tf = p53.synthetic_alignment(pm, n_sites, seed=0, reference_leaf=leaf)
+    return pm, packing.pack_alignment(pm, ls, tt, tf)
+
+
+def test_same_seed_same_result(nb):
+    a = _run(nb, toymodel.BlinkModelB, [toydata.DataC] * 4)
+    b = _run(nb, toymodel.BlinkModelB, [toydata.DataC] * 4)
+    assert (a[0] == b[0]).all()
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-11, atol=1e-9)
+    c = _run(nb, toymodel.BlinkModelB, [toydata.DataC] * 4, seed=6)
+    assert (a[0] != c[0]).any()
+
+
+def test_capacity_tiers_and_geometry_do_not_change_results(nb):
+    pm, data = _p53_inputs(24)
+    base = _run(nb, pm, data, chains=8, validate=True)
+    assert base[0][-1] == 24 * 8 * 6                     # nsamples
+    small = _run(nb, pm, data, chains=8, cap_scale=0.55)  # forces the deferral path
+    assert small[2]['deferred_units'] > 0
+    few = _run(nb, pm, data, chains=8, max_warps=3)
+    for other in (small, few):
+        assert (base[0] == other[0]).all()
+        np.testing.assert_allclose(base[1], other[1], rtol=1e-11, atol=1e-9)
+        assert base[2]['n_blk_events'] == other[2]['n_blk_events']
+        assert base[2]['n_pri_events'] == other[2]['n_pri_events']
+
+
+def test_sharding_over_handles_is_invisible(nb):
+    """Two handles with half the sites each (unit_offset = first global unit) give
+    the same integer statistics as one handle with all sites."""
+    pm, data = _p53_inputs(16)
+    chains = 4
+    whole = _run(nb, pm, data, chains=chains)
+    lo = packing.PackedData(data.pri_ok[:8], data.tol_true_ok[:8], data.tol_false_ok[:8])
+    hi = packing.PackedData(data.pri_ok[8:], data.tol_true_ok[8:], data.tol_false_ok[8:])
+    a = _run(nb, pm, lo, chains=chains, unit_offset=0)
+    b = _run(nb, pm, hi, chains=chains, unit_offset=8 * chains)
+    assert (whole[0] == a[0] + b[0]).all()
+    np.testing.assert_allclose(whole[1], a[1] + b[1], rtol=1e-11, atol=1e-9)
+
+
+def test_conservation_properties_at_scale(nb):
+    """Size-independent properties on a large batch: total dwell per edge equals
+    branch length x samples; root ON + OFF = K x samples; blink on/off transition
+    counts balance against the endpoint states."""
+    pm, data = _p53_inputs(512)
+    s = nb.BlinkSampler(pm)
+    s.set_data(data)
+    s.init_chains(chains=32, seed=9)
+    s.sweep(2, accumulate=False)
+    s.sweep(3, accumulate=True)
+    sm = s.summary()
+    n = sm.nsamples
+    assert n == 512 * 32 * 3
+    E, K = pm.n_nodes - 1, pm.n_classes
+    np.testing.assert_allclose(sm.flat['T'].sum(axis=1), pm.blen[1:] * n, rtol=1e-10)
+    assert sm.root_on_total + sm.root_off_count == K * n
+    assert sum(sm.root_pri_to_count.values()) == n
+    tot = sm.flat['off_xon_dwell'] + sm.flat['xon_off_dwell']
+    np.testing.assert_allclose(tot, (K - 1) * pm.blen[1:] * n, rtol=1e-10)
+    assert (sm.flat['Doff'] >= 0).all() and (sm.flat['pri_dwell'] >= -1e-9).all()
+    st = s.stats()
+    R = (st['n_pri_events'] + st['n_blk_events']) / st['n_units']
+    assert 60 < R < 160          # ~84-121 retained events at the p53 shape
+    s.close()
