@@ -294,7 +294,10 @@ def run_gpu_arm(args, rank, local_rank, world):
         except Exception:
             pass
         cores = os.cpu_count() or 1
-        cpu_val, cpu_wall = cpu_site_sweeps_per_sec(cores, 1, args.cpu_sweeps)
+        if args.cpu_sweeps > 0:
+            cpu_val, cpu_wall = cpu_site_sweeps_per_sec(cores, 1, args.cpu_sweeps)
+        else:
+            cpu_val, cpu_wall = None, 0.0
         R = (st1['n_pri_events'] + st1['n_blk_events']) / st1['n_units']
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
