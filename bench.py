@@ -290,7 +290,9 @@ def run_gpu_arm(args, rank, local_rank, world):
         traffic = None
         try:
             with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-                traffic = json.load(f).get('dram_bytes_per_launch')
+                # ncu capture (one launch at a smaller batch) -> bytes per unit-sweep,
+                # scaled to the units one timed launch processes
+                traffic = json.load(f)['dram_bytes_per_unit_sweep'] * n_units * args.steps / max(launches, 1)
         except Exception:
             pass
         cores = os.cpu_count() or 1
