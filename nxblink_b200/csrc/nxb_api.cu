@@ -119,33 +119,30 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
         }
         tick(c, T_LOAD);
         bool spilled = false;
+        // one phase per iteration, so that every phase function has a single call site
+        // (the kernel is much larger than the instruction cache)
         while (rc == RC_OK && (hdr.phase == NXB_PHASE_INIT || hdr.sweeps_done < p.target_sweeps)) {
-            if (hdr.phase == NXB_PHASE_INIT) {
-                c.sweep = NXB_SWEEP_INIT;
+            const bool init = hdr.phase == NXB_PHASE_INIT;
+            c.sweep = init ? NXB_SWEEP_INIT : hdr.sweeps_done;
+            const bool accum = !init && hdr.sweeps_done >= p.accum_from;
+            if (init) {
                 rc = init_blink(c);
                 if (rc) break;
-                rc = primary_phase<MSG>(c, true, false);
-                if (rc) break;
-                hdr.phase = NXB_PHASE_PRIMARY;
-                if (p.validate) rc = validate_unit(c);
-                continue;
             }
-            c.sweep = hdr.sweeps_done;
-            const bool accum = hdr.sweeps_done >= p.accum_from;
-            if (hdr.phase == NXB_PHASE_PRIMARY) {
-                rc = primary_phase<MSG>(c, false, accum);
+            if (hdr.phase != NXB_PHASE_BLINK) {
+                rc = primary_phase<MSG>(c, init, accum);
                 if (rc) break;
-                hdr.phase = NXB_PHASE_BLINK;
-                if (p.validate) { rc = validate_unit(c); if (rc) break; }
-            }
-            rc = blink_phase(c, accum);
-            if (rc == RC_DEFER && c.nB < 0) {     // sweep complete, blink list spilled to HBM
+                hdr.phase = init ? NXB_PHASE_PRIMARY : NXB_PHASE_BLINK;
+            } else {
+                rc = blink_phase(c, accum);
+                if (rc == RC_DEFER && c.nB < 0) {     // sweep complete, blink list spilled to HBM
+                    hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
+                    spilled = true;
+                    break;
+                }
+                if (rc) break;
                 hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
-                spilled = true;
-                break;
             }
-            if (rc) break;
-            hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
             if (p.validate) rc = validate_unit(c);
         }
         if (rc == RC_ERROR) continue;

@@ -76,11 +76,17 @@ __device__ __forceinline__ void tick(Ctx& c, int which) {
     }
 }
 
+// One out-of-line copy: the sweep kernel is far larger than the instruction cache, so
+// code size (not call overhead) is what matters for the helpers below.
+__device__ __noinline__ NxbU4 philox_call(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                          unsigned k0, unsigned k1) {
+    return nxb_philox4x32_10(c0, c1, c2, c3, k0, k1);
+}
 __device__ __forceinline__ NxbU4 rng(const Ctx& c, unsigned stream, unsigned block) {
-    return nxb_philox4x32_10(c.unit32, c.sweep, stream, block, c.k0, c.k1);
+    return philox_call(c.unit32, c.sweep, stream, block, c.k0, c.k1);
 }
 
-__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
+__device__ __noinline__ int warp_excl_scan(int v, int lane, int& total) {
     int x = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -111,7 +117,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Draw an index from 64 non-negative weights, two per lane (items lane, lane+32).
 // Returns -1 if all weights are zero.  u in (0,1).
-__device__ __forceinline__ int warp_sample64(double w_lo, double w_hi, double u, int lane) {
+__device__ __noinline__ int warp_sample64(double w_lo, double w_hi, double u, int lane) {
     double s_lo = warp_incl_scan(w_lo, lane);
     double tot_lo = __shfl_sync(FULL, s_lo, 31);
     double s_hi = warp_incl_scan(w_hi, lane) + tot_lo;
@@ -129,7 +135,7 @@ __device__ __forceinline__ int warp_sample64(double w_lo, double w_hi, double u,
     return 31 - __clz(p_lo);
 }
 
-__device__ __forceinline__ int poisson_inv(double u, double p0, double lam) {
+__device__ __noinline__ int poisson_inv(double u, double p0, double lam) {
     int n = 0;
     double pr = p0, cdf = p0;
     while (u > cdf && n < 1000) {
@@ -150,12 +156,23 @@ __device__ __forceinline__ double rsum_masked(const Ctx& c, int s, unsigned mask
     return acc;
 }
 
+// fallback when K is too large for the 2^K table
+__device__ __noinline__ double rmax_compute(const unsigned short* qptr, const unsigned short* qinfo,
+                                            const double* qval, int P, unsigned mask) {
+    double m = 0.0;
+    for (int s = 0; s < P; ++s) {
+        double acc = 0.0;
+        for (int idx = qptr[s]; idx < qptr[s + 1]; ++idx)
+            if ((mask >> (qinfo[idx] >> 8)) & 1u) acc += qval[idx];
+        m = fmax(m, acc);
+    }
+    return m;
+}
+
 // max over ALL source states (poisson.py:88-90 / util.py:13-17)
 __device__ __forceinline__ double rmax_lookup(const Ctx& c, unsigned mask) {
     if (c.p->rmax_tab) return __ldg(c.p->rmax_tab + mask);
-    double m = 0.0;
-    for (int s = 0; s < c.P; ++s) m = fmax(m, rsum_masked(c, s, mask));
-    return m;
+    return rmax_compute(c.qptr, c.qinfo, c.qval, c.P, mask);
 }
 
 __device__ __forceinline__ void fail(const Ctx& c, int code, int detail) {
@@ -173,7 +190,7 @@ __device__ __forceinline__ void fail(const Ctx& c, int code, int detail) {
 // ---------------------------------------------------------------------------
 
 // poff[e] = first retained primary event on edge e (events are sorted by edge, time)
-__device__ void build_poff(Ctx& c) {
+__device__ __forceinline__ void build_poff(Ctx& c) {
     const int E = c.E, lane = c.lane;
     for (int e = lane; e <= E; e += 32) c.tmpa[e] = 0;
     __syncwarp();
@@ -195,7 +212,7 @@ __device__ void build_poff(Ctx& c) {
 // PRIMARY TRACK UPDATE  (raoteh.py:394-411; init: raoteh.py:350-361)
 // ---------------------------------------------------------------------------
 template <typename MSG>
-__device__ int primary_phase(Ctx& c, bool init, bool accumulate) {
+__device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate) {
     const NxbSweepParams& p = *c.p;
     const NxbWarpLayout& wl = p.wl;
     const int E = c.E, N = c.N, P = c.P, K = c.K, lane = c.lane;
@@ -551,7 +568,7 @@ __device__ int primary_phase(Ctx& c, bool init, bool accumulate) {
 // ---------------------------------------------------------------------------
 // TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, lane k = track k
 // ---------------------------------------------------------------------------
-__device__ int blink_phase(Ctx& c, bool accumulate) {
+__device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     const NxbSweepParams& p = *c.p;
     const NxbWarpLayout& wl = p.wl;
     const NxbModelLayout& ml = p.ml;
@@ -839,7 +856,7 @@ __device__ int blink_phase(Ctx& c, bool accumulate) {
 // ---------------------------------------------------------------------------
 // initial tolerance histories  (raoteh.py:187-229)
 // ---------------------------------------------------------------------------
-__device__ int init_blink(Ctx& c) {
+__device__ __forceinline__ int init_blink(Ctx& c) {
     const int E = c.E, N = c.N, K = c.K, lane = c.lane;
     const unsigned ALLK = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
     int bad = 0;
@@ -887,7 +904,7 @@ __device__ int init_blink(Ctx& c) {
 // trajectory invariants (the checks of navigation.py:39-44,121-135, chunking.py:96-100,
 // summary.py:243, plus the model constraints of nxblink/compound.py:23-40)
 // ---------------------------------------------------------------------------
-__device__ int validate_unit(Ctx& c) {
+__device__ __forceinline__ int validate_unit(Ctx& c) {
     const int E = c.E, N = c.N, K = c.K, lane = c.lane;
     unsigned short* bord = (unsigned short*)(c.wbase + c.p->wl.off_bord);
     int bad = 0;
