@@ -51,6 +51,8 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     c.pi = (const double*)(smem + ml.off_pi);
     c.qm = (const double*)(smem + ml.off_qm);
     c.clsmask = (const unsigned long long*)(smem + ml.off_clsmask);
+    c.ell_info = smem + ml.off_ell_info;
+    c.ell_q = smem + ml.off_ell_q;
     c.s_off_on = stats;
     c.s_on_off = stats + ml.E;
     c.s_root_pri = stats + 2 * ml.E;
@@ -414,13 +416,14 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     wl->off_callow = take(8 * (capF + 1), 8);
     wl->off_cstate = take(capF + 1, 1);
     wl->off_msg = take((msg_f64 ? 8 : 4) * (capF + 1) * NXB_PPAD, 16);
+    wl->off_finv = take((msg_f64 ? 8 : 4) * capF, 8);
+    wl->off_fu = take(8 * (capF + 1), 8);
     const int end_pri = o;
     // blink-phase scratch (aliases the primary-phase scratch)
     o = scratch0;
     wl->off_ctm = take(8 * capC, 8);
     wl->off_cell = take(4 * capC, 4);
     wl->off_cedge = take(2 * capC, 2);
-    wl->off_cflag = take(capC, 1);
     wl->off_toff = take(4 * (K + 1), 4);
     wl->off_acc = take(8 * 3 * K * ml.nslots, 8);
     wl->off_newtol = take(4 * N, 4);
@@ -449,7 +452,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     if (!d || !out) return set_err(nullptr, NXB_ERR_BAD_ARG, "null argument");
     *out = nullptr;
     const int N = d->n_nodes, P = d->n_states, K = d->n_classes, nnz = d->nnz, E = N - 1;
-    if (N < 2 || N > 65535) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 2 <= n_nodes <= 65535");
+    if (N < 2 || N > 16384) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 2 <= n_nodes <= 16384");
     if (P < 1 || P > NXB_MAX_STATES) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 1 <= n_states <= 64");
     if (K < 1 || K > NXB_MAX_CLASSES) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 1 <= n_classes <= 32");
     if (!(d->rate_on > 0.0) || !(d->rate_off > 0.0))
@@ -465,8 +468,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     for (int s = 0; s < P; ++s) {
         if (d->state_class[s] < 0 || d->state_class[s] >= K)
             return set_err(nullptr, NXB_ERR_BAD_ARG, "state_class out of range");
-        if (d->q_ptr[s + 1] - d->q_ptr[s] > 63)
-            return set_err(nullptr, NXB_ERR_BAD_ARG, "at most 63 transitions per primary state");
+        if (d->q_ptr[s + 1] - d->q_ptr[s] > 31)
+            return set_err(nullptr, NXB_ERR_BAD_ARG, "at most 31 transitions per primary state");
         for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i) {
             if (d->q_col[i] < 0 || d->q_col[i] >= P || d->q_col[i] == s || !(d->q_val[i] > 0.0))
                 return set_err(nullptr, NXB_ERR_BAD_ARG, "bad primary rate matrix entry");
@@ -603,6 +606,27 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         std::vector<unsigned long long> clsmask(K, 0ull);
         for (int s = 0; s < P; ++s) clsmask[d->state_class[s]] |= 1ull << s;
         ml.off_clsmask = put(clsmask.data(), 8 * K, 8);
+        // transposed ELL copy of Q for the branch-free mat-vec: [w][row], padded rows/entries 0
+        int W = 1;
+        for (int s = 0; s < P; ++s) W = std::max(W, d->q_ptr[s + 1] - d->q_ptr[s]);
+        ml.ell_w = W;
+        std::vector<unsigned short> ell_info((size_t)W * NXB_PPAD, 0);
+        std::vector<float> ell_q32((size_t)W * NXB_PPAD, 0.f);
+        std::vector<double> ell_q64((size_t)W * NXB_PPAD, 0.0);
+        for (int s = 0; s < NXB_PPAD; ++s)
+            for (int w = 0; w < W; ++w) {
+                const size_t o = (size_t)w * NXB_PPAD + s;
+                ell_info[o] = (unsigned short)(s < P ? s : 0);     // padding: self, rate 0
+                if (s < P && d->q_ptr[s] + w < d->q_ptr[s + 1]) {
+                    const int i = d->q_ptr[s] + w;
+                    ell_info[o] = qinfo[i];
+                    ell_q32[o] = (float)d->q_val[i];
+                    ell_q64[o] = d->q_val[i];
+                }
+            }
+        ml.off_ell_info = put(ell_info.data(), 2 * W * NXB_PPAD, 2);
+        ml.off_ell_q = h->msg_f64 ? put(ell_q64.data(), 8 * W * NXB_PPAD, 8)
+                                  : put(ell_q32.data(), 4 * W * NXB_PPAD, 8);
         blob.resize(align_up((int)blob.size(), 16));
         ml.bytes = (int)blob.size();
         ml.off_stats = ml.bytes;

@@ -58,6 +58,9 @@ struct NxbModelLayout {
     int off_pi;         // f64    [P]
     int off_qm;         // f64    [P*K] dense Q_meta (model.py:93-106)
     int off_clsmask;    // u64    [K]   states belonging to class k
+    int ell_w;          // padded row width of the ELL copy of Q (max out-degree)
+    int off_ell_info;   // u16    [ell_w*64] column | class << 8, transposed: [w][row]
+    int off_ell_q;      // f32 or f64 (message type) [ell_w*64] rates, 0 in the padding
     int bytes;
     double rate_on, rate_off;
     double inv_omega_pri;   // 1 / (2 * Rmax(all classes on))
@@ -79,9 +82,10 @@ struct NxbWarpLayout {
     int off_boff, off_poff, off_tmpa, off_tmpb, off_tmpc;
     // primary-phase scratch
     int off_bord, off_rtm, off_rmask, off_ftm, off_fmask, off_fedge,
-        off_nchunk, off_jump, off_par, off_toland, off_callow, off_cstate, off_msg;
+        off_nchunk, off_jump, off_par, off_toland, off_callow, off_cstate, off_msg,
+        off_finv, off_fu;
     // blink-phase scratch
-    int off_ctm, off_cell, off_cedge, off_cflag, off_toff, off_acc, off_newtol;
+    int off_ctm, off_cell, off_cedge, off_toff, off_acc, off_newtol;
     int bytes;
 };
 

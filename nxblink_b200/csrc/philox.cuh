@@ -51,10 +51,25 @@ NXB_HD double nxb_u32(uint32_t x) {
     return ((double)x + 0.5) * (1.0 / 4294967296.0);
 }
 
+// xoshiro128++ (Blackman & Vigna): the per-track sequential stream of the tolerance
+// update (thinning and backward-sampling decisions, consumed in the canonical
+// (edge, time) walk order).  Seeded from one Philox block per (unit, sweep, track).
+struct NxbXo { uint32_t s0, s1, s2, s3; };
+NXB_HD uint32_t nxb_rotl(uint32_t x, int k) { return (x << k) | (x >> (32 - k)); }
+NXB_HD uint32_t nxb_xo_next(NxbXo& g) {
+    uint32_t result = nxb_rotl(g.s0 + g.s3, 7) + g.s0;
+    uint32_t t = g.s1 << 9;
+    g.s2 ^= g.s0; g.s3 ^= g.s1; g.s1 ^= g.s2; g.s0 ^= g.s3;
+    g.s2 ^= t;
+    g.s3 = nxb_rotl(g.s3, 11);
+    return result;
+}
+
 // RNG stream identifiers (counter word c2)
 #define NXB_STREAM_PRI_EDGE   0x01000000u   // | edge        : candidate count, times, thinning
 #define NXB_STREAM_PRI_FFBS   0x02000000u   //               : block = chunk index
-#define NXB_STREAM_BLK_PAIR   0x03000000u   // | k<<16 | edge: candidate count, times, thinning
-#define NXB_STREAM_BLK_FFBS   0x04000000u   // | k<<16       : block = pool index (root: 0xffffffff)
+#define NXB_STREAM_BLK_PAIR   0x03000000u   // | k<<16 | edge: candidate times (2 per block)
+#define NXB_STREAM_BLK_COUNT  0x06000000u   // | pair group  : 4 candidate counts per block
+#define NXB_STREAM_BLK_FFBS   0x04000000u   // | k<<16       : block 0 seeds the track's xoshiro stream
 #define NXB_STREAM_INIT_BLK   0x05000000u   // | k<<16 | edge
 #define NXB_SWEEP_INIT        0xFFFFFFFFu   // counter word c1 used by the initialisation pass

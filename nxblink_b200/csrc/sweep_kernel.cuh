@@ -31,8 +31,6 @@
 
 #define FULL 0xffffffffu
 #define NXB_INF (__longlong_as_double(0x7ff0000000000000LL))
-#define FLAG_OLD 1
-#define FLAG_DEAD 2
 
 namespace nxb {
 
@@ -49,6 +47,7 @@ struct Ctx {
     const unsigned short *qinfo, *qptr;
     const unsigned char* cls;
     const unsigned long long* clsmask;
+    const void* ell_info; const void* ell_q;
     // CTA-level statistic partials (shared memory)
     unsigned long long *s_off_on, *s_on_off, *s_root_pri, *s_root_misc, *s_root_on_cls;
     // per-warp persistent state (shared memory)
@@ -433,43 +432,64 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     }
     tick(c, T_P2);
     // ---- P3: upward pass over the chunk tree ------------------------------------------
+    // Hoisted, lane-parallel: per-event 1/(2*Rmax(mask)) and the uniforms of the backward pass.
+    MSG* finv = (MSG*)(c.wbase + wl.off_finv);
+    double* fu = (double*)(c.wbase + wl.off_fu);
+    {
+        int bad = 0;
+        for (int j = lane; j <= F; j += 32) {
+            if (j < F) {
+                double rm = rmax_lookup(c, fmask[j]);
+                if (!(rm > 0.0)) bad = 1;
+                finv[j] = (MSG)(0.5 / rm);
+            }
+            NxbU4 r = rng(c, NXB_STREAM_PRI_FFBS, (unsigned)j);
+            fu[j] = nxb_u53(r.x, r.y);
+        }
+        if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_ZERO_RATE, 0); return RC_ERROR; }
+    }
     for (int i = lane; i < (F + 1) * NXB_PPAD; i += 32) msg[i] = (MSG)1.0;
     __syncwarp();
+    const unsigned short* ell_info = (const unsigned short*)(c.ell_info);
+    const MSG* ell_q = (const MSG*)(c.ell_q);
+    const int W = p.ml.ell_w;
+    const bool two = P > 32;
     for (int j = F - 1; j >= 0; --j) {
         const int ci = j + 1, pi_ = par[ci];
         const unsigned fm = fmask[j];
         const unsigned long long allow = callow[ci];
-        const double rm = rmax_lookup(c, fm);
-        if (!(rm > 0.0)) { fail(c, NXB_ERR_ZERO_RATE, j); return RC_ERROR; }
-        const double inv = 0.5 / rm;
+        const MSG inv = finv[j];
         MSG* mc = msg + ci * NXB_PPAD;
         MSG* mp = msg + pi_ * NXB_PPAD;
-        double v0 = (lane < P && ((allow >> lane) & 1ull)) ? (double)mc[lane] : 0.0;
-        double v1 = (lane + 32 < P && ((allow >> (lane + 32)) & 1ull)) ? (double)mc[lane + 32] : 0.0;
-        double mx = warp_max(fmax(v0, v1));
-        if (!(mx > 0.0)) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
-        double sc = 1.0 / mx;
-        mc[lane] = (MSG)(v0 * sc);
-        mc[lane + 32] = (MSG)(v1 * sc);
-        __syncwarp();
+        MSG v0 = ((allow >> lane) & 1ull) ? mc[lane] : (MSG)0;
+        MSG v1 = (two && ((allow >> (lane + 32)) & 1ull)) ? mc[lane + 32] : (MSG)0;
+        MSG mx = v0 > v1 ? v0 : v1;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int a = lane + 32 * half;
-            if (a < P) {
-                double aq = 0.0, am = 0.0;
-                for (int idx = c.qptr[a]; idx < c.qptr[a + 1]; ++idx) {
-                    unsigned info = c.qinfo[idx];
-                    if ((fm >> (info >> 8)) & 1u) {
-                        double q = c.qval[idx];
-                        aq += q;
-                        am += q * (double)mc[info & 0xffu];
-                    }
-                }
-                double self = (double)mc[a];
-                double up = self + inv * (am - aq * self);
-                mp[a] = (MSG)((double)mp[a] * up);
+        for (int o = 16; o > 0; o >>= 1) { MSG y = __shfl_xor_sync(FULL, mx, o); mx = y > mx ? y : mx; }
+        if (!(mx > (MSG)0)) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
+        const MSG sc = (MSG)1 / mx;
+        v0 *= sc; v1 *= sc;
+        mc[lane] = v0;
+        mc[lane + 32] = v1;
+        __syncwarp();
+        // branch-free sparse mat-vec from the transposed ELL copy of Q: row a of the
+        // uniformized matrix is  P[a][a] = 1 - inv*R_a(mask),  P[a][b] = inv*q_ab [class(b) on]
+        MSG aq0 = 0, am0 = 0, aq1 = 0, am1 = 0;
+#pragma unroll 3
+        for (int w = 0; w < W; ++w) {
+            const unsigned i0 = ell_info[w * NXB_PPAD + lane];
+            const MSG q0 = ((fm >> (i0 >> 8)) & 1u) ? ell_q[w * NXB_PPAD + lane] : (MSG)0;
+            aq0 += q0;
+            am0 += q0 * mc[i0 & 0xffu];
+            if (two) {
+                const unsigned i1 = ell_info[w * NXB_PPAD + lane + 32];
+                const MSG q1 = ((fm >> (i1 >> 8)) & 1u) ? ell_q[w * NXB_PPAD + lane + 32] : (MSG)0;
+                aq1 += q1;
+                am1 += q1 * mc[i1 & 0xffu];
             }
         }
+        mp[lane] *= v0 + inv * (am0 - aq0 * v0);
+        if (two) mp[lane + 32] *= v1 + inv * (am1 - aq1 * v1);
         __syncwarp();
     }
     tick(c, T_P3);
@@ -479,8 +499,7 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         double w0 = (lane < P && ((allow >> lane) & 1ull)) ? (double)msg[lane] * c.pi[lane] : 0.0;
         double w1 = (lane + 32 < P && ((allow >> (lane + 32)) & 1ull))
                     ? (double)msg[lane + 32] * c.pi[lane + 32] : 0.0;
-        NxbU4 r = rng(c, NXB_STREAM_PRI_FFBS, 0u);
-        int s0 = warp_sample64(w0, w1, nxb_u53(r.x, r.y), lane);
+        int s0 = warp_sample64(w0, w1, fu[0], lane);
         if (s0 < 0) { fail(c, NXB_ERR_INFEASIBLE, -1); return RC_ERROR; }
         if (lane == 0) cstate[0] = (unsigned char)s0;
     }
@@ -489,28 +508,37 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         const int ci = j + 1;
         const int a = cstate[par[ci]];
         const unsigned fm = fmask[j];
-        const double inv = 0.5 / rmax_lookup(c, fm);
+        const MSG inv = finv[j];
         const MSG* mc = msg + ci * NXB_PPAD;
-        const int q0 = c.qptr[a], deg = c.qptr[a + 1] - q0;
-        // items: 0 = stay in a (diagonal of the uniformized matrix), i>=1 = neighbour i-1
-        double q_lo = 0.0, q_hi = 0.0; int b_lo = a, b_hi = a;
-        if (lane >= 1 && lane <= deg) {
-            unsigned info = c.qinfo[q0 + lane - 1];
-            if ((fm >> (info >> 8)) & 1u) q_lo = c.qval[q0 + lane - 1];
-            b_lo = info & 0xffu;
+        // lane 0: stay in a (diagonal of the uniformized matrix); lane w+1: ELL entry w of row a
+        MSG q = 0;
+        int b = a;
+        if (lane >= 1 && lane <= W) {
+            const unsigned info = ell_info[(lane - 1) * NXB_PPAD + a];
+            b = info & 0xffu;
+            if ((fm >> (info >> 8)) & 1u) q = ell_q[(lane - 1) * NXB_PPAD + a];
         }
-        if (lane + 32 <= deg) {
-            unsigned info = c.qinfo[q0 + lane + 31];
-            if ((fm >> (info >> 8)) & 1u) q_hi = c.qval[q0 + lane + 31];
-            b_hi = info & 0xffu;
+        const MSG wgt = inv * q * mc[b];
+        MSG sq = q, sw = wgt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            MSG y = __shfl_up_sync(FULL, sq, d), z = __shfl_up_sync(FULL, sw, d);
+            if (lane >= d) { sq += y; sw += z; }
         }
-        double ra = warp_sum(q_lo + q_hi);
-        double w_lo = (lane == 0) ? (1.0 - inv * ra) * (double)mc[a] : inv * q_lo * (double)mc[b_lo];
-        double w_hi = inv * q_hi * (double)mc[b_hi];
-        NxbU4 r = rng(c, NXB_STREAM_PRI_FFBS, (unsigned)ci);
-        int item = warp_sample64(w_lo, w_hi, nxb_u53(r.x, r.y), lane);
-        if (item < 0) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
-        int bsel = (item < 32) ? __shfl_sync(FULL, b_lo, item) : __shfl_sync(FULL, b_hi, item - 32);
+        const MSG totq = __shfl_sync(FULL, sq, 31), totw = __shfl_sync(FULL, sw, 31);
+        const MSG w_stay = ((MSG)1 - inv * totq) * mc[a];
+        const MSG total = w_stay + totw;
+        if (!(total > (MSG)0)) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
+        const MSG target = (MSG)fu[ci] * total;
+        int bsel = a;
+        if (!(target < w_stay)) {
+            unsigned bal = __ballot_sync(FULL, wgt > (MSG)0 && (w_stay + sw) > target);
+            if (bal) bsel = __shfl_sync(FULL, b, __ffs(bal) - 1);
+            else {
+                unsigned pos = __ballot_sync(FULL, wgt > (MSG)0);
+                if (pos) bsel = __shfl_sync(FULL, b, 31 - __clz(pos));
+            }
+        }
         if (lane == 0) cstate[ci] = (unsigned char)bsel;
         __syncwarp();
     }
@@ -568,6 +596,11 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 // ---------------------------------------------------------------------------
 // TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, lane k = track k
 // ---------------------------------------------------------------------------
+#define CE_EDGE 0x3fffu
+#define CE_OLD 0x4000u      // pool entry is a retained event of the old trajectory
+#define CE_DEAD 0x8000u     // candidate rejected by thinning
+#define CE_NEW1 0x4000u     // (survivors only) new state of the surviving event
+
 __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     const NxbSweepParams& p = *c.p;
     const NxbWarpLayout& wl = p.wl;
@@ -575,9 +608,8 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     const int E = c.E, N = c.N, P = c.P, K = c.K, lane = c.lane;
 
     double* ctm = (double*)(c.wbase + wl.off_ctm);
-    unsigned* cell = (unsigned*)(c.wbase + wl.off_cell);       // thinning uniform, then float l
+    float* cell = (float*)(c.wbase + wl.off_cell);              // ON-probability below the event
     unsigned short* cedge = (unsigned short*)(c.wbase + wl.off_cedge);
-    unsigned char* cflag = (unsigned char*)(c.wbase + wl.off_cflag);
     int* toff = (int*)(c.wbase + wl.off_toff);
     double* acc = (double*)(c.wbase + wl.off_acc);              // [slot][K][3]: u0, u1, penalty
     unsigned* newtol = (unsigned*)(c.wbase + wl.off_newtol);
@@ -585,55 +617,94 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
 
     build_poff(c);
 
-    // ---- B0: candidate pool, (track, edge)-major, time-sorted; lanes over pairs ------------
+    // ---- B0: candidate pool, (track, edge)-major, time-sorted.  Four consecutive pairs per
+    // lane and round: one Philox block gives the four dominating-Poisson counts, one warp scan
+    // places the lane's four regions.
     const int npairs = K * E;
+    const int ngroups = (npairs + 3) >> 2;
     int run = 0, cur = 0;
-    for (int b = 0; b < npairs; b += 32) {
-        const int pr = b + lane;
-        const bool valid = pr < npairs;
-        int k = 0, e = 0;
-        if (valid) { k = pr / E; e = pr - k * E; }
-        const unsigned mykey = ((unsigned)k << 16) | (unsigned)e;
-        int lastp = min(b + 31, npairs - 1);
-        int lk = lastp / E;
-        const unsigned lastkey = ((unsigned)lk << 16) | (unsigned)(lastp - lk * E);
-        int n_old = 0, first = 0;
-        int i = cur;
+    for (int g0 = 0; g0 < ngroups; g0 += 32) {
+        const int g = g0 + lane;
+        const bool valid = g < ngroups;
+        const int pfirst = g * 4;
+        int k0 = 0, e0 = 0;
+        if (valid) { k0 = pfirst / E; e0 = pfirst - k0 * E; }
+        // keys of this lane's first/last pair and of the round's last pair
+        const int plast = min(pfirst + 3, npairs - 1);
+        const int kl = plast / E;
+        const unsigned key_lo = ((unsigned)k0 << 16) | (unsigned)e0;
+        const unsigned key_hi = ((unsigned)kl << 16) | (unsigned)(plast - kl * E);
+        const int rlast = min((g0 + 32) * 4, npairs) - 1;
+        const int rk = rlast / E;
+        const unsigned key_round = ((unsigned)rk << 16) | (unsigned)(rlast - rk * E);
+        // old events of the round are a contiguous run starting at `cur`; this lane's are the
+        // sub-run [lo, hi)
+        int lo = cur, hi = cur, i = cur;
         while (i < c.nB) {
-            unsigned key = c.bcode[i] & 0x00ffffffu;
-            if (key > lastkey) break;
-            if (valid && key == mykey) { if (n_old == 0) first = i; ++n_old; }
+            const unsigned key = c.bcode[i] & 0x00ffffffu;
+            if (key > key_round) break;
+            lo += key < key_lo;
+            hi += key <= key_hi;
             ++i;
         }
         cur = i;
-        int n_new = 0;
-        bool active = valid && (c.len[e] > 0.0) && (c.rate[e] > 0.0);
-        if (active) {
-            NxbU4 r = rng(c, NXB_STREAM_BLK_PAIR | mykey, 0u);
-            n_new = poisson_inv(nxb_u32(r.x), c.p0_blk[e], c.lam_blk[e]);
+        unsigned n_new4 = 0, n_old4 = 0;
+        int size = 0;
+        if (valid) {
+            NxbU4 r = rng(c, NXB_STREAM_BLK_COUNT | (unsigned)g, 0u);
+            int k = k0, e = e0, io = lo;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                if (pfirst + m < npairs) {
+                    const unsigned key = ((unsigned)k << 16) | (unsigned)e;
+                    int n_old = 0;
+                    while (io < hi && (c.bcode[io] & 0x00ffffffu) == key) { ++io; ++n_old; }
+                    int n_new = 0;
+                    if (c.len[e] > 0.0 && c.rate[e] > 0.0) {
+                        const unsigned word = (m == 0) ? r.x : (m == 1) ? r.y : (m == 2) ? r.z : r.w;
+                        n_new = min(poisson_inv(nxb_u32(word), c.p0_blk[e], c.lam_blk[e]), 255);
+                    }
+                    n_old = min(n_old, 255);
+                    n_new4 |= (unsigned)n_new << (8 * m);
+                    n_old4 |= (unsigned)n_old << (8 * m);
+                    size += n_old + n_new;
+                    if (++e == E) { e = 0; ++k; }
+                }
+            }
         }
-        int size = n_old + n_new, tot;
+        int tot;
         int base = run + warp_excl_scan(size, lane, tot);
         run += tot;
         if (run > wl.capC) return RC_DEFER;
         if (valid) {
-            if (e == 0) toff[k] = base;
-            for (int q = 0; q < n_old; ++q) {
-                ctm[base + q] = c.btm[first + q];
-                cflag[base + q] = FLAG_OLD;
-                cell[base + q] = 0u;
-                cedge[base + q] = (unsigned short)e;
-            }
-            const double tma = c.tma[e], len = c.len[e];
-            for (int q = 0; q < n_new; ++q) {
-                NxbU4 r = rng(c, NXB_STREAM_BLK_PAIR | mykey, 1u + (unsigned)q);
-                double t = tma + len * nxb_u53(r.x, r.y);
-                int j = base + n_old + q - 1;
-                while (j >= base && ctm[j] > t) {
-                    ctm[j + 1] = ctm[j]; cflag[j + 1] = cflag[j]; cell[j + 1] = cell[j]; --j;
+            int k = k0, e = e0, io = lo;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                if (pfirst + m < npairs) {
+                    const int n_old = (n_old4 >> (8 * m)) & 0xff, n_new = (n_new4 >> (8 * m)) & 0xff;
+                    if (e == 0) toff[k] = base;
+                    for (int q = 0; q < n_old; ++q) {
+                        ctm[base + q] = c.btm[io + q];
+                        cedge[base + q] = (unsigned short)(e | CE_OLD);
+                    }
+                    io += n_old;
+                    const double tma = c.tma[e], len = c.len[e];
+                    const unsigned stream = NXB_STREAM_BLK_PAIR | ((unsigned)k << 16) | (unsigned)e;
+                    for (int q = 0; q < n_new; q += 2) {
+                        NxbU4 r = rng(c, stream, (unsigned)(q >> 1));
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (q + h < n_new) {
+                                const double t = tma + len * (h ? nxb_u53(r.z, r.w) : nxb_u53(r.x, r.y));
+                                int j = base + n_old + q + h - 1;
+                                while (j >= base && ctm[j] > t) { ctm[j + 1] = ctm[j]; cedge[j + 1] = cedge[j]; --j; }
+                                ctm[j + 1] = t; cedge[j + 1] = (unsigned short)e;
+                            }
+                        }
+                    }
+                    base += n_old + n_new;
+                    if (++e == E) { e = 0; ++k; }
                 }
-                ctm[j + 1] = t; cflag[j + 1] = 0; cell[j + 1] = r.z;
-                cedge[base + n_old + q] = (unsigned short)e;
             }
         }
     }
@@ -645,87 +716,98 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     const int k = trk ? lane : 0;
     const int t_lo = trk ? toff[k] : 0;
     const int t_hi = trk ? toff[k + 1] : 0;
-    int rc_lane = 0;     // per-lane infeasibility flag, reduced after the loops
-
-    // ---- B1: upward pass, edges in descending index (children before parents) -----------------
+    int bad = 0;
+    // per-track sequential stream for thinning and backward-sampling decisions
+    NxbXo xo;
     {
-        int ic = t_hi;                 // this lane's pool cursor (exclusive upper end)
-        unsigned inited = 0u;          // uniform bitmask of live accumulator slots
-        for (int e = E - 1; e >= 0; --e) {
-            const int vb = e + 1, va = c.parent[e];
-            const int sb_slot = c.slot[vb], sa_slot = c.slot[va];
-            const double tma = c.tma[e], rate = c.rate[e];
-            double u0 = 1.0, u1 = 1.0, pen = 0.0;
-            if (trk) {
-                if (sb_slot >= 0 && ((inited >> sb_slot) & 1u)) {
-                    const double* a = acc + (sb_slot * K + k) * 3;
-                    u0 = a[0]; u1 = a[1]; pen = a[2];
+        NxbU4 r = rng(c, NXB_STREAM_BLK_FFBS | ((unsigned)k << 16), 0u);
+        xo.s0 = r.x; xo.s1 = r.y; xo.s2 = r.z; xo.s3 = r.w | 1u;
+    }
+
+    // ---- B1: upward pass.  Every lane walks its own track through the edges in descending
+    // index (children before parents), one boundary (event or edge top) per iteration, without
+    // waiting for the other lanes at edge boundaries.
+    {
+        int e = trk ? E - 1 : -1;
+        int ic = t_hi;                 // pool cursor (exclusive upper end)
+        unsigned inited = 0u;          // live accumulator slots of this lane
+        bool fresh = true;
+        double tma = 0.0, rate = 0.0, tcur = 0.0, u0 = 1.0, u1 = 1.0, pen = 0.0;
+        int s = 0, ip = 0, ip0 = 0, sa_slot = 0, sb_slot = -1;
+        unsigned xold = 0u;
+        while (__any_sync(FULL, e >= 0)) {
+            if (e >= 0) {
+                if (fresh) {
+                    const int vb = e + 1, va = c.parent[e];
+                    sb_slot = c.slot[vb]; sa_slot = c.slot[va];
+                    tma = c.tma[e]; rate = c.rate[e]; tcur = tma + c.len[e];
+                    u0 = 1.0; u1 = 1.0; pen = 0.0;
+                    if (sb_slot >= 0 && ((inited >> sb_slot) & 1u)) {
+                        const double* a = acc + (sb_slot * K + k) * 3;
+                        u0 = a[0]; u1 = a[1]; pen = a[2];
+                    }
+                    if (!((c.tt_ok[vb] >> k) & 1u)) u1 = 0.0;
+                    if (!((c.tf_ok[vb] >> k) & 1u)) u0 = 0.0;
+                    s = c.node_pri[vb];
+                    xold = (c.node_tol[vb] >> k) & 1u;
+                    ip = poff[e + 1] - 1; ip0 = poff[e];
+                    fresh = false;
                 }
-                if (!((c.tt_ok[vb] >> k) & 1u)) u1 = 0.0;
-                if (!((c.tf_ok[vb] >> k) & 1u)) u0 = 0.0;
-                int s = c.node_pri[vb];
-                unsigned xold = (c.node_tol[vb] >> k) & 1u;
-                int ip = poff[e + 1] - 1;
-                const int ip0 = poff[e];
-                double tcur = tma + c.len[e];
-                while (true) {
-                    double tp = (ip >= ip0) ? c.ptm[ip] : -NXB_INF;
-                    bool hasc = (ic > t_lo) && (cedge[ic - 1] == (unsigned short)e);
-                    double tc = hasc ? ctm[ic - 1] : -NXB_INF;
-                    double tnext = fmax(fmax(tp, tc), tma);
-                    const bool own = (c.cls[s] == k);
-                    // chunking.py:67-79: own class forces ON; ON pays the rate into class k
-                    pen += c.qm[s * K + k] * rate * (tcur - tnext);
-                    if (own) u0 = 0.0;
-                    if (tp == -NXB_INF && tc == -NXB_INF) break;
-                    if (tc > tp) {
-                        const int id = ic - 1;
-                        --ic;
-                        bool live = true;
-                        if (cflag[id] & FLAG_OLD) xold ^= 1u;
+                const double tp = (ip >= ip0) ? c.ptm[ip] : -NXB_INF;
+                const bool hasc = (ic > t_lo) && ((cedge[ic - 1] & CE_EDGE) == (unsigned)e);
+                const double tc = hasc ? ctm[ic - 1] : -NXB_INF;
+                const double tnext = fmax(fmax(tp, tc), tma);
+                const bool own = (c.cls[s] == k);
+                // chunking.py:67-79: own class forces ON; ON pays the rate into class k
+                pen += c.qm[s * K + k] * rate * (tcur - tnext);
+                if (own) u0 = 0.0;
+                tcur = tnext;
+                if (tp == -NXB_INF && tc == -NXB_INF) {
+                    // top of the edge: fold into the parent's accumulator
+                    double mx = fmax(u0, u1);
+                    if (!(mx > 0.0)) { bad = 1; mx = 1.0; }
+                    const double r = 1.0 / mx;
+                    u0 *= r; u1 *= r;
+                    double* a = acc + (sa_slot * K + k) * 3;
+                    if ((inited >> sa_slot) & 1u) {
+                        double n0 = a[0] * u0, n1 = a[1] * u1;
+                        double m2 = fmax(n0, n1);
+                        if (!(m2 > 0.0)) { bad = 1; m2 = 1.0; }
+                        const double r2 = 1.0 / m2;
+                        a[0] = n0 * r2; a[1] = n1 * r2; a[2] += pen;
+                    } else { a[0] = u0; a[1] = u1; a[2] = pen; }
+                    inited |= 1u << sa_slot;
+                    if (sb_slot >= 0) inited &= ~(1u << sb_slot);
+                    --e;
+                    fresh = true;
+                } else if (tc > tp) {
+                    const int id = --ic;
+                    bool live = true;
+                    if (cedge[id] & CE_OLD) xold ^= 1u;
+                    else {
+                        // poisson.py:111-116 by thinning the dominating process
+                        live = nxb_u32(nxb_xo_next(xo)) < ml.acc_blk[(own ? 2 : 0) + (int)xold];
+                        if (!live) cedge[id] |= CE_DEAD;
+                    }
+                    if (live) {
+                        if (pen != 0.0) { u1 *= exp(-pen); pen = 0.0; }
+                        double ssum = u0 + u1;
+                        if (!(ssum > 0.0)) { bad = 1; ssum = 1.0; }
+                        const double r = 1.0 / ssum;
+                        const double l1 = u1 * r, l0 = u0 * r;
+                        cell[id] = (float)l1;
+                        // uniformized 2x2 matrix of this context (poisson.py:92-96)
+                        if (own) { u0 = 0.5 * l0 + 0.5 * l1; u1 = l1; }
                         else {
-                            double a = ml.acc_blk[(own ? 2 : 0) + (int)xold];
-                            live = nxb_u32(cell[id]) < a;
-                            if (!live) cflag[id] = FLAG_DEAD;
+                            u0 = (1.0 - ml.a_on) * l0 + ml.a_on * l1;
+                            u1 = ml.a_off * l0 + (1.0 - ml.a_off) * l1;
                         }
-                        if (live) {
-                            u1 *= exp(-pen); pen = 0.0;
-                            double ssum = u0 + u1;
-                            if (!(ssum > 0.0)) { rc_lane = 1; ssum = 1.0; }
-                            double l1 = u1 / ssum, l0 = u0 / ssum;
-                            cell[id] = __float_as_uint((float)l1);
-                            // uniformized 2x2 matrix of this context (poisson.py:92-96)
-                            if (own) { u0 = 0.5 * l0 + 0.5 * l1; u1 = l1; }
-                            else {
-                                double n0 = (1.0 - ml.a_on) * l0 + ml.a_on * l1;
-                                double n1 = ml.a_off * l0 + (1.0 - ml.a_off) * l1;
-                                u0 = n0; u1 = n1;
-                            }
-                        }
-                    } else {
-                        s = (c.pcode[ip] >> 16) & 0xffu;     // going rootward: state before the event
-                        --ip;
                     }
-                    tcur = tnext;
+                } else {
+                    s = (c.pcode[ip] >> 16) & 0xffu;     // rootward: the state before the event
+                    --ip;
                 }
-                // fold into the parent's accumulator
-                double mx = fmax(u0, u1);
-                if (!(mx > 0.0)) { rc_lane = 1; mx = 1.0; }
-                u0 /= mx; u1 /= mx;
-                double* a = acc + (sa_slot * K + k) * 3;
-                if ((inited >> sa_slot) & 1u) {
-                    double n0 = a[0] * u0, n1 = a[1] * u1;
-                    double m2 = fmax(n0, n1);
-                    if (!(m2 > 0.0)) {
-                        // the two factors may only be compatible after their penalties are
-                        // applied; both are max-normalised so a zero product is a true zero
-                        rc_lane = 1; m2 = 1.0;
-                    }
-                    a[0] = n0 / m2; a[1] = n1 / m2; a[2] += pen;
-                } else { a[0] = u0; a[1] = u1; a[2] = pen; }
             }
-            inited |= 1u << sa_slot;
-            if (sb_slot >= 0) inited &= ~(1u << sb_slot);
         }
     }
     __syncwarp();
@@ -739,81 +821,86 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         if (!((c.tt_ok[0] >> k) & 1u)) w1 = 0.0;
         if (!((c.tf_ok[0] >> k) & 1u)) w0 = 0.0;
         if (c.cls[c.node_pri[0]] == k) w0 = 0.0;
-        if (!(w0 + w1 > 0.0)) rc_lane = 1;
-        NxbU4 r = rng(c, NXB_STREAM_BLK_FFBS | ((unsigned)k << 16), 0xffffffffu);
-        x = (nxb_u53(r.x, r.y) * (w0 + w1) < w1) ? 1u : 0u;
+        if (!(w0 + w1 > 0.0)) bad = 1;
+        x = (nxb_u32(nxb_xo_next(xo)) * (w0 + w1) < w1) ? 1u : 0u;
     }
-    if (__any_sync(FULL, rc_lane)) { fail(c, NXB_ERR_INFEASIBLE, -2); return RC_ERROR; }
+    if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_INFEASIBLE, -2); return RC_ERROR; }
     {
         unsigned bal = __ballot_sync(FULL, x);
-        if (lane == 0) newtol[0] = bal;
+        for (int v = lane; v < N; v += 32) newtol[v] = (v == 0) ? bal : 0u;
     }
     __syncwarp();
 
-    // ---- B2: downward sampling, edges in ascending index; statistics fused in ------------------------
+    // ---- B2: downward sampling, edges in ascending index, same flattened walk; the OFF-time and
+    // transition statistics are fused in (summary.py:123-131,234-243)
     const NxbSummaryLayout& sl = p.sl;
-    int w = t_lo, ic = t_lo;
-    for (int e = 0; e < E; ++e) {
-        const int vb = e + 1, va = c.parent[e];
-        if (trk) {
-            x = (newtol[va] >> k) & 1u;
-            int s = c.node_pri[va];
-            int ip = poff[e];
-            const int ipe = poff[e + 1];
-            const double tmb = c.tma[e] + c.len[e];
-            double tcur = c.tma[e];
-            double offtime = 0.0;
-            int n_on = 0, n_off = 0;
-            while (true) {
-                double tp = (ip < ipe) ? c.ptm[ip] : NXB_INF;
-                bool hasc = (ic < t_hi) && (cedge[ic] == (unsigned short)e);
-                double tc = hasc ? ctm[ic] : NXB_INF;
-                double tnext = fmin(fmin(tp, tc), tmb);
+    int w = t_lo;
+    {
+        int e = trk ? 0 : E;
+        int ic = t_lo;
+        bool fresh = true;
+        int s = 0, ip = 0, ipe = 0, vb = 0, n_on = 0, n_off = 0;
+        double tmb = 0.0, tcur = 0.0, offtime = 0.0;
+        while (__any_sync(FULL, e < E)) {
+            if (e < E) {
+                if (fresh) {
+                    vb = e + 1;
+                    const int va = c.parent[e];
+                    x = (newtol[va] >> k) & 1u;
+                    s = c.node_pri[va];
+                    ip = poff[e]; ipe = poff[e + 1];
+                    tcur = c.tma[e]; tmb = tcur + c.len[e];
+                    offtime = 0.0; n_on = 0; n_off = 0;
+                    fresh = false;
+                }
+                const double tp = (ip < ipe) ? c.ptm[ip] : NXB_INF;
+                const bool hasc = (ic < t_hi) && ((cedge[ic] & CE_EDGE) == (unsigned)e);
+                const double tc = hasc ? ctm[ic] : NXB_INF;
+                const double tnext = fmin(fmin(tp, tc), tmb);
                 if (!x) offtime += tnext - tcur;
                 tcur = tnext;
-                if (tp == NXB_INF && tc == NXB_INF) {
-                    if (accumulate && offtime > 0.0)
-                        atomicAdd(p.dwell + sl.d_off + ((long long)e * P + s) * K + k, offtime);
-                    break;
-                }
                 if (tc < tp) {
-                    const int id = ic;
-                    ++ic;
-                    if (!(cflag[id] & FLAG_DEAD)) {
+                    const int id = ic++;
+                    if (!(cedge[id] & CE_DEAD)) {
                         const bool own = (c.cls[s] == k);
-                        double l1 = (double)__uint_as_float(cell[id]);
-                        double p1 = own ? (x ? 1.0 : 0.5) : (x ? 1.0 - ml.a_off : ml.a_on);
-                        double w1 = p1 * l1, w0 = (1.0 - p1) * (1.0 - l1);
-                        NxbU4 r = rng(c, NXB_STREAM_BLK_FFBS | ((unsigned)k << 16), (unsigned)id);
-                        unsigned xn = (nxb_u32(r.x) * (w0 + w1) < w1) ? 1u : 0u;
-                        if (!(w0 + w1 > 0.0)) rc_lane = 1;
+                        const double l1 = (double)cell[id];
+                        const double p1 = own ? (x ? 1.0 : 0.5) : (x ? 1.0 - ml.a_off : ml.a_on);
+                        const double w1 = p1 * l1, w0 = (1.0 - p1) * (1.0 - l1);
+                        if (!(w0 + w1 > 0.0)) bad = 1;
+                        const unsigned xn = (nxb_u32(nxb_xo_next(xo)) * (w0 + w1) < w1) ? 1u : 0u;
                         if (xn != x) {
-                            ctm[w] = tc; cedge[w] = (unsigned short)e; cflag[w] = (unsigned char)xn;
+                            ctm[w] = tc;
+                            cedge[w] = (unsigned short)(e | (xn ? CE_NEW1 : 0u));
                             ++w;
                             if (xn) ++n_on; else ++n_off;
                             x = xn;
                         }
                     }
                 } else {
+                    // primary event or the bottom of the edge: close the OFF-time segment
                     if (accumulate && offtime > 0.0)
                         atomicAdd(p.dwell + sl.d_off + ((long long)e * P + s) * K + k, offtime);
                     offtime = 0.0;
-                    s = (c.pcode[ip] >> 24) & 0xffu;
-                    ++ip;
+                    if (tp != NXB_INF) {
+                        s = (c.pcode[ip] >> 24) & 0xffu;
+                        ++ip;
+                    } else {
+                        if (accumulate) {
+                            if (n_on) atomicAdd(&c.s_off_on[e], (unsigned long long)n_on);
+                            if (n_off) atomicAdd(&c.s_on_off[e], (unsigned long long)n_off);
+                        }
+                        if (x) atomicOr(&newtol[vb], 1u << k);
+                        ++e;
+                        fresh = true;
+                    }
                 }
             }
-            if (accumulate) {
-                if (n_on) atomicAdd(&c.s_off_on[e], (unsigned long long)n_on);
-                if (n_off) atomicAdd(&c.s_on_off[e], (unsigned long long)n_off);
-            }
         }
-        unsigned bal = __ballot_sync(FULL, trk && x);
-        if (lane == 0) newtol[vb] = bal;
-        __syncwarp();
     }
-    if (__any_sync(FULL, rc_lane)) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
-
+    __syncwarp();
+    if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
     tick(c, T_B2);
+
     // ---- write back: new retained blink events, (track, edge, time) order -----------------------------
     int n_mine = trk ? (w - t_lo) : 0, total;
     int dst = warp_excl_scan(n_mine, lane, total);
@@ -835,8 +922,8 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         unsigned* gbcode = (unsigned*)(slab + p.so_bcode);
         for (int q = 0; q < n_mine; ++q) {
             gbtm[dst + q] = ctm[t_lo + q];
-            gbcode[dst + q] = (unsigned)cedge[t_lo + q] | ((unsigned)k << 16)
-                              | ((unsigned)cflag[t_lo + q] << 31);
+            gbcode[dst + q] = (unsigned)(cedge[t_lo + q] & CE_EDGE) | ((unsigned)k << 16)
+                              | ((cedge[t_lo + q] & CE_NEW1) ? (1u << 31) : 0u);
         }
         c.nB = -total;      // negative: already in HBM
         __syncwarp();
@@ -844,8 +931,8 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     }
     for (int q = 0; q < n_mine; ++q) {
         c.btm[dst + q] = ctm[t_lo + q];
-        c.bcode[dst + q] = (unsigned)cedge[t_lo + q] | ((unsigned)k << 16)
-                           | ((unsigned)cflag[t_lo + q] << 31);
+        c.bcode[dst + q] = (unsigned)(cedge[t_lo + q] & CE_EDGE) | ((unsigned)k << 16)
+                           | ((cedge[t_lo + q] & CE_NEW1) ? (1u << 31) : 0u);
     }
     c.nB = total;
     __syncwarp();
