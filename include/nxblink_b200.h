@@ -48,6 +48,8 @@ typedef struct {
     double cap_scale;        /* scales every per-unit capacity; 0 or 1.0 = default */
     int32_t validate;        /* 1: check trajectory invariants after every phase */
     int32_t max_warps;       /* 0 = auto */
+    int32_t lockstep_warps;  /* warps per phase-lockstep group (instruction-cache sharing);
+                                0 = default (10), negative = independent warps */
 } nxb_model_desc;
 
 /* Sizes of the flat statistic buffers (see nxb_summary_read). */

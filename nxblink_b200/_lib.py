@@ -32,6 +32,7 @@ class ModelDesc(C.Structure):
         ('diameter', C.c_int32), ('msg_f64', C.c_int32),
         ('cap_scale', C.c_double),
         ('validate', C.c_int32), ('max_warps', C.c_int32),
+        ('lockstep_warps', C.c_int32),
     ]
 
 

@@ -11,7 +11,7 @@
 #include "../../include/nxblink_b200.h"
 #include "sweep_kernel.cuh"
 
-#define NXB_MAX_THREADS 512
+#define NXB_MAX_THREADS 640
 
 namespace nxb {
 
@@ -59,6 +59,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     c.s_root_misc = stats + 2 * ml.E + ml.P;
     c.s_root_on_cls = stats + 2 * ml.E + ml.P + 4;
     c.wbase = smem + p.smem_warp0 + (size_t)warp * wl.bytes;
+    c.gbase = p.gscratch + ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * p.gscratch_stride;
     c.node_tol = (unsigned*)(c.wbase + wl.off_node_tol);
     c.node_pri = (unsigned char*)(c.wbase + wl.off_node_pri);
     c.ptm = (double*)(c.wbase + wl.off_ptm);
@@ -79,26 +80,53 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     const int N = ml.N;
     const long long n_work = p.unit_list ? (long long)p.n_list : p.n_units;
     c.t_last = clock64();
+    // Lockstep groups: GW consecutive warps take a batch of GW units and run every sub-phase
+    // together (named barrier per group).  GW == 1: independent warps (deferral tiers).
+    const int GW = p.group_warps > 1 ? p.group_warps : 1;
+    const int group = warp / GW, wing = warp - group * GW;
+    const bool lockstep = GW > 1;
+    c.bar_id = 1 + group;
+    c.bar_threads = lockstep ? GW * 32 : 32;
+    c.nbar = 0;
+    unsigned long long* s_batch = (unsigned long long*)(smem + ml.off_stats) + ml.stats_words;
+    const unsigned n_steps = p.init ? 1u : (p.target_sweeps - p.begin_sweeps);
 
     while (true) {
         unsigned long long widx = 0;
-        if (lane == 0) widx = atomicAdd(p.work_counter, 1ull);
-        widx = __shfl_sync(FULL, widx, 0);
-        if ((long long)widx >= n_work) break;
-        const long long u = p.unit_list ? (long long)p.unit_list[widx] : (long long)widx;
-        c.unit = u;
-        c.unit32 = (unsigned)(p.unit_offset + u);
-        unsigned char* slab = p.state + u * p.state_stride;
-        NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;
-        if (p.init) { hdr.sweeps_done = 0; hdr.n_pri = 0; hdr.n_blk = 0; hdr.phase = NXB_PHASE_INIT; hdr.pad = 0; }
+        if (lockstep) {
+            if (wing == 0 && lane == 0) s_batch[group] = atomicAdd(p.work_counter, 1ull);
+            phase_sync(c);
+            widx = s_batch[group] * GW + wing;
+            phase_sync(c);
+            if ((long long)(s_batch[group] * GW) >= n_work) break;
+        } else {
+            if (lane == 0) widx = atomicAdd(p.work_counter, 1ull);
+            widx = __shfl_sync(FULL, widx, 0);
+            if ((long long)widx >= n_work) break;
+        }
+        bool has = (long long)widx < n_work;
+        long long u = 0;
+        unsigned char* slab = nullptr;
+        NxbUnitHeader hdr;
+        hdr.sweeps_done = 0; hdr.n_pri = 0; hdr.n_blk = 0; hdr.phase = NXB_PHASE_PRIMARY; hdr.pad = 0;
         int rc = RC_OK;
-        if ((int)hdr.n_pri > wl.capP || (int)hdr.n_blk > wl.capB) {
-            // does not fit this tier's shared-memory arrays: untouched, next tier
-            if (lane == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)u;
-            continue;
+        if (has) {
+            u = p.unit_list ? (long long)p.unit_list[widx] : (long long)widx;
+            c.unit = u;
+            c.unit32 = (unsigned)(p.unit_offset + u);
+            slab = p.state + u * p.state_stride;
+            hdr = *(const NxbUnitHeader*)slab;
+            if (p.init) { hdr.sweeps_done = 0; hdr.n_pri = 0; hdr.n_blk = 0; hdr.phase = NXB_PHASE_INIT; hdr.pad = 0; }
+            const bool off_schedule = lockstep && !p.init &&
+                (hdr.phase != NXB_PHASE_PRIMARY || hdr.sweeps_done != p.begin_sweeps);
+            if ((int)hdr.n_pri > wl.capP || (int)hdr.n_blk > wl.capB || off_schedule) {
+                // does not fit this tier's shared-memory arrays: untouched, next tier
+                if (lane == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)u;
+                has = false;
+            }
         }
         // ---- load the unit (coalesced; only the live part of the slab is read) ----
-        {
+        if (has) {
             const long long site = u / p.chains;
             const unsigned long long* g_pri = p.pri_ok + site * N;
             const unsigned* g_tt = p.tol_true_ok + site * N;
@@ -121,59 +149,69 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
         }
         tick(c, T_LOAD);
         bool spilled = false;
-        // one phase per iteration, so that every phase function has a single call site
-        // (the kernel is much larger than the instruction cache)
-        while (rc == RC_OK && (hdr.phase == NXB_PHASE_INIT || hdr.sweeps_done < p.target_sweeps)) {
+        // One phase per iteration, so that every phase function has a single call site.  In
+        // lockstep mode every warp of the group runs the same number of iterations and arrives
+        // at every barrier, whether or not its unit is still active.
+        unsigned step = 0;
+        while (true) {
+            bool active = has && rc == RC_OK && !spilled;
+            const bool more = hdr.phase == NXB_PHASE_INIT || hdr.sweeps_done < p.target_sweeps;
+            if (lockstep) { if (step >= 2 * n_steps) break; }
+            else if (!(active && more)) break;
+            active = active && more;
             const bool init = hdr.phase == NXB_PHASE_INIT;
+            const bool blink_turn = lockstep ? ((step & 1u) != 0u && !p.init) : (hdr.phase == NXB_PHASE_BLINK);
+            ++step;
+            if (lockstep && p.init && (step & 1u) == 0u) continue;     // init: one primary pass only
+            if (lockstep && active && blink_turn != (hdr.phase == NXB_PHASE_BLINK)) active = false;
             c.sweep = init ? NXB_SWEEP_INIT : hdr.sweeps_done;
             const bool accum = !init && hdr.sweeps_done >= p.accum_from;
-            if (init) {
-                rc = init_blink(c);
-                if (rc) break;
-            }
-            if (hdr.phase != NXB_PHASE_BLINK) {
-                rc = primary_phase<MSG>(c, init, accum);
-                if (rc) break;
-                hdr.phase = init ? NXB_PHASE_PRIMARY : NXB_PHASE_BLINK;
-            } else {
-                rc = blink_phase(c, accum);
-                if (rc == RC_DEFER && c.nB < 0) {     // sweep complete, blink list spilled to HBM
-                    hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
-                    spilled = true;
-                    break;
+            c.nbar = 0;
+            if (!blink_turn) {
+                if (active && init) rc = init_blink(c);
+                if (active && rc == RC_OK) {
+                    rc = primary_phase<MSG>(c, init, accum);
+                    if (rc == RC_OK) hdr.phase = init ? NXB_PHASE_PRIMARY : NXB_PHASE_BLINK;
                 }
-                if (rc) break;
-                hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
+                phase_drain(c, NXB_NBAR_PRIMARY);
+            } else {
+                if (active) {
+                    rc = blink_phase(c, accum);
+                    if (rc == RC_DEFER && c.nB < 0) {     // sweep complete, blink list spilled to HBM
+                        hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
+                        spilled = true;
+                    } else if (rc == RC_OK) { hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++; }
+                }
+                phase_drain(c, NXB_NBAR_BLINK);
             }
-            if (p.validate) rc = validate_unit(c);
-        }
-        if (rc == RC_ERROR) continue;
-        if (c.nP > p.gcapP || (!spilled && c.nB > p.gcapB)) {
-            fail(c, NXB_ERR_STATE_CAP, c.nP > p.gcapP ? c.nP : c.nB);
-            continue;
+            if (p.validate && active && rc == RC_OK) rc = validate_unit(c);
         }
         // ---- store the unit ----
-        {
-            __syncwarp();
-            hdr.n_pri = (uint16_t)c.nP;
-            hdr.n_blk = (uint16_t)(spilled ? -c.nB : c.nB);
-            if (lane == 0) *(NxbUnitHeader*)slab = hdr;
-            if (hdr.phase != NXB_PHASE_INIT) {
-                unsigned* g_tol = (unsigned*)(slab + p.so_tol);
-                unsigned* g_npri = (unsigned*)(slab + p.so_pri);
-                for (int v = lane; v < N; v += 32) g_tol[v] = c.node_tol[v];
-                for (int v = lane; v < (N + 3) / 4; v += 32) g_npri[v] = ((unsigned*)c.node_pri)[v];
-                double* g_ptm = (double*)(slab + p.so_ptm);
-                unsigned* g_pcode = (unsigned*)(slab + p.so_pcode);
-                for (int i = lane; i < c.nP; i += 32) { g_ptm[i] = c.ptm[i]; g_pcode[i] = c.pcode[i]; }
-                if (!spilled) {
-                    double* g_btm = (double*)(slab + p.so_btm);
-                    unsigned* g_bcode = (unsigned*)(slab + p.so_bcode);
-                    for (int i = lane; i < c.nB; i += 32) { g_btm[i] = c.btm[i]; g_bcode[i] = c.bcode[i]; }
+        if (has && rc != RC_ERROR) {
+            if (c.nP > p.gcapP || (!spilled && c.nB > p.gcapB)) {
+                fail(c, NXB_ERR_STATE_CAP, c.nP > p.gcapP ? c.nP : c.nB);
+            } else {
+                __syncwarp();
+                hdr.n_pri = (uint16_t)c.nP;
+                hdr.n_blk = (uint16_t)(spilled ? -c.nB : c.nB);
+                if (lane == 0) *(NxbUnitHeader*)slab = hdr;
+                if (hdr.phase != NXB_PHASE_INIT) {
+                    unsigned* g_tol = (unsigned*)(slab + p.so_tol);
+                    unsigned* g_npri = (unsigned*)(slab + p.so_pri);
+                    for (int v = lane; v < N; v += 32) g_tol[v] = c.node_tol[v];
+                    for (int v = lane; v < (N + 3) / 4; v += 32) g_npri[v] = ((unsigned*)c.node_pri)[v];
+                    double* g_ptm = (double*)(slab + p.so_ptm);
+                    unsigned* g_pcode = (unsigned*)(slab + p.so_pcode);
+                    for (int i = lane; i < c.nP; i += 32) { g_ptm[i] = c.ptm[i]; g_pcode[i] = c.pcode[i]; }
+                    if (!spilled) {
+                        double* g_btm = (double*)(slab + p.so_btm);
+                        unsigned* g_bcode = (unsigned*)(slab + p.so_bcode);
+                        for (int i = lane; i < c.nB; i += 32) { g_btm[i] = c.btm[i]; g_bcode[i] = c.bcode[i]; }
+                    }
                 }
+                if (rc == RC_DEFER && lane == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)u;
+                __syncwarp();
             }
-            if (rc == RC_DEFER && lane == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)u;
-            __syncwarp();
         }
         tick(c, T_STORE);
     }
@@ -332,7 +370,11 @@ struct nxb_handle {
     std::vector<Tier> tiers;        // steady-state sweeps
     std::vector<Tier> init_tiers;   // initial trajectories (raoteh.py:337-361) hold far more events
     unsigned long long* d_perf = nullptr;
+    unsigned char* d_gscratch = nullptr;
+    long long gscratch_stride = 0;
+    int g_off_msg = 0, g_off_ctm = 0, g_off_cell = 0, g_off_cedge = 0, gcapF = 0, gcapC = 0;
     int profile = 0;
+    int lockstep = 0;              // warps per lockstep group in tier 0 (0: independent warps)
     int gcapP = 0, gcapB = 0;
     int so_tol = 0, so_pri = 0, so_ptm = 0, so_pcode = 0, so_btm = 0, so_bcode = 0;
     long long stride = 0;
@@ -415,15 +457,13 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     wl->off_toland = take(4 * (capF + 1), 4);
     wl->off_callow = take(8 * (capF + 1), 8);
     wl->off_cstate = take(capF + 1, 1);
-    wl->off_msg = take((msg_f64 ? 8 : 4) * (capF + 1) * NXB_PPAD, 16);
+    wl->off_msg = take((msg_f64 ? 8 : 4) * NXB_PPAD, 16);     // one staging row; the messages are global
     wl->off_finv = take((msg_f64 ? 8 : 4) * capF, 8);
     wl->off_fu = take(8 * (capF + 1), 8);
     const int end_pri = o;
     // blink-phase scratch (aliases the primary-phase scratch)
     o = scratch0;
-    wl->off_ctm = take(8 * capC, 8);
-    wl->off_cell = take(4 * capC, 4);
-    wl->off_cedge = take(2 * capC, 2);
+    wl->off_ctm = wl->off_cell = wl->off_cedge = 0;            // candidate pool is global
     wl->off_toff = take(4 * (K + 1), 4);
     wl->off_acc = take(8 * 3 * K * ml.nslots, 8);
     wl->off_newtol = take(4 * N, 4);
@@ -484,6 +524,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     h->device = device;
     h->msg_f64 = d->msg_f64 != 0;
     h->validate = d->validate;
+    // default: groups of 10 warps (measured best at the p53 shape); negative switches it off
+    h->lockstep = d->lockstep_warps == 0 ? 10 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);
 #define CUDA_TRY_C(call)                                                                  \
     do {                                                                                  \
         cudaError_t e_ = (call);                                                          \
@@ -709,7 +751,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         int capC = cap(mean_blk + cand_blk, 4.0, 16.0);
         h->gcapP = std::min(65535, align_up(4 * capP + 32, 8));
         h->gcapB = std::min(65535, align_up(4 * capB + 64, 8));
-        const int stats_bytes = align_up(8 * ml.stats_words, 16);
+        const int stats_bytes = align_up(8 * (ml.stats_words + 16), 16);   // + lockstep batch slots
         const int fixed = ml.bytes + stats_bytes;
         const int max_warps = (d->max_warps > 0) ? std::min(d->max_warps, NXB_MAX_THREADS / 32)
                                                  : NXB_MAX_THREADS / 32;
@@ -738,6 +780,23 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         if (h->tiers.empty() || h->init_tiers.empty()) {
             set_err(nullptr, NXB_ERR_BAD_ARG, "model too large: one unit does not fit in shared memory");
             nxb_destroy(h); return NXB_ERR_BAD_ARG;
+        }
+        // global scratch per warp slot: chunk messages + candidate pool
+        {
+            int max_w = 1;
+            for (auto& t : h->tiers) max_w = std::max(max_w, t.warps);
+            for (auto& t : h->init_tiers) max_w = std::max(max_w, t.warps);
+            h->gcapF = std::max(8 * capF, E * d->diameter + 8);
+            h->gcapC = 8 * capC + 256;
+            int o = 0;
+            h->g_off_msg = o; o += (h->msg_f64 ? 8 : 4) * (h->gcapF + 1) * NXB_PPAD;
+            o = align_up(o, 16);
+            h->g_off_ctm = o; o += 8 * h->gcapC;
+            h->g_off_cell = o; o += 4 * h->gcapC;
+            h->g_off_cedge = o; o += 2 * h->gcapC;
+            h->gscratch_stride = align_up(o, 256);
+            cudaError_t e1 = cudaMalloc(&h->d_gscratch, (size_t)h->gscratch_stride * max_w * h->num_sms);
+            if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }
         }
         // slab layout
         int o = (int)sizeof(NxbUnitHeader);
@@ -770,7 +829,7 @@ extern "C" int nxb_destroy(nxb_handle* h) {
     cudaFree(h->d_blob); cudaFree(h->d_rmax); cudaFree(h->d_pri_ok); cudaFree(h->d_tt); cudaFree(h->d_tf);
     cudaFree(h->d_state); cudaFree(h->d_counts); cudaFree(h->d_dwell); cudaFree(h->d_status);
     cudaFree(h->d_work); cudaFree(h->d_defer[0]); cudaFree(h->d_defer[1]); cudaFree(h->d_defer_count);
-    cudaFree(h->d_scratch); cudaFree(h->d_perf);
+    cudaFree(h->d_scratch); cudaFree(h->d_perf); cudaFree(h->d_gscratch);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -833,18 +892,25 @@ static int run_tiers(nxb_handle* h, unsigned target, unsigned accum_from, int in
         p.defer_list = h->d_defer[t & 1]; p.defer_count = h->d_defer_count;
         p.seed = h->seed; p.target_sweeps = target; p.accum_from = accum_from;
         p.init = (init && t == 0) ? 1 : 0;
+        p.group_warps = (t == 0 && h->lockstep) ? std::min(tier.warps, h->lockstep) : 1;
+        p.begin_sweeps = h->sweeps;
         p.validate = h->validate;
         p.counts = h->d_counts; p.dwell = h->d_dwell; p.status = h->d_status;
         p.work_counter = h->d_work;
         p.perf = h->profile ? h->d_perf : nullptr;
+        p.gscratch = h->d_gscratch; p.gscratch_stride = h->gscratch_stride;
+        p.g_off_msg = h->g_off_msg; p.g_off_ctm = h->g_off_ctm; p.g_off_cell = h->g_off_cell;
+        p.g_off_cedge = h->g_off_cedge; p.gcapF = h->gcapF; p.gcapC = h->gcapC;
         CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
         CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
         const long long n_work = list ? n_list : h->n_units;
-        int grid = (int)std::min<long long>(h->num_sms, (n_work + tier.warps - 1) / tier.warps);
+        const int gw = (t == 0 && h->lockstep) ? std::min(tier.warps, h->lockstep) : 1;
+        const int launch_warps = tier.warps / gw * gw;       // whole groups only
+        int grid = (int)std::min<long long>(h->num_sms, (n_work + launch_warps - 1) / launch_warps);
         grid = std::max(grid, 1);
         CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-        if (h->msg_f64) sweep_kernel<double><<<grid, tier.warps * 32, tier.smem, h->stream>>>(p);
-        else sweep_kernel<float><<<grid, tier.warps * 32, tier.smem, h->stream>>>(p);
+        if (h->msg_f64) sweep_kernel<double><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
+        else sweep_kernel<float><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
         int hs[5];

@@ -133,10 +133,18 @@ struct NxbSweepParams {
     unsigned target_sweeps;             // run every unit up to this absolute sweep count
     unsigned accum_from;                // accumulate statistics for sweeps >= this
     int init;                           // 1: initialise trajectories (raoteh.py:337-361)
+    int group_warps;                    // >1: warps run in phase lockstep in groups of this size
+    unsigned begin_sweeps;              // lockstep: every unit starts the launch at this sweep count
     int validate;                       // 1: check trajectory invariants after every phase
     unsigned long long* counts;
     double* dwell;
     int* status;                        // [4]: code, unit, detail, detail
     unsigned long long* work_counter;
-    unsigned long long* perf;           // [8] optional counters (events, candidates, bytes)
+    unsigned long long* perf;           // [12] optional per-phase cycle counters
+    // per-warp-slot scratch in global memory (L2-resident): chunk messages of the primary
+    // FFBS and the candidate pool of the tolerance update
+    unsigned char* gscratch;
+    long long gscratch_stride;
+    int g_off_msg, g_off_ctm, g_off_cell, g_off_cedge;
+    int gcapF, gcapC;
 };

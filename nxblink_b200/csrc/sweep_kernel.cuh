@@ -52,6 +52,7 @@ struct Ctx {
     unsigned long long *s_off_on, *s_on_off, *s_root_pri, *s_root_misc, *s_root_on_cls;
     // per-warp persistent state (shared memory)
     unsigned char* wbase;
+    unsigned char* gbase;     // this warp slot's scratch in global memory
     unsigned* node_tol; unsigned char* node_pri;
     double* ptm; unsigned* pcode; double* btm; unsigned* bcode;
     int nP, nB;
@@ -63,7 +64,24 @@ struct Ctx {
     long long unit;       // local unit index
     // phase timers (cycles, lane 0)
     long long t_last;
+    // phase lockstep: the warps of a group run the same sub-phase at the same time so that
+    // its code is fetched once per SM instead of once per warp (the kernel is several times
+    // larger than the instruction cache and instruction fetch was the top limiter)
+    int bar_id, bar_threads, nbar;
 };
+
+#define NXB_NBAR_PRIMARY 6
+#define NXB_NBAR_BLINK 4
+
+__device__ __forceinline__ void phase_sync(Ctx& c) {
+    if (c.bar_threads > 32)
+        asm volatile("bar.sync %0, %1;" :: "r"(c.bar_id), "r"(c.bar_threads) : "memory");
+    ++c.nbar;
+}
+// after a phase function returned (possibly early), arrive at the barriers it skipped
+__device__ __forceinline__ void phase_drain(Ctx& c, int expected) {
+    while (c.nbar < expected) phase_sync(c);
+}
 
 enum { T_LOAD = 0, T_P0, T_P1, T_P2, T_P3, T_P4, T_P5, T_B0, T_B1, T_B2, T_BW, T_STORE };
 
@@ -229,10 +247,12 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     unsigned* toland = (unsigned*)(c.wbase + wl.off_toland);
     unsigned long long* callow = (unsigned long long*)(c.wbase + wl.off_callow);
     unsigned char* cstate = (unsigned char*)(c.wbase + wl.off_cstate);
-    MSG* msg = (MSG*)(c.wbase + wl.off_msg);
+    MSG* msg = (MSG*)(c.gbase + p.g_off_msg);          // chunk messages: global (L2)
+    MSG* srow = (MSG*)(c.wbase + wl.off_msg);           // staging row of the chunk being pushed up
     int* boff = c.boff; int* poff = c.poff;
     int* mE = c.tmpa; int* rbase = c.tmpb; int* foff = c.tmpc;
 
+    phase_sync(c);
     // ---- P0: edge-major, time-sorted view of the retained blink events ----------
     for (int e = lane; e <= E; e += 32) { c.tmpa[e] = 0; c.tmpb[e] = 0; }
     __syncwarp();
@@ -269,6 +289,7 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     __syncwarp();
     build_poff(c);   // uses tmpa
     tick(c, T_P0);
+    phase_sync(c);
 
     // ---- P1: candidates by thinning, merged walk, foreground event regions ------
     int run = 0;
@@ -360,9 +381,10 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         }
         F = acc;
     }
-    if (F > wl.capF) return RC_DEFER;
+    if (F > wl.capF || F > p.gcapF) return RC_DEFER;
     __syncwarp();
     tick(c, T_P1);
+    phase_sync(c);
     for (int e = lane; e < E; e += 32) {
         int src = rbase[e], dst = foff[e], m = mE[e];
         for (int i = 0; i < m; ++i) {
@@ -431,6 +453,7 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         callow[j] &= ok;
     }
     tick(c, T_P2);
+    phase_sync(c);
     // ---- P3: upward pass over the chunk tree ------------------------------------------
     // Hoisted, lane-parallel: per-event 1/(2*Rmax(mask)) and the uniforms of the backward pass.
     MSG* finv = (MSG*)(c.wbase + wl.off_finv);
@@ -461,6 +484,7 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         const MSG inv = finv[j];
         MSG* mc = msg + ci * NXB_PPAD;
         MSG* mp = msg + pi_ * NXB_PPAD;
+        // each lane reads back exactly the two entries it wrote itself (program order)
         MSG v0 = ((allow >> lane) & 1ull) ? mc[lane] : (MSG)0;
         MSG v1 = (two && ((allow >> (lane + 32)) & 1ull)) ? mc[lane + 32] : (MSG)0;
         MSG mx = v0 > v1 ? v0 : v1;
@@ -469,8 +493,10 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         if (!(mx > (MSG)0)) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
         const MSG sc = (MSG)1 / mx;
         v0 *= sc; v1 *= sc;
-        mc[lane] = v0;
+        mc[lane] = v0;                   // kept for the backward pass
         mc[lane + 32] = v1;
+        srow[lane] = v0;                 // shared-memory copy for the gather below
+        srow[lane + 32] = v1;
         __syncwarp();
         // branch-free sparse mat-vec from the transposed ELL copy of Q: row a of the
         // uniformized matrix is  P[a][a] = 1 - inv*R_a(mask),  P[a][b] = inv*q_ab [class(b) on]
@@ -480,12 +506,12 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
             const unsigned i0 = ell_info[w * NXB_PPAD + lane];
             const MSG q0 = ((fm >> (i0 >> 8)) & 1u) ? ell_q[w * NXB_PPAD + lane] : (MSG)0;
             aq0 += q0;
-            am0 += q0 * mc[i0 & 0xffu];
+            am0 += q0 * srow[i0 & 0xffu];
             if (two) {
                 const unsigned i1 = ell_info[w * NXB_PPAD + lane + 32];
                 const MSG q1 = ((fm >> (i1 >> 8)) & 1u) ? ell_q[w * NXB_PPAD + lane + 32] : (MSG)0;
                 aq1 += q1;
-                am1 += q1 * mc[i1 & 0xffu];
+                am1 += q1 * srow[i1 & 0xffu];
             }
         }
         mp[lane] *= v0 + inv * (am0 - aq0 * v0);
@@ -493,6 +519,7 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         __syncwarp();
     }
     tick(c, T_P3);
+    phase_sync(c);
     // ---- P4: root draw and downward sampling ----------------------------------------------
     {
         const unsigned long long allow = callow[0];
@@ -543,6 +570,7 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         __syncwarp();
     }
     tick(c, T_P4);
+    phase_sync(c);
     // ---- P5: write back, dropping self transitions (raoteh.py:411) ------------------------------
     int nkeep = 0;
     for (int b = 0; b < F; b += 32) {
@@ -607,14 +635,16 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     const NxbModelLayout& ml = p.ml;
     const int E = c.E, N = c.N, P = c.P, K = c.K, lane = c.lane;
 
-    double* ctm = (double*)(c.wbase + wl.off_ctm);
-    float* cell = (float*)(c.wbase + wl.off_cell);              // ON-probability below the event
-    unsigned short* cedge = (unsigned short*)(c.wbase + wl.off_cedge);
+    // candidate pool: global (L2-resident) scratch of this warp slot
+    double* ctm = (double*)(c.gbase + p.g_off_ctm);
+    float* cell = (float*)(c.gbase + p.g_off_cell);             // ON-probability below the event
+    unsigned short* cedge = (unsigned short*)(c.gbase + p.g_off_cedge);
     int* toff = (int*)(c.wbase + wl.off_toff);
     double* acc = (double*)(c.wbase + wl.off_acc);              // [slot][K][3]: u0, u1, penalty
     unsigned* newtol = (unsigned*)(c.wbase + wl.off_newtol);
     int* poff = c.poff;
 
+    phase_sync(c);
     build_poff(c);
 
     // ---- B0: candidate pool, (track, edge)-major, time-sorted.  Four consecutive pairs per
@@ -675,7 +705,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         int tot;
         int base = run + warp_excl_scan(size, lane, tot);
         run += tot;
-        if (run > wl.capC) return RC_DEFER;
+        if (run > p.gcapC) { fail(c, NXB_ERR_SCRATCH_CAP, run); return RC_ERROR; }
         if (valid) {
             int k = k0, e = e0, io = lo;
 #pragma unroll
@@ -711,6 +741,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     if (lane == 0) toff[K] = run;
     __syncwarp();
     tick(c, T_B0);
+    phase_sync(c);
 
     const bool trk = lane < K;
     const int k = trk ? lane : 0;
@@ -812,6 +843,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     }
     __syncwarp();
     tick(c, T_B1);
+    phase_sync(c);
     // ---- root draw (prior: toymodel.py:17-27 get_blink_distn) ----------------------------------------
     unsigned x = 0u;
     if (trk) {
@@ -900,6 +932,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     __syncwarp();
     if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
     tick(c, T_B2);
+    phase_sync(c);
 
     // ---- write back: new retained blink events, (track, edge, time) order -----------------------------
     int n_mine = trk ? (w - t_lo) : 0, total;
