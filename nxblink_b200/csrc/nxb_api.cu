@@ -94,6 +94,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     while (true) {
         unsigned long long widx = 0;
         if (lockstep) {
+            c.sync_mask = 0xffffffffu; c.nbar = 0;
             if (wing == 0 && lane == 0) s_batch[group] = atomicAdd(p.work_counter, 1ull);
             phase_sync(c);
             widx = s_batch[group] * GW + wing;
@@ -167,6 +168,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             c.sweep = init ? NXB_SWEEP_INIT : hdr.sweeps_done;
             const bool accum = !init && hdr.sweeps_done >= p.accum_from;
             c.nbar = 0;
+            c.sync_mask = blink_turn ? (p.sync_mask >> NXB_NBAR_PRIMARY) : p.sync_mask;
             if (!blink_turn) {
                 if (active && init) rc = init_blink(c);
                 if (active && rc == RC_OK) {
@@ -375,6 +377,7 @@ struct nxb_handle {
     int g_off_msg = 0, g_off_ctm = 0, g_off_cell = 0, g_off_cedge = 0, gcapF = 0, gcapC = 0;
     int profile = 0;
     int lockstep = 0;              // warps per lockstep group in tier 0 (0: independent warps)
+    unsigned sync_mask = 0x3ffu;
     int gcapP = 0, gcapB = 0;
     int so_tol = 0, so_pri = 0, so_ptm = 0, so_pcode = 0, so_btm = 0, so_bcode = 0;
     long long stride = 0;
@@ -524,8 +527,9 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     h->device = device;
     h->msg_f64 = d->msg_f64 != 0;
     h->validate = d->validate;
-    // default: groups of 10 warps (measured best at the p53 shape); negative switches it off
-    h->lockstep = d->lockstep_warps == 0 ? 10 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);
+    if (getenv("NXB_SYNC_MASK")) h->sync_mask = (unsigned)strtoul(getenv("NXB_SYNC_MASK"), nullptr, 0);
+    // default: one group of up to 20 warps (measured best at the p53 shape); negative switches it off
+    h->lockstep = d->lockstep_warps == 0 ? 20 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);
 #define CUDA_TRY_C(call)                                                                  \
     do {                                                                                  \
         cudaError_t e_ = (call);                                                          \
@@ -894,6 +898,7 @@ static int run_tiers(nxb_handle* h, unsigned target, unsigned accum_from, int in
         p.init = (init && t == 0) ? 1 : 0;
         p.group_warps = (t == 0 && h->lockstep) ? std::min(tier.warps, h->lockstep) : 1;
         p.begin_sweeps = h->sweeps;
+        p.sync_mask = h->sync_mask;
         p.validate = h->validate;
         p.counts = h->d_counts; p.dwell = h->d_dwell; p.status = h->d_status;
         p.work_counter = h->d_work;

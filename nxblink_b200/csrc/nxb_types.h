@@ -134,6 +134,7 @@ struct NxbSweepParams {
     unsigned accum_from;                // accumulate statistics for sweeps >= this
     int init;                           // 1: initialise trajectories (raoteh.py:337-361)
     int group_warps;                    // >1: warps run in phase lockstep in groups of this size
+    unsigned sync_mask;                 // lockstep: bits 0-5 primary sync points, 6-9 blink sync points
     unsigned begin_sweeps;              // lockstep: every unit starts the launch at this sweep count
     int validate;                       // 1: check trajectory invariants after every phase
     unsigned long long* counts;

@@ -68,13 +68,14 @@ struct Ctx {
     // its code is fetched once per SM instead of once per warp (the kernel is several times
     // larger than the instruction cache and instruction fetch was the top limiter)
     int bar_id, bar_threads, nbar;
+    unsigned sync_mask;       // which of the sync points actually wait (bit = nbar index)
 };
 
 #define NXB_NBAR_PRIMARY 6
 #define NXB_NBAR_BLINK 4
 
 __device__ __forceinline__ void phase_sync(Ctx& c) {
-    if (c.bar_threads > 32)
+    if (c.bar_threads > 32 && ((c.sync_mask >> c.nbar) & 1u))
         asm volatile("bar.sync %0, %1;" :: "r"(c.bar_id), "r"(c.bar_threads) : "memory");
     ++c.nbar;
 }
@@ -683,7 +684,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         if (valid) {
             NxbU4 r = rng(c, NXB_STREAM_BLK_COUNT | (unsigned)g, 0u);
             int k = k0, e = e0, io = lo;
-#pragma unroll
+#pragma unroll 1
             for (int m = 0; m < 4; ++m) {
                 if (pfirst + m < npairs) {
                     const unsigned key = ((unsigned)k << 16) | (unsigned)e;
@@ -708,30 +709,61 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         if (run > p.gcapC) { fail(c, NXB_ERR_SCRATCH_CAP, run); return RC_ERROR; }
         if (valid) {
             int k = k0, e = e0, io = lo;
-#pragma unroll
+#pragma unroll 1
             for (int m = 0; m < 4; ++m) {
                 if (pfirst + m < npairs) {
                     const int n_old = (n_old4 >> (8 * m)) & 0xff, n_new = (n_new4 >> (8 * m)) & 0xff;
                     if (e == 0) toff[k] = base;
-                    for (int q = 0; q < n_old; ++q) {
-                        ctm[base + q] = c.btm[io + q];
-                        cedge[base + q] = (unsigned short)(e | CE_OLD);
-                    }
-                    io += n_old;
                     const double tma = c.tma[e], len = c.len[e];
                     const unsigned stream = NXB_STREAM_BLK_PAIR | ((unsigned)k << 16) | (unsigned)e;
-                    for (int q = 0; q < n_new; q += 2) {
-                        NxbU4 r = rng(c, stream, (unsigned)(q >> 1));
+                    if (n_old + n_new <= 4) {
+                        // common case: build the pair's sorted list in registers (no reads of
+                        // the L2-resident pool), then write it out once
+                        double r0 = NXB_INF, r1 = NXB_INF, r2 = NXB_INF, r3 = NXB_INF;
+                        unsigned f0 = 0u, f1 = 0u, f2 = 0u, f3 = 0u;
+                        if (n_old > 0) { r0 = c.btm[io]; f0 = CE_OLD; }
+                        if (n_old > 1) { r1 = c.btm[io + 1]; f1 = CE_OLD; }
+                        if (n_old > 2) { r2 = c.btm[io + 2]; f2 = CE_OLD; }
+                        if (n_old > 3) { r3 = c.btm[io + 3]; f3 = CE_OLD; }
+                        for (int q = 0; q < n_new; q += 2) {
+                            NxbU4 r = rng(c, stream, (unsigned)(q >> 1));
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (q + h < n_new) {
-                                const double t = tma + len * (h ? nxb_u53(r.z, r.w) : nxb_u53(r.x, r.y));
-                                int j = base + n_old + q + h - 1;
-                                while (j >= base && ctm[j] > t) { ctm[j + 1] = ctm[j]; cedge[j + 1] = cedge[j]; --j; }
-                                ctm[j + 1] = t; cedge[j + 1] = (unsigned short)e;
+                            for (int h = 0; h < 2; ++h) {
+                                if (q + h < n_new) {
+                                    double t = tma + len * (h ? nxb_u53(r.z, r.w) : nxb_u53(r.x, r.y));
+                                    unsigned f = 0u;
+                                    // insert (t, f) into the sorted registers: the unused tail is +inf
+                                    if (t < r0) { double x_ = r0; r0 = t; t = x_; unsigned y_ = f0; f0 = f; f = y_; }
+                                    if (t < r1) { double x_ = r1; r1 = t; t = x_; unsigned y_ = f1; f1 = f; f = y_; }
+                                    if (t < r2) { double x_ = r2; r2 = t; t = x_; unsigned y_ = f2; f2 = f; f = y_; }
+                                    if (t < r3) { r3 = t; f3 = f; }
+                                }
+                            }
+                        }
+                        const int n = n_old + n_new;
+                        if (n > 0) { ctm[base] = r0; cedge[base] = (unsigned short)(e | f0); }
+                        if (n > 1) { ctm[base + 1] = r1; cedge[base + 1] = (unsigned short)(e | f1); }
+                        if (n > 2) { ctm[base + 2] = r2; cedge[base + 2] = (unsigned short)(e | f2); }
+                        if (n > 3) { ctm[base + 3] = r3; cedge[base + 3] = (unsigned short)(e | f3); }
+                    } else {
+                        for (int q = 0; q < n_old; ++q) {
+                            ctm[base + q] = c.btm[io + q];
+                            cedge[base + q] = (unsigned short)(e | CE_OLD);
+                        }
+                        for (int q = 0; q < n_new; q += 2) {
+                            NxbU4 r = rng(c, stream, (unsigned)(q >> 1));
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                if (q + h < n_new) {
+                                    const double t = tma + len * (h ? nxb_u53(r.z, r.w) : nxb_u53(r.x, r.y));
+                                    int j = base + n_old + q + h - 1;
+                                    while (j >= base && ctm[j] > t) { ctm[j + 1] = ctm[j]; cedge[j + 1] = cedge[j]; --j; }
+                                    ctm[j + 1] = t; cedge[j + 1] = (unsigned short)e;
+                                }
                             }
                         }
                     }
+                    io += n_old;
                     base += n_old + n_new;
                     if (++e == E) { e = 0; ++k; }
                 }
@@ -757,8 +789,15 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
 
     // ---- B1: upward pass.  Every lane walks its own track through the edges in descending
     // index (children before parents), one boundary (event or edge top) per iteration, without
-    // waiting for the other lanes at edge boundaries.
+    // waiting for the other lanes at edge boundaries.  The next pool entry is prefetched one
+    // iteration ahead (the pool lives in L2).
     {
+        // thinning acceptance as integer thresholds: u32 < acc * 2^32
+        const unsigned long long thr_o0 = (unsigned long long)(ml.acc_blk[0] * 4294967296.0);
+        const unsigned long long thr_o1 = (unsigned long long)(ml.acc_blk[1] * 4294967296.0);
+        const unsigned long long thr_w0 = (unsigned long long)(ml.acc_blk[2] * 4294967296.0);
+        const unsigned long long thr_w1 = (unsigned long long)(ml.acc_blk[3] * 4294967296.0);
+        const double a_on = ml.a_on, a_off = ml.a_off;
         int e = trk ? E - 1 : -1;
         int ic = t_hi;                 // pool cursor (exclusive upper end)
         unsigned inited = 0u;          // live accumulator slots of this lane
@@ -766,6 +805,9 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         double tma = 0.0, rate = 0.0, tcur = 0.0, u0 = 1.0, u1 = 1.0, pen = 0.0;
         int s = 0, ip = 0, ip0 = 0, sa_slot = 0, sb_slot = -1;
         unsigned xold = 0u;
+        double pf_t = -NXB_INF;
+        unsigned pf_e = 0xffffu;       // edge | flags of the prefetched entry; 0xffff: none left
+        if (ic > t_lo) { pf_t = ctm[ic - 1]; pf_e = cedge[ic - 1]; }
         while (__any_sync(FULL, e >= 0)) {
             if (e >= 0) {
                 if (fresh) {
@@ -785,8 +827,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     fresh = false;
                 }
                 const double tp = (ip >= ip0) ? c.ptm[ip] : -NXB_INF;
-                const bool hasc = (ic > t_lo) && ((cedge[ic - 1] & CE_EDGE) == (unsigned)e);
-                const double tc = hasc ? ctm[ic - 1] : -NXB_INF;
+                const double tc = ((pf_e & CE_EDGE) == (unsigned)e) ? pf_t : -NXB_INF;
                 const double tnext = fmax(fmax(tp, tc), tma);
                 const bool own = (c.cls[s] == k);
                 // chunking.py:67-79: own class forces ON; ON pays the rate into class k
@@ -794,34 +835,33 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                 if (own) u0 = 0.0;
                 tcur = tnext;
                 if (tp == -NXB_INF && tc == -NXB_INF) {
-                    // top of the edge: fold into the parent's accumulator
-                    double mx = fmax(u0, u1);
-                    if (!(mx > 0.0)) { bad = 1; mx = 1.0; }
-                    const double r = 1.0 / mx;
-                    u0 *= r; u1 *= r;
+                    // top of the edge: fold into the parent's accumulator (one normalisation)
                     double* a = acc + (sa_slot * K + k) * 3;
-                    if ((inited >> sa_slot) & 1u) {
-                        double n0 = a[0] * u0, n1 = a[1] * u1;
-                        double m2 = fmax(n0, n1);
-                        if (!(m2 > 0.0)) { bad = 1; m2 = 1.0; }
-                        const double r2 = 1.0 / m2;
-                        a[0] = n0 * r2; a[1] = n1 * r2; a[2] += pen;
-                    } else { a[0] = u0; a[1] = u1; a[2] = pen; }
+                    double n0 = u0, n1 = u1, np = pen;
+                    if ((inited >> sa_slot) & 1u) { n0 *= a[0]; n1 *= a[1]; np += a[2]; }
+                    double m2 = fmax(n0, n1);
+                    if (!(m2 > 0.0)) { bad = 1; m2 = 1.0; }
+                    const double r2 = 1.0 / m2;
+                    a[0] = n0 * r2; a[1] = n1 * r2; a[2] = np;
                     inited |= 1u << sa_slot;
                     if (sb_slot >= 0) inited &= ~(1u << sb_slot);
                     --e;
                     fresh = true;
                 } else if (tc > tp) {
                     const int id = --ic;
+                    const unsigned flags = pf_e;
+                    if (ic > t_lo) { pf_t = ctm[ic - 1]; pf_e = cedge[ic - 1]; }
+                    else { pf_t = -NXB_INF; pf_e = 0xffffu; }
                     bool live = true;
-                    if (cedge[id] & CE_OLD) xold ^= 1u;
+                    if (flags & CE_OLD) xold ^= 1u;
                     else {
                         // poisson.py:111-116 by thinning the dominating process
-                        live = nxb_u32(nxb_xo_next(xo)) < ml.acc_blk[(own ? 2 : 0) + (int)xold];
-                        if (!live) cedge[id] |= CE_DEAD;
+                        const unsigned long long thr = own ? (xold ? thr_w1 : thr_w0) : (xold ? thr_o1 : thr_o0);
+                        live = (unsigned long long)nxb_xo_next(xo) < thr;
+                        if (!live) cedge[id] = (unsigned short)(flags | CE_DEAD);
                     }
                     if (live) {
-                        if (pen != 0.0) { u1 *= exp(-pen); pen = 0.0; }
+                        if (pen != 0.0) { u1 *= (double)expf((float)(-pen)); pen = 0.0; }
                         double ssum = u0 + u1;
                         if (!(ssum > 0.0)) { bad = 1; ssum = 1.0; }
                         const double r = 1.0 / ssum;
@@ -830,8 +870,8 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                         // uniformized 2x2 matrix of this context (poisson.py:92-96)
                         if (own) { u0 = 0.5 * l0 + 0.5 * l1; u1 = l1; }
                         else {
-                            u0 = (1.0 - ml.a_on) * l0 + ml.a_on * l1;
-                            u1 = ml.a_off * l0 + (1.0 - ml.a_off) * l1;
+                            u0 = l0 + a_on * (l1 - l0);
+                            u1 = l1 + a_off * (l0 - l1);
                         }
                     }
                 } else {
@@ -868,11 +908,14 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     const NxbSummaryLayout& sl = p.sl;
     int w = t_lo;
     {
+        const float a_on_f = (float)ml.a_on, a_off1_f = (float)(1.0 - ml.a_off);
         int e = trk ? 0 : E;
         int ic = t_lo;
         bool fresh = true;
         int s = 0, ip = 0, ipe = 0, vb = 0, n_on = 0, n_off = 0;
         double tmb = 0.0, tcur = 0.0, offtime = 0.0;
+        double pf_t = NXB_INF; unsigned pf_e = 0xffffu; float pf_l = 0.f;
+        if (ic < t_hi) { pf_t = ctm[ic]; pf_e = cedge[ic]; pf_l = cell[ic]; }
         while (__any_sync(FULL, e < E)) {
             if (e < E) {
                 if (fresh) {
@@ -886,20 +929,23 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     fresh = false;
                 }
                 const double tp = (ip < ipe) ? c.ptm[ip] : NXB_INF;
-                const bool hasc = (ic < t_hi) && ((cedge[ic] & CE_EDGE) == (unsigned)e);
-                const double tc = hasc ? ctm[ic] : NXB_INF;
+                const double tc = ((pf_e & CE_EDGE) == (unsigned)e) ? pf_t : NXB_INF;
                 const double tnext = fmin(fmin(tp, tc), tmb);
                 if (!x) offtime += tnext - tcur;
                 tcur = tnext;
                 if (tc < tp) {
-                    const int id = ic++;
-                    if (!(cedge[id] & CE_DEAD)) {
+                    const unsigned flags = pf_e;
+                    const float l1 = pf_l;
+                    ++ic;
+                    if (ic < t_hi) { pf_t = ctm[ic]; pf_e = cedge[ic]; pf_l = cell[ic]; }
+                    else { pf_t = NXB_INF; pf_e = 0xffffu; }
+                    if (!(flags & CE_DEAD)) {
                         const bool own = (c.cls[s] == k);
-                        const double l1 = (double)cell[id];
-                        const double p1 = own ? (x ? 1.0 : 0.5) : (x ? 1.0 - ml.a_off : ml.a_on);
-                        const double w1 = p1 * l1, w0 = (1.0 - p1) * (1.0 - l1);
-                        if (!(w0 + w1 > 0.0)) bad = 1;
-                        const unsigned xn = (nxb_u32(nxb_xo_next(xo)) * (w0 + w1) < w1) ? 1u : 0u;
+                        const float p1 = own ? (x ? 1.f : 0.5f) : (x ? a_off1_f : a_on_f);
+                        const float w1 = p1 * l1, w0 = (1.f - p1) * (1.f - l1);
+                        if (!(w0 + w1 > 0.f)) bad = 1;
+                        const float u = (float)(nxb_xo_next(xo) >> 8) * (1.0f / 16777216.0f);
+                        const unsigned xn = (u * (w0 + w1) < w1) ? 1u : 0u;
                         if (xn != x) {
                             ctm[w] = tc;
                             cedge[w] = (unsigned short)(e | (xn ? CE_NEW1 : 0u));
