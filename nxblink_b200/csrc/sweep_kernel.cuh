@@ -72,7 +72,7 @@ struct Ctx {
 };
 
 #define NXB_NBAR_PRIMARY 6
-#define NXB_NBAR_BLINK 4
+#define NXB_NBAR_BLINK 4   /* start, after B0 (setup), after B1, after B2 */
 
 __device__ __forceinline__ void phase_sync(Ctx& c) {
     if (c.bar_threads > 32 && ((c.sync_mask >> c.nbar) & 1u))
@@ -626,8 +626,6 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 // TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, lane k = track k
 // ---------------------------------------------------------------------------
 #define CE_EDGE 0x3fffu
-#define CE_OLD 0x4000u      // pool entry is a retained event of the old trajectory
-#define CE_DEAD 0x8000u     // candidate rejected by thinning
 #define CE_NEW1 0x4000u     // (survivors only) new state of the surviving event
 
 __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
@@ -636,11 +634,12 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     const NxbModelLayout& ml = p.ml;
     const int E = c.E, N = c.N, P = c.P, K = c.K, lane = c.lane;
 
-    // candidate pool: global (L2-resident) scratch of this warp slot
-    double* ctm = (double*)(c.gbase + p.g_off_ctm);
-    float* cell = (float*)(c.gbase + p.g_off_cell);             // ON-probability below the event
-    unsigned short* cedge = (unsigned short*)(c.gbase + p.g_off_cedge);
-    int* toff = (int*)(c.wbase + wl.off_toff);
+    // live foreground events of this sweep: global (L2-resident) scratch, one fixed region per
+    // track, filled by the upward pass and consumed backwards by the downward pass
+    const int TCAP = p.gcapC;
+    double* ctm = (double*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
+    float* cell = (float*)(c.gbase + p.g_off_cell) + (size_t)lane * TCAP;   // ON-probability below the event
+    unsigned short* cedge = (unsigned short*)(c.gbase + p.g_off_cedge) + (size_t)lane * TCAP;
     double* acc = (double*)(c.wbase + wl.off_acc);              // [slot][K][3]: u0, u1, penalty
     unsigned* newtol = (unsigned*)(c.wbase + wl.off_newtol);
     int* poff = c.poff;
@@ -648,168 +647,52 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     phase_sync(c);
     build_poff(c);
 
-    // ---- B0: candidate pool, (track, edge)-major, time-sorted.  Four consecutive pairs per
-    // lane and round: one Philox block gives the four dominating-Poisson counts, one warp scan
-    // places the lane's four regions.
-    const int npairs = K * E;
-    const int ngroups = (npairs + 3) >> 2;
-    int run = 0, cur = 0;
-    for (int g0 = 0; g0 < ngroups; g0 += 32) {
-        const int g = g0 + lane;
-        const bool valid = g < ngroups;
-        const int pfirst = g * 4;
-        int k0 = 0, e0 = 0;
-        if (valid) { k0 = pfirst / E; e0 = pfirst - k0 * E; }
-        // keys of this lane's first/last pair and of the round's last pair
-        const int plast = min(pfirst + 3, npairs - 1);
-        const int kl = plast / E;
-        const unsigned key_lo = ((unsigned)k0 << 16) | (unsigned)e0;
-        const unsigned key_hi = ((unsigned)kl << 16) | (unsigned)(plast - kl * E);
-        const int rlast = min((g0 + 32) * 4, npairs) - 1;
-        const int rk = rlast / E;
-        const unsigned key_round = ((unsigned)rk << 16) | (unsigned)(rlast - rk * E);
-        // old events of the round are a contiguous run starting at `cur`; this lane's are the
-        // sub-run [lo, hi)
-        int lo = cur, hi = cur, i = cur;
-        while (i < c.nB) {
-            const unsigned key = c.bcode[i] & 0x00ffffffu;
-            if (key > key_round) break;
-            lo += key < key_lo;
-            hi += key <= key_hi;
-            ++i;
-        }
-        cur = i;
-        unsigned n_new4 = 0, n_old4 = 0;
-        int size = 0;
-        if (valid) {
-            NxbU4 r = rng(c, NXB_STREAM_BLK_COUNT | (unsigned)g, 0u);
-            int k = k0, e = e0, io = lo;
-#pragma unroll 1
-            for (int m = 0; m < 4; ++m) {
-                if (pfirst + m < npairs) {
-                    const unsigned key = ((unsigned)k << 16) | (unsigned)e;
-                    int n_old = 0;
-                    while (io < hi && (c.bcode[io] & 0x00ffffffu) == key) { ++io; ++n_old; }
-                    int n_new = 0;
-                    if (c.len[e] > 0.0 && c.rate[e] > 0.0) {
-                        const unsigned word = (m == 0) ? r.x : (m == 1) ? r.y : (m == 2) ? r.z : r.w;
-                        n_new = min(poisson_inv(nxb_u32(word), c.p0_blk[e], c.lam_blk[e]), 255);
-                    }
-                    n_old = min(n_old, 255);
-                    n_new4 |= (unsigned)n_new << (8 * m);
-                    n_old4 |= (unsigned)n_old << (8 * m);
-                    size += n_old + n_new;
-                    if (++e == E) { e = 0; ++k; }
-                }
-            }
-        }
-        int tot;
-        int base = run + warp_excl_scan(size, lane, tot);
-        run += tot;
-        if (run > p.gcapC) { fail(c, NXB_ERR_SCRATCH_CAP, run); return RC_ERROR; }
-        if (valid) {
-            int k = k0, e = e0, io = lo;
-#pragma unroll 1
-            for (int m = 0; m < 4; ++m) {
-                if (pfirst + m < npairs) {
-                    const int n_old = (n_old4 >> (8 * m)) & 0xff, n_new = (n_new4 >> (8 * m)) & 0xff;
-                    if (e == 0) toff[k] = base;
-                    const double tma = c.tma[e], len = c.len[e];
-                    const unsigned stream = NXB_STREAM_BLK_PAIR | ((unsigned)k << 16) | (unsigned)e;
-                    if (n_old + n_new <= 4) {
-                        // common case: build the pair's sorted list in registers (no reads of
-                        // the L2-resident pool), then write it out once
-                        double r0 = NXB_INF, r1 = NXB_INF, r2 = NXB_INF, r3 = NXB_INF;
-                        unsigned f0 = 0u, f1 = 0u, f2 = 0u, f3 = 0u;
-                        if (n_old > 0) { r0 = c.btm[io]; f0 = CE_OLD; }
-                        if (n_old > 1) { r1 = c.btm[io + 1]; f1 = CE_OLD; }
-                        if (n_old > 2) { r2 = c.btm[io + 2]; f2 = CE_OLD; }
-                        if (n_old > 3) { r3 = c.btm[io + 3]; f3 = CE_OLD; }
-                        for (int q = 0; q < n_new; q += 2) {
-                            NxbU4 r = rng(c, stream, (unsigned)(q >> 1));
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                if (q + h < n_new) {
-                                    double t = tma + len * (h ? nxb_u53(r.z, r.w) : nxb_u53(r.x, r.y));
-                                    unsigned f = 0u;
-                                    // insert (t, f) into the sorted registers: the unused tail is +inf
-                                    if (t < r0) { double x_ = r0; r0 = t; t = x_; unsigned y_ = f0; f0 = f; f = y_; }
-                                    if (t < r1) { double x_ = r1; r1 = t; t = x_; unsigned y_ = f1; f1 = f; f = y_; }
-                                    if (t < r2) { double x_ = r2; r2 = t; t = x_; unsigned y_ = f2; f2 = f; f = y_; }
-                                    if (t < r3) { r3 = t; f3 = f; }
-                                }
-                            }
-                        }
-                        const int n = n_old + n_new;
-                        if (n > 0) { ctm[base] = r0; cedge[base] = (unsigned short)(e | f0); }
-                        if (n > 1) { ctm[base + 1] = r1; cedge[base + 1] = (unsigned short)(e | f1); }
-                        if (n > 2) { ctm[base + 2] = r2; cedge[base + 2] = (unsigned short)(e | f2); }
-                        if (n > 3) { ctm[base + 3] = r3; cedge[base + 3] = (unsigned short)(e | f3); }
-                    } else {
-                        for (int q = 0; q < n_old; ++q) {
-                            ctm[base + q] = c.btm[io + q];
-                            cedge[base + q] = (unsigned short)(e | CE_OLD);
-                        }
-                        for (int q = 0; q < n_new; q += 2) {
-                            NxbU4 r = rng(c, stream, (unsigned)(q >> 1));
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                if (q + h < n_new) {
-                                    const double t = tma + len * (h ? nxb_u53(r.z, r.w) : nxb_u53(r.x, r.y));
-                                    int j = base + n_old + q + h - 1;
-                                    while (j >= base && ctm[j] > t) { ctm[j + 1] = ctm[j]; cedge[j + 1] = cedge[j]; --j; }
-                                    ctm[j + 1] = t; cedge[j + 1] = (unsigned short)e;
-                                }
-                            }
-                        }
-                    }
-                    io += n_old;
-                    base += n_old + n_new;
-                    if (++e == E) { e = 0; ++k; }
-                }
-            }
-        }
-    }
-    if (lane == 0) toff[K] = run;
-    __syncwarp();
-    tick(c, T_B0);
-    phase_sync(c);
-
     const bool trk = lane < K;
     const int k = trk ? lane : 0;
-    const int t_lo = trk ? toff[k] : 0;
-    const int t_hi = trk ? toff[k + 1] : 0;
+    // retained events of track k are the contiguous run [olo, ohi) of the (track, edge, time)
+    // sorted list
+    int olo = 0, ohi = 0;
+    for (int i = 0; i < c.nB; ++i) {
+        const int kt = (int)((c.bcode[i] >> 16) & 0xffu);
+        olo += kt < k;
+        ohi += kt <= k;
+    }
     int bad = 0;
-    // per-track sequential stream for thinning and backward-sampling decisions
+    // per-track sequential stream: candidate gaps, thinning and backward-sampling decisions
     NxbXo xo;
     {
         NxbU4 r = rng(c, NXB_STREAM_BLK_FFBS | ((unsigned)k << 16), 0u);
         xo.s0 = r.x; xo.s1 = r.y; xo.s2 = r.z; xo.s3 = r.w | 1u;
     }
+    tick(c, T_B0);
+    phase_sync(c);
 
     // ---- B1: upward pass.  Every lane walks its own track through the edges in descending
-    // index (children before parents), one boundary (event or edge top) per iteration, without
-    // waiting for the other lanes at edge boundaries.  The next pool entry is prefetched one
-    // iteration ahead (the pool lives in L2).
+    // index (children before parents), one boundary per iteration: a retained event of the old
+    // trajectory, a candidate, a primary event, or the top of the edge.  Candidates are the
+    // arrivals of the dominating Poisson process of the edge, generated backwards in time by
+    // exponential gaps (poisson.py:22-50 draws count + uniform times; same process), then thinned
+    // to the local rate (poisson.py:111-116).  Only accepted ("live") events are stored.
+    int cnt = 0;                       // live events pushed by this lane
     {
-        // thinning acceptance as integer thresholds: u32 < acc * 2^32
         const unsigned long long thr_o0 = (unsigned long long)(ml.acc_blk[0] * 4294967296.0);
         const unsigned long long thr_o1 = (unsigned long long)(ml.acc_blk[1] * 4294967296.0);
         const unsigned long long thr_w0 = (unsigned long long)(ml.acc_blk[2] * 4294967296.0);
         const unsigned long long thr_w1 = (unsigned long long)(ml.acc_blk[3] * 4294967296.0);
         const double a_on = ml.a_on, a_off = ml.a_off;
+        const float gap_scale = (float)(0.6931471805599453 / (2.0 * fmax(ml.rate_on, ml.rate_off)));
         int e = trk ? E - 1 : -1;
-        int ic = t_hi;                 // pool cursor (exclusive upper end)
+        int io = ohi - 1;              // cursor into the retained events (descending)
         unsigned inited = 0u;          // live accumulator slots of this lane
         bool fresh = true;
         double tma = 0.0, rate = 0.0, tcur = 0.0, u0 = 1.0, u1 = 1.0, pen = 0.0;
+        double tcand = -NXB_INF;
+        float gsc = 0.f;
         int s = 0, ip = 0, ip0 = 0, sa_slot = 0, sb_slot = -1;
         unsigned xold = 0u;
-        double pf_t = -NXB_INF;
-        unsigned pf_e = 0xffffu;       // edge | flags of the prefetched entry; 0xffff: none left
-        if (ic > t_lo) { pf_t = ctm[ic - 1]; pf_e = cedge[ic - 1]; }
         while (__any_sync(FULL, e >= 0)) {
             if (e >= 0) {
+                bool draw_gap = false;
                 if (fresh) {
                     const int vb = e + 1, va = c.parent[e];
                     sb_slot = c.slot[vb]; sa_slot = c.slot[va];
@@ -824,17 +707,29 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     s = c.node_pri[vb];
                     xold = (c.node_tol[vb] >> k) & 1u;
                     ip = poff[e + 1] - 1; ip0 = poff[e];
+                    // dominating rate of the edge: 2 * max(on, off) * rate_e per unit time
+                    draw_gap = rate > 0.0 && tcur > tma;
+                    gsc = draw_gap ? gap_scale / (float)rate : 0.f;
+                    tcand = tcur;
+                    if (!draw_gap) tcand = -NXB_INF;
                     fresh = false;
                 }
+                if (draw_gap) {
+                    const float f = ((float)(nxb_xo_next(xo) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                    tcand -= (double)(-__log2f(f) * gsc);
+                    if (!(tcand > tma)) tcand = -NXB_INF;
+                }
                 const double tp = (ip >= ip0) ? c.ptm[ip] : -NXB_INF;
-                const double tc = ((pf_e & CE_EDGE) == (unsigned)e) ? pf_t : -NXB_INF;
-                const double tnext = fmax(fmax(tp, tc), tma);
+                const bool haso = (io >= olo) && ((c.bcode[io] & 0xffffu) == (unsigned)e);
+                const double to = haso ? c.btm[io] : -NXB_INF;
+                const double tf = fmax(to, tcand);
+                const double tnext = fmax(fmax(tp, tf), tma);
                 const bool own = (c.cls[s] == k);
                 // chunking.py:67-79: own class forces ON; ON pays the rate into class k
                 pen += c.qm[s * K + k] * rate * (tcur - tnext);
                 if (own) u0 = 0.0;
                 tcur = tnext;
-                if (tp == -NXB_INF && tc == -NXB_INF) {
+                if (tp == -NXB_INF && tf == -NXB_INF) {
                     // top of the edge: fold into the parent's accumulator (one normalisation)
                     double* a = acc + (sa_slot * K + k) * 3;
                     double n0 = u0, n1 = u1, np = pen;
@@ -847,18 +742,16 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     if (sb_slot >= 0) inited &= ~(1u << sb_slot);
                     --e;
                     fresh = true;
-                } else if (tc > tp) {
-                    const int id = --ic;
-                    const unsigned flags = pf_e;
-                    if (ic > t_lo) { pf_t = ctm[ic - 1]; pf_e = cedge[ic - 1]; }
-                    else { pf_t = -NXB_INF; pf_e = 0xffffu; }
+                } else if (tf > tp) {
                     bool live = true;
-                    if (flags & CE_OLD) xold ^= 1u;
+                    if (to > tcand) { xold ^= 1u; --io; }
                     else {
-                        // poisson.py:111-116 by thinning the dominating process
                         const unsigned long long thr = own ? (xold ? thr_w1 : thr_w0) : (xold ? thr_o1 : thr_o0);
                         live = (unsigned long long)nxb_xo_next(xo) < thr;
-                        if (!live) cedge[id] = (unsigned short)(flags | CE_DEAD);
+                        // next arrival of the dominating process (rootward)
+                        const float f = ((float)(nxb_xo_next(xo) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                        tcand -= (double)(-__log2f(f) * gsc);
+                        if (!(tcand > tma)) tcand = -NXB_INF;
                     }
                     if (live) {
                         if (pen != 0.0) { u1 *= (double)expf((float)(-pen)); pen = 0.0; }
@@ -866,7 +759,10 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                         if (!(ssum > 0.0)) { bad = 1; ssum = 1.0; }
                         const double r = 1.0 / ssum;
                         const double l1 = u1 * r, l0 = u0 * r;
-                        cell[id] = (float)l1;
+                        if (cnt < TCAP) {
+                            ctm[cnt] = tnext; cell[cnt] = (float)l1; cedge[cnt] = (unsigned short)e;
+                        } else bad = 2;
+                        ++cnt;
                         // uniformized 2x2 matrix of this context (poisson.py:92-96)
                         if (own) { u0 = 0.5 * l0 + 0.5 * l1; u1 = l1; }
                         else {
@@ -896,26 +792,29 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         if (!(w0 + w1 > 0.0)) bad = 1;
         x = (nxb_u32(nxb_xo_next(xo)) * (w0 + w1) < w1) ? 1u : 0u;
     }
-    if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_INFEASIBLE, -2); return RC_ERROR; }
     {
+        const int worst = __reduce_max_sync(FULL, bad);
+        if (worst == 2) { fail(c, NXB_ERR_SCRATCH_CAP, cnt); return RC_ERROR; }
+        if (worst) { fail(c, NXB_ERR_INFEASIBLE, -2); return RC_ERROR; }
         unsigned bal = __ballot_sync(FULL, x);
         for (int v = lane; v < N; v += 32) newtol[v] = (v == 0) ? bal : 0u;
     }
     __syncwarp();
 
-    // ---- B2: downward sampling, edges in ascending index, same flattened walk; the OFF-time and
-    // transition statistics are fused in (summary.py:123-131,234-243)
+    // ---- B2: downward sampling, edges in ascending index: the live events are read back in
+    // reverse; survivors (real transitions) are written from the top of the region downwards.
+    // The OFF-time and transition statistics are fused in (summary.py:123-131,234-243).
     const NxbSummaryLayout& sl = p.sl;
-    int w = t_lo;
+    int wtop = TCAP - 1;
     {
         const float a_on_f = (float)ml.a_on, a_off1_f = (float)(1.0 - ml.a_off);
         int e = trk ? 0 : E;
-        int ic = t_lo;
+        int ir = cnt - 1;              // read cursor (descending)
         bool fresh = true;
         int s = 0, ip = 0, ipe = 0, vb = 0, n_on = 0, n_off = 0;
         double tmb = 0.0, tcur = 0.0, offtime = 0.0;
         double pf_t = NXB_INF; unsigned pf_e = 0xffffu; float pf_l = 0.f;
-        if (ic < t_hi) { pf_t = ctm[ic]; pf_e = cedge[ic]; pf_l = cell[ic]; }
+        if (ir >= 0) { pf_t = ctm[ir]; pf_e = cedge[ir]; pf_l = cell[ir]; }
         while (__any_sync(FULL, e < E)) {
             if (e < E) {
                 if (fresh) {
@@ -929,30 +828,27 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     fresh = false;
                 }
                 const double tp = (ip < ipe) ? c.ptm[ip] : NXB_INF;
-                const double tc = ((pf_e & CE_EDGE) == (unsigned)e) ? pf_t : NXB_INF;
+                const double tc = (pf_e == (unsigned)e) ? pf_t : NXB_INF;
                 const double tnext = fmin(fmin(tp, tc), tmb);
                 if (!x) offtime += tnext - tcur;
                 tcur = tnext;
                 if (tc < tp) {
-                    const unsigned flags = pf_e;
                     const float l1 = pf_l;
-                    ++ic;
-                    if (ic < t_hi) { pf_t = ctm[ic]; pf_e = cedge[ic]; pf_l = cell[ic]; }
+                    --ir;
+                    if (ir >= 0) { pf_t = ctm[ir]; pf_e = cedge[ir]; pf_l = cell[ir]; }
                     else { pf_t = NXB_INF; pf_e = 0xffffu; }
-                    if (!(flags & CE_DEAD)) {
-                        const bool own = (c.cls[s] == k);
-                        const float p1 = own ? (x ? 1.f : 0.5f) : (x ? a_off1_f : a_on_f);
-                        const float w1 = p1 * l1, w0 = (1.f - p1) * (1.f - l1);
-                        if (!(w0 + w1 > 0.f)) bad = 1;
-                        const float u = (float)(nxb_xo_next(xo) >> 8) * (1.0f / 16777216.0f);
-                        const unsigned xn = (u * (w0 + w1) < w1) ? 1u : 0u;
-                        if (xn != x) {
-                            ctm[w] = tc;
-                            cedge[w] = (unsigned short)(e | (xn ? CE_NEW1 : 0u));
-                            ++w;
-                            if (xn) ++n_on; else ++n_off;
-                            x = xn;
-                        }
+                    const bool own = (c.cls[s] == k);
+                    const float p1 = own ? (x ? 1.f : 0.5f) : (x ? a_off1_f : a_on_f);
+                    const float w1 = p1 * l1, w0 = (1.f - p1) * (1.f - l1);
+                    if (!(w0 + w1 > 0.f)) bad = 1;
+                    const float u = (float)(nxb_xo_next(xo) >> 8) * (1.0f / 16777216.0f);
+                    const unsigned xn = (u * (w0 + w1) < w1) ? 1u : 0u;
+                    if (xn != x) {
+                        ctm[wtop] = tc;
+                        cedge[wtop] = (unsigned short)(e | (xn ? CE_NEW1 : 0u));
+                        --wtop;
+                        if (xn) ++n_on; else ++n_off;
+                        x = xn;
                     }
                 } else {
                     // primary event or the bottom of the edge: close the OFF-time segment
@@ -981,7 +877,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     phase_sync(c);
 
     // ---- write back: new retained blink events, (track, edge, time) order -----------------------------
-    int n_mine = trk ? (w - t_lo) : 0, total;
+    int n_mine = trk ? (TCAP - 1 - wtop) : 0, total;
     int dst = warp_excl_scan(n_mine, lane, total);
     for (int v = lane; v < N; v += 32) c.node_tol[v] = newtol[v];
     if (accumulate && lane == 0) {
@@ -991,31 +887,27 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         atomicAdd(&c.s_root_on_cls[c.cls[c.node_pri[0]]], (unsigned long long)on);
         atomicAdd(&c.s_root_misc[2], 1ull);
     }
-    if (total > wl.capB) {
+    double* obtm = c.btm; unsigned* obcode = c.bcode;
+    const bool spill = total > wl.capB;
+    if (spill) {
         // The sweep is complete and its statistics are booked; only the shared-memory
         // arrays are too small.  Spill the new blink list straight to the HBM slab and
         // let the next capacity tier pick the unit up at the next sweep boundary.
         if (total > p.gcapB) { fail(c, NXB_ERR_STATE_CAP, total); return RC_ERROR; }
         unsigned char* slab = p.state + c.unit * p.state_stride;
-        double* gbtm = (double*)(slab + p.so_btm);
-        unsigned* gbcode = (unsigned*)(slab + p.so_bcode);
-        for (int q = 0; q < n_mine; ++q) {
-            gbtm[dst + q] = ctm[t_lo + q];
-            gbcode[dst + q] = (unsigned)(cedge[t_lo + q] & CE_EDGE) | ((unsigned)k << 16)
-                              | ((cedge[t_lo + q] & CE_NEW1) ? (1u << 31) : 0u);
-        }
-        c.nB = -total;      // negative: already in HBM
-        __syncwarp();
-        return RC_DEFER;
+        obtm = (double*)(slab + p.so_btm);
+        obcode = (unsigned*)(slab + p.so_bcode);
     }
     for (int q = 0; q < n_mine; ++q) {
-        c.btm[dst + q] = ctm[t_lo + q];
-        c.bcode[dst + q] = (unsigned)(cedge[t_lo + q] & CE_EDGE) | ((unsigned)k << 16)
-                           | ((cedge[t_lo + q] & CE_NEW1) ? (1u << 31) : 0u);
+        const int src = TCAP - 1 - q;          // first survivor (rootmost, earliest) sits at the top
+        const unsigned ce = cedge[src];
+        obtm[dst + q] = ctm[src];
+        obcode[dst + q] = (unsigned)(ce & CE_EDGE) | ((unsigned)k << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);
     }
-    c.nB = total;
     __syncwarp();
     tick(c, T_BW);
+    if (spill) { c.nB = -total; return RC_DEFER; }
+    c.nB = total;
     return RC_OK;
 }
 

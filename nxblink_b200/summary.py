@@ -101,6 +101,9 @@ class Summary(object):
         Doff = dwell[L.d_off:L.d_off + E * P * K].reshape(E, P, K)
         colcls = pm.state_class[pm.q_col]
         pri_dwell = T[:, pm.q_row] - Doff[:, pm.q_row, colcls]          # [E, nnz]
+        # T and Doff are sums of the same time pieces in different orders: a class that was
+        # OFF for the whole stay leaves a rounding residue instead of an exact zero
+        pri_dwell = np.where(pri_dwell > 1e-11 * T[:, pm.q_row], pri_dwell, 0.0)
         off_xon_dwell = Doff.sum(axis=(1, 2))
         xon_off_dwell = (K - 1) * T.sum(axis=1) - off_xon_dwell
         self.flat = dict(pri_trans=pri_trans, pri_dwell=pri_dwell, off_on=off_on,
