@@ -625,6 +625,15 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 // ---------------------------------------------------------------------------
 // TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, lane k = track k
 // ---------------------------------------------------------------------------
+// Exponential gap of the dominating Poisson process, mean gsc / ln 2 (time units).  The
+// logarithm is taken in f32 (23-bit uniform, accurate log2f so that the gap is strictly
+// positive); a second word spreads the result over the f64 grid so that event times never tie.
+__device__ __forceinline__ double exp_gap(NxbXo& xo, float gsc) {
+    const float f = ((float)(nxb_xo_next(xo) >> 9) + 0.5f) * (1.0f / 8388608.0f);   // in (0,1), exact
+    const double g = (double)(-log2f(f) * gsc);
+    return g * (1.0 + ((double)nxb_xo_next(xo) + 0.5) * (1.0 / 72057594037927936.0));   // * (1 + u * 2^-24)
+}
+
 #define CE_EDGE 0x3fffu
 #define CE_NEW1 0x4000u     // (survivors only) new state of the surviving event
 
@@ -673,6 +682,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     // arrivals of the dominating Poisson process of the edge, generated backwards in time by
     // exponential gaps (poisson.py:22-50 draws count + uniform times; same process), then thinned
     // to the local rate (poisson.py:111-116).  Only accepted ("live") events are stored.
+    // (log2f, not the MUFU approximation: the gap must be strictly positive for f close to 1.)
     int cnt = 0;                       // live events pushed by this lane
     {
         const unsigned long long thr_o0 = (unsigned long long)(ml.acc_blk[0] * 4294967296.0);
@@ -715,8 +725,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     fresh = false;
                 }
                 if (draw_gap) {
-                    const float f = ((float)(nxb_xo_next(xo) >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                    tcand -= (double)(-__log2f(f) * gsc);
+                    tcand -= exp_gap(xo, gsc);
                     if (!(tcand > tma)) tcand = -NXB_INF;
                 }
                 const double tp = (ip >= ip0) ? c.ptm[ip] : -NXB_INF;
@@ -747,10 +756,10 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     if (to > tcand) { xold ^= 1u; --io; }
                     else {
                         const unsigned long long thr = own ? (xold ? thr_w1 : thr_w0) : (xold ? thr_o1 : thr_o0);
-                        live = (unsigned long long)nxb_xo_next(xo) < thr;
+                        // (a candidate that ties with a retained event is dropped: probability ~2^-50)
+                        live = ((unsigned long long)nxb_xo_next(xo) < thr) && (tcand != to);
                         // next arrival of the dominating process (rootward)
-                        const float f = ((float)(nxb_xo_next(xo) >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                        tcand -= (double)(-__log2f(f) * gsc);
+                        tcand -= exp_gap(xo, gsc);
                         if (!(tcand > tma)) tcand = -NXB_INF;
                     }
                     if (live) {
@@ -759,6 +768,9 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                         if (!(ssum > 0.0)) { bad = 1; ssum = 1.0; }
                         const double r = 1.0 / ssum;
                         const double l1 = u1 * r, l0 = u0 * r;
+                        if (p.validate && cnt > 0 && cnt < TCAP && cedge[cnt - 1] == (unsigned short)e && !(ctm[cnt - 1] > tnext))
+                            printf("[nxb B1] unit %lld sweep %u k %d e %d cnt %d prev %.17g tnext %.17g to %.17g tcand %.17g tp %.17g tma %.17g gsc %g\n",
+                                   c.unit, c.sweep, k, e, cnt, ctm[cnt - 1], tnext, to, tcand, tp, tma, (double)gsc);
                         if (cnt < TCAP) {
                             ctm[cnt] = tnext; cell[cnt] = (float)l1; cedge[cnt] = (unsigned short)e;
                         } else bad = 2;
@@ -973,7 +985,11 @@ __device__ __forceinline__ int validate_unit(Ctx& c) {
     }
     for (int i = lane; i + 1 < c.nB; i += 32) {
         unsigned ka = c.bcode[i] & 0xffffffu, kb = c.bcode[i + 1] & 0xffffffu;
-        if (ka > kb || (ka == kb && !(c.btm[i] < c.btm[i + 1]))) bad = 2;
+        if (ka > kb || (ka == kb && !(c.btm[i] < c.btm[i + 1]))) {
+            bad = 2;
+            printf("[nxb validate] unit %lld sweep %u blink order: i=%d/%d key %06x %06x time %.17g %.17g\n",
+                   c.unit, c.sweep, i, c.nB, ka, kb, c.btm[i], c.btm[i + 1]);
+        }
     }
     if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_INVARIANT, __reduce_max_sync(FULL, bad)); return RC_ERROR; }
     // edge-major view of the blink events

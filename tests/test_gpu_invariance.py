@@ -94,3 +94,16 @@ def test_conservation_properties_at_scale(nb):
     R = (st['n_pri_events'] + st['n_blk_events']) / st['n_units']
     assert 60 < R < 160          # ~84-121 retained events at the p53 shape
     s.close()
+
+
+def test_invariants_hold_over_a_million_unit_sweeps(nb):
+    """Every trajectory invariant (sorted strictly increasing event times, compatible
+    transitions, own class ON, data constraints; navigation.py:39-44,121-135) checked after
+    every phase of 1.3 million unit-sweeps at the p53 shape."""
+    pm, data = _p53_inputs(4096)
+    s = nb.BlinkSampler(pm, validate=True)
+    s.set_data(data)
+    s.init_chains(chains=16, seed=3)
+    s.sweep(20, accumulate=True)
+    assert s.summary().nsamples == 4096 * 16 * 20
+    s.close()
