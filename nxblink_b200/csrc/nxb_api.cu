@@ -800,7 +800,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             h->g_off_msg = o; o += (h->msg_f64 ? 8 : 4) * (h->gcapF + 1) * NXB_PPAD;
             o = align_up(o, 16);
             h->g_off_ctm = o; o += 8 * h->gcapC * 32;      // one region per lane (track)
-            h->g_off_cell = o; o += 4 * h->gcapC * 32;
+            h->g_off_cell = o; o += 8 * h->gcapC * 32;     // float2 per live event
             h->g_off_cedge = o; o += 2 * h->gcapC * 32;
             h->gscratch_stride = align_up(o, 256);
             cudaError_t e1 = cudaMalloc(&h->d_gscratch, (size_t)h->gscratch_stride * max_w * h->num_sms);

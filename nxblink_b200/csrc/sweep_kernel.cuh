@@ -626,12 +626,20 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 // TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, lane k = track k
 // ---------------------------------------------------------------------------
 // Exponential gap of the dominating Poisson process, mean gsc / ln 2 (time units).  The
-// logarithm is taken in f32 (23-bit uniform, accurate log2f so that the gap is strictly
-// positive); a second word spreads the result over the f64 grid so that event times never tie.
+// logarithm is taken in f32 (23-bit uniform); a second word spreads the result over the f64 grid so that event times never tie.
 __device__ __forceinline__ double exp_gap(NxbXo& xo, float gsc) {
     const float f = ((float)(nxb_xo_next(xo) >> 9) + 0.5f) * (1.0f / 8388608.0f);   // in (0,1), exact
-    const double g = (double)(-log2f(f) * gsc);
+    // MUFU.LG2 has ~2^-22 absolute error, which only matters for f within 1e-6 of 1: clamp so
+    // that the gap stays strictly positive (affects one draw in a million by < 1e-7 of a mean gap)
+    const double g = (double)(fmaxf(-__log2f(f), 5.9604645e-8f) * gsc);
     return g * (1.0 + ((double)nxb_xo_next(xo) + 0.5) * (1.0 / 72057594037927936.0));   // * (1 + u * 2^-24)
+}
+
+// 2^-floor(log2 m) for a positive finite m: exact power-of-two rescaling that keeps message
+// magnitudes in [1, 2) without a division and preserves exact zeros of the other component.
+__device__ __forceinline__ double pow2_rescale(double m) {
+    const long long bits = __double_as_longlong(m);
+    return __longlong_as_double((0x7fdLL << 52) - (bits & (0x7ffLL << 52)));
 }
 
 #define CE_EDGE 0x3fffu
@@ -647,7 +655,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     // track, filled by the upward pass and consumed backwards by the downward pass
     const int TCAP = p.gcapC;
     double* ctm = (double*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
-    float* cell = (float*)(c.gbase + p.g_off_cell) + (size_t)lane * TCAP;   // ON-probability below the event
+    float2* cell = (float2*)(c.gbase + p.g_off_cell) + (size_t)lane * TCAP;  // (OFF, ON) message below the event
     unsigned short* cedge = (unsigned short*)(c.gbase + p.g_off_cedge) + (size_t)lane * TCAP;
     double* acc = (double*)(c.wbase + wl.off_acc);              // [slot][K][3]: u0, u1, penalty
     unsigned* newtol = (unsigned*)(c.wbase + wl.off_newtol);
@@ -682,7 +690,6 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     // arrivals of the dominating Poisson process of the edge, generated backwards in time by
     // exponential gaps (poisson.py:22-50 draws count + uniform times; same process), then thinned
     // to the local rate (poisson.py:111-116).  Only accepted ("live") events are stored.
-    // (log2f, not the MUFU approximation: the gap must be strictly positive for f close to 1.)
     int cnt = 0;                       // live events pushed by this lane
     {
         const unsigned long long thr_o0 = (unsigned long long)(ml.acc_blk[0] * 4294967296.0);
@@ -745,7 +752,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     if ((inited >> sa_slot) & 1u) { n0 *= a[0]; n1 *= a[1]; np += a[2]; }
                     double m2 = fmax(n0, n1);
                     if (!(m2 > 0.0)) { bad = 1; m2 = 1.0; }
-                    const double r2 = 1.0 / m2;
+                    const double r2 = pow2_rescale(m2);
                     a[0] = n0 * r2; a[1] = n1 * r2; a[2] = np;
                     inited |= 1u << sa_slot;
                     if (sb_slot >= 0) inited &= ~(1u << sb_slot);
@@ -764,15 +771,13 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     }
                     if (live) {
                         if (pen != 0.0) { u1 *= (double)expf((float)(-pen)); pen = 0.0; }
-                        double ssum = u0 + u1;
-                        if (!(ssum > 0.0)) { bad = 1; ssum = 1.0; }
-                        const double r = 1.0 / ssum;
-                        const double l1 = u1 * r, l0 = u0 * r;
-                        if (p.validate && cnt > 0 && cnt < TCAP && cedge[cnt - 1] == (unsigned short)e && !(ctm[cnt - 1] > tnext))
-                            printf("[nxb B1] unit %lld sweep %u k %d e %d cnt %d prev %.17g tnext %.17g to %.17g tcand %.17g tp %.17g tma %.17g gsc %g\n",
-                                   c.unit, c.sweep, k, e, cnt, ctm[cnt - 1], tnext, to, tcand, tp, tma, (double)gsc);
+                        double mx = fmax(u0, u1);
+                        if (!(mx > 0.0)) { bad = 1; mx = 1.0; }
+                        const double r = pow2_rescale(mx);
+                        const double l1 = u1 * r, l0 = u0 * r;       // scale-free message below the event
                         if (cnt < TCAP) {
-                            ctm[cnt] = tnext; cell[cnt] = (float)l1; cedge[cnt] = (unsigned short)e;
+                            ctm[cnt] = tnext; cell[cnt] = make_float2((float)l0, (float)l1);
+                            cedge[cnt] = (unsigned short)e;
                         } else bad = 2;
                         ++cnt;
                         // uniformized 2x2 matrix of this context (poisson.py:92-96)
@@ -825,7 +830,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         bool fresh = true;
         int s = 0, ip = 0, ipe = 0, vb = 0, n_on = 0, n_off = 0;
         double tmb = 0.0, tcur = 0.0, offtime = 0.0;
-        double pf_t = NXB_INF; unsigned pf_e = 0xffffu; float pf_l = 0.f;
+        double pf_t = NXB_INF; unsigned pf_e = 0xffffu; float2 pf_l = make_float2(0.f, 0.f);
         if (ir >= 0) { pf_t = ctm[ir]; pf_e = cedge[ir]; pf_l = cell[ir]; }
         while (__any_sync(FULL, e < E)) {
             if (e < E) {
@@ -845,13 +850,13 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                 if (!x) offtime += tnext - tcur;
                 tcur = tnext;
                 if (tc < tp) {
-                    const float l1 = pf_l;
+                    const float l0 = pf_l.x, l1 = pf_l.y;
                     --ir;
                     if (ir >= 0) { pf_t = ctm[ir]; pf_e = cedge[ir]; pf_l = cell[ir]; }
                     else { pf_t = NXB_INF; pf_e = 0xffffu; }
                     const bool own = (c.cls[s] == k);
                     const float p1 = own ? (x ? 1.f : 0.5f) : (x ? a_off1_f : a_on_f);
-                    const float w1 = p1 * l1, w0 = (1.f - p1) * (1.f - l1);
+                    const float w1 = p1 * l1, w0 = (1.f - p1) * l0;
                     if (!(w0 + w1 > 0.f)) bad = 1;
                     const float u = (float)(nxb_xo_next(xo) >> 8) * (1.0f / 16777216.0f);
                     const unsigned xn = (u * (w0 + w1) < w1) ? 1u : 0u;
@@ -985,11 +990,7 @@ __device__ __forceinline__ int validate_unit(Ctx& c) {
     }
     for (int i = lane; i + 1 < c.nB; i += 32) {
         unsigned ka = c.bcode[i] & 0xffffffu, kb = c.bcode[i + 1] & 0xffffffu;
-        if (ka > kb || (ka == kb && !(c.btm[i] < c.btm[i + 1]))) {
-            bad = 2;
-            printf("[nxb validate] unit %lld sweep %u blink order: i=%d/%d key %06x %06x time %.17g %.17g\n",
-                   c.unit, c.sweep, i, c.nB, ka, kb, c.btm[i], c.btm[i + 1]);
-        }
+        if (ka > kb || (ka == kb && !(c.btm[i] < c.btm[i + 1]))) bad = 2;
     }
     if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_INVARIANT, __reduce_max_sync(FULL, bad)); return RC_ERROR; }
     // edge-major view of the blink events
