@@ -126,6 +126,21 @@ int nxb_last_kernel_ms(nxb_handle* h, float* total_ms, int32_t* n_launches);
  * copied out and cleared.  Diagnostic only. */
 int nxb_profile(nxb_handle* h, int32_t enable, uint64_t* cycles12);
 
+/* ---- deterministic dense path (FP64 tensor pipe) --------------------------------------
+ * P_b = expm(Q * t_b), b < batch, for one n x n rate matrix (row-major, n <= 64).
+ * Replaces scipy.linalg.expm per edge, examples/codon2x3/toymodel-analytic.py:112-121.
+ * Host buffers: Q[n*n], t[batch], out[batch*n*n]. */
+int nxb_expm_batched(int device, int32_t n, int32_t batch, const double* Q, const double* t,
+                     double* out);
+/* Pruning log-likelihood per site.  Replaces nxmctree.dynamic_fset_lhood.get_lhood,
+ * toymodel-analytic.py:123-126.  parent[v] < v, root 0; P[e] is the n x n transition
+ * matrix of the edge into node e+1; masks[s*n_nodes+v] bit i: state i feasible at node v
+ * of site s.  Host buffers. */
+int nxb_pruning_loglik(int device, int32_t n, int32_t n_nodes, const int32_t* parent,
+                       const double* P, const double* prior, int64_t n_sites,
+                       const uint64_t* masks, double* loglik);
+const char* nxb_dense_last_error(void);
+
 /* Known-answer hook for the counter-based generator (host code path). */
 void nxb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
