@@ -137,14 +137,16 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             if (hdr.phase != NXB_PHASE_INIT) {
                 const unsigned* g_tol = (const unsigned*)(slab + p.so_tol);
                 const unsigned* g_npri = (const unsigned*)(slab + p.so_pri);
-                for (int v = lane; v < N; v += 32) c.node_tol[v] = g_tol[v];
-                for (int v = lane; v < (N + 3) / 4; v += 32) ((unsigned*)c.node_pri)[v] = g_npri[v];
+                // streaming (evict-first) accesses: the slab is touched once per launch and must
+                // not displace the L2-resident scratch of the resident warps
+                for (int v = lane; v < N; v += 32) c.node_tol[v] = __ldcs(g_tol + v);
+                for (int v = lane; v < (N + 3) / 4; v += 32) ((unsigned*)c.node_pri)[v] = __ldcs(g_npri + v);
                 const double* g_ptm = (const double*)(slab + p.so_ptm);
                 const unsigned* g_pcode = (const unsigned*)(slab + p.so_pcode);
-                for (int i = lane; i < c.nP; i += 32) { c.ptm[i] = g_ptm[i]; c.pcode[i] = g_pcode[i]; }
+                for (int i = lane; i < c.nP; i += 32) { c.ptm[i] = __ldcs(g_ptm + i); c.pcode[i] = __ldcs(g_pcode + i); }
                 const double* g_btm = (const double*)(slab + p.so_btm);
                 const unsigned* g_bcode = (const unsigned*)(slab + p.so_bcode);
-                for (int i = lane; i < c.nB; i += 32) { c.btm[i] = g_btm[i]; c.bcode[i] = g_bcode[i]; }
+                for (int i = lane; i < c.nB; i += 32) { c.btm[i] = __ldcs(g_btm + i); c.bcode[i] = __ldcs(g_bcode + i); }
             }
             __syncwarp();
         }
@@ -200,15 +202,15 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
                 if (hdr.phase != NXB_PHASE_INIT) {
                     unsigned* g_tol = (unsigned*)(slab + p.so_tol);
                     unsigned* g_npri = (unsigned*)(slab + p.so_pri);
-                    for (int v = lane; v < N; v += 32) g_tol[v] = c.node_tol[v];
-                    for (int v = lane; v < (N + 3) / 4; v += 32) g_npri[v] = ((unsigned*)c.node_pri)[v];
+                    for (int v = lane; v < N; v += 32) __stcs(g_tol + v, c.node_tol[v]);
+                    for (int v = lane; v < (N + 3) / 4; v += 32) __stcs(g_npri + v, ((unsigned*)c.node_pri)[v]);
                     double* g_ptm = (double*)(slab + p.so_ptm);
                     unsigned* g_pcode = (unsigned*)(slab + p.so_pcode);
-                    for (int i = lane; i < c.nP; i += 32) { g_ptm[i] = c.ptm[i]; g_pcode[i] = c.pcode[i]; }
+                    for (int i = lane; i < c.nP; i += 32) { __stcs(g_ptm + i, c.ptm[i]); __stcs(g_pcode + i, c.pcode[i]); }
                     if (!spilled) {
                         double* g_btm = (double*)(slab + p.so_btm);
                         unsigned* g_bcode = (unsigned*)(slab + p.so_bcode);
-                        for (int i = lane; i < c.nB; i += 32) { g_btm[i] = c.btm[i]; g_bcode[i] = c.bcode[i]; }
+                        for (int i = lane; i < c.nB; i += 32) { __stcs(g_btm + i, c.btm[i]); __stcs(g_bcode + i, c.bcode[i]); }
                     }
                 }
                 if (rc == RC_DEFER && lane == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)u;
