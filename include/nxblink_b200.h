@@ -116,6 +116,14 @@ int nxb_export_unit(nxb_handle* h, int64_t unit, int32_t* node_pri, uint32_t* no
                     int32_t* n_blk, double* blk_time, int32_t* blk_edge,
                     int32_t* blk_track, int32_t* blk_state);
 
+/* Forward (prior) simulation of n_units independent trajectories from the model, root to
+ * leaves (nxblink/fwdsample.py:67-262 gen_forward_samples), written into the unit slabs: they can
+ * then be summarised (nxb_summarize_current), exported (nxb_export_unit, nxb_read_node_states:
+ * synthetic alignments) or swept.  Replaces any data previously set with unconstrained data. */
+int nxb_forward_sample(nxb_handle* h, int64_t n_units, uint64_t seed, int64_t unit_offset);
+/* Node states of every unit: node_pri[n_units*N], node_tol[n_units*N] (bit k: class k on). */
+int nxb_read_node_states(nxb_handle* h, int32_t* node_pri, uint32_t* node_tol);
+
 int nxb_get_stats(nxb_handle* h, nxb_stats* out);
 /* Last sweep-kernel launch times (ms, CUDA events on the launching stream). */
 int nxb_last_kernel_ms(nxb_handle* h, float* total_ms, int32_t* n_launches);

@@ -64,6 +64,7 @@ EXPORTS = (
     'nxb_summarize_current', 'nxb_export_unit', 'nxb_get_stats',
     'nxb_last_kernel_ms', 'nxb_profile', 'nxb_philox4x32_10',
     'nxb_expm_batched', 'nxb_pruning_loglik', 'nxb_dense_last_error',
+    'nxb_forward_sample', 'nxb_read_node_states',
 )
 
 _lib = None
@@ -102,6 +103,8 @@ def load():
     lib.nxb_pruning_loglik.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.nxb_dense_last_error.restype = C.c_char_p
+    lib.nxb_forward_sample.argtypes = [H, C.c_int64, C.c_uint64, C.c_int64]
+    lib.nxb_read_node_states.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.nxb_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nxb_philox4x32_10.restype = None
     for name in EXPORTS:

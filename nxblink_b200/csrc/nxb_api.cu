@@ -319,6 +319,171 @@ __global__ void summarize_kernel(const __grid_constant__ NxbSweepParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Forward (prior) simulation of the blink process, root to leaves: the Gillespie loop of
+// nxblink/fwdsample.py:67-262, one thread per unit, written straight into the unit slabs so that
+// the sampled trajectories can be summarised, exported or used as chain states.
+// Semantics: the primary state's own tolerance class cannot switch off (the reference's
+// comment at fwdsample.py:57-59; its guard at :60-64 tests the wrong track and lets it through,
+// SURVEY.md component 13).  Root: primary ~ prior, own class ON, other classes ~ blink prior.
+// ---------------------------------------------------------------------------
+__global__ void forward_kernel(const __grid_constant__ NxbSweepParams p, int cap_events,
+                               unsigned short* __restrict__ tmp_code, double* __restrict__ tmp_time) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const NxbModelLayout& ml = p.ml;
+    for (int i = threadIdx.x * 16; i < ml.bytes; i += blockDim.x * 16)
+        *(uint4*)(smem + i) = *(const uint4*)(p.blob + i);
+    __syncthreads();
+    const int* parent = (const int*)(smem + ml.off_parent);
+    const double* tma = (const double*)(smem + ml.off_tma);
+    const double* len = (const double*)(smem + ml.off_len);
+    const double* rate = (const double*)(smem + ml.off_rate);
+    const double* qval = (const double*)(smem + ml.off_qval);
+    const unsigned short* qinfo = (const unsigned short*)(smem + ml.off_qinfo);
+    const unsigned short* qptr = (const unsigned short*)(smem + ml.off_qptr);
+    const unsigned char* cls = (const unsigned char*)(smem + ml.off_cls);
+    const double* pi = (const double*)(smem + ml.off_pi);
+    const int E = ml.E, P = ml.P, K = ml.K;
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= p.n_units) return;
+    unsigned char* slab = p.state + u * p.state_stride;
+    unsigned* g_tol = (unsigned*)(slab + p.so_tol);
+    unsigned char* g_npri = (unsigned char*)(slab + p.so_pri);
+    double* g_ptm = (double*)(slab + p.so_ptm);
+    unsigned* g_pcode = (unsigned*)(slab + p.so_pcode);
+    double* g_btm = (double*)(slab + p.so_btm);
+    unsigned* g_bcode = (unsigned*)(slab + p.so_bcode);
+    unsigned short* bcode_tmp = tmp_code + u * (long long)cap_events;     // edge | track<<... staged unsorted
+    double* btime_tmp = tmp_time + u * (long long)cap_events;
+    NxbXo xo;
+    {
+        NxbU4 r = nxb_philox4x32_10((unsigned)(p.unit_offset + u), 0xFFFFFFFEu, 0x07000000u, 0u,
+                                    (unsigned)(p.seed & 0xffffffffull), (unsigned)(p.seed >> 32));
+        xo.s0 = r.x; xo.s1 = r.y; xo.s2 = r.z; xo.s3 = r.w | 1u;
+    }
+    auto unif = [&]() { return nxb_u53(nxb_xo_next(xo), nxb_xo_next(xo)); };
+    // root
+    int s0 = P - 1;
+    {
+        double target = unif(), acc = 0.0, tot = 0.0;
+        for (int s = 0; s < P; ++s) tot += pi[s];
+        target *= tot;
+        for (int s = 0; s < P; ++s) { acc += pi[s]; if (acc > target) { s0 = s; break; } }
+    }
+    unsigned m0 = 0u;
+    for (int k = 0; k < K; ++k)
+        if (k == cls[s0] || unif() < ml.p_on) m0 |= 1u << k;
+    g_npri[0] = (unsigned char)s0;
+    g_tol[0] = m0;
+    int nP = 0, nB = 0;
+    bool overflow = false;
+    for (int e = 0; e < E; ++e) {
+        const int va = parent[e];
+        int s = g_npri[va];
+        unsigned m = g_tol[va];
+        double t = tma[e];
+        const double tend = tma[e] + len[e], rho = rate[e];
+        if (rho > 0.0 && len[e] > 0.0) {
+            while (true) {
+                double rpri = 0.0;
+                for (int i = qptr[s]; i < qptr[s + 1]; ++i)
+                    if ((m >> (qinfo[i] >> 8)) & 1u) rpri += qval[i];
+                const int n_on = __popc(m);
+                const double r_on = ml.rate_on * (K - n_on), r_off = ml.rate_off * (n_on - 1);
+                const double total = rho * (rpri + r_on + r_off);
+                if (!(total > 0.0)) break;
+                t += -log(unif()) / total;
+                if (!(t < tend)) break;
+                double x = unif() * (rpri + r_on + r_off);
+                if (x < rpri) {
+                    int sb = s;
+                    for (int i = qptr[s]; i < qptr[s + 1]; ++i)
+                        if ((m >> (qinfo[i] >> 8)) & 1u) { sb = qinfo[i] & 0xffu; x -= qval[i]; if (x < 0.0) break; }
+                    if (nP < p.gcapP) {
+                        g_ptm[nP] = t;
+                        g_pcode[nP] = (unsigned)e | ((unsigned)s << 16) | ((unsigned)sb << 24);
+                    } else overflow = true;
+                    ++nP;
+                    s = sb;
+                } else {
+                    x -= rpri;
+                    int kk = -1;
+                    if (x < r_on) {            // an OFF class switches on
+                        int j = (int)(x / ml.rate_on);
+                        for (int k = 0; k < K; ++k) if (!((m >> k) & 1u)) { kk = k; if (j-- == 0) break; }
+                    } else {                   // an ON class other than the own one switches off
+                        int j = (int)((x - r_on) / ml.rate_off);
+                        for (int k = 0; k < K; ++k)
+                            if (((m >> k) & 1u) && k != cls[s]) { kk = k; if (j-- == 0) break; }
+                    }
+                    if (kk >= 0) {
+                        m ^= 1u << kk;
+                        if (nB < cap_events) {
+                            btime_tmp[nB] = t;
+                            bcode_tmp[nB] = (unsigned short)(e | (((m >> kk) & 1u) ? 0x8000u : 0u));
+                            // track kept in the low bits of the time's companion array below
+                            g_bcode[nB] = (unsigned)kk;      // staged: track only (cap_events == gcapB)
+                        } else overflow = true;
+                        ++nB;
+                    }
+                }
+            }
+        }
+        g_npri[e + 1] = (unsigned char)s;
+        g_tol[e + 1] = m;
+    }
+    if (nB > p.gcapB || nB > cap_events) overflow = true;
+    if (overflow) {
+        if (atomicCAS(p.status, 0, NXB_ERR_STATE_CAP) == 0) { p.status[1] = (int)u; p.status[2] = nB; p.status[3] = nP; }
+        nP = 0; nB = 0;
+    }
+    // blink events were generated in (edge, time) order; the slab wants (track, edge, time):
+    // stable counting sort by track
+    if (nB > 0) {
+        // g_bcode[i] currently holds the track of staged event i
+        int offs[NXB_MAX_CLASSES + 1];
+        for (int k = 0; k <= K; ++k) offs[k] = 0;
+        for (int i = 0; i < nB; ++i) offs[g_bcode[i] + 1]++;
+        for (int k = 0; k < K; ++k) offs[k + 1] += offs[k];
+        // tracks are needed after g_bcode is overwritten: stash them in the spare high bits of
+        // the staged code (edge < 2^14, bit 15 = new state, bit 14 unused) -> use a second pass
+        for (int i = 0; i < nB; ++i) {
+            const unsigned k = g_bcode[i];
+            const int dst = offs[k]++;
+            g_btm[dst] = btime_tmp[i];
+        }
+        // rebuild offsets and write the codes
+        for (int k = 0; k <= K; ++k) offs[k] = 0;
+        for (int i = 0; i < nB; ++i) offs[g_bcode[i] + 1]++;
+        for (int k = 0; k < K; ++k) offs[k + 1] += offs[k];
+        // codes go to the temporary first (g_bcode still holds the tracks we are reading)
+        unsigned* code_out = (unsigned*)btime_tmp;      // reuse: times are already copied out
+        for (int i = 0; i < nB; ++i) {
+            const unsigned k = g_bcode[i];
+            const int dst = offs[k]++;
+            const unsigned c16 = bcode_tmp[i];
+            code_out[dst] = (c16 & 0x3fffu) | (k << 16) | ((c16 & 0x8000u) ? (1u << 31) : 0u);
+        }
+        for (int i = 0; i < nB; ++i) g_bcode[i] = code_out[i];
+    }
+    NxbUnitHeader hdr;
+    hdr.sweeps_done = 0; hdr.n_pri = (uint16_t)nP; hdr.n_blk = (uint16_t)nB;
+    hdr.phase = NXB_PHASE_PRIMARY; hdr.pad = 0;
+    *(NxbUnitHeader*)slab = hdr;
+}
+
+__global__ void node_states_kernel(const unsigned char* state, long long stride, long long n, int N,
+                                   int so_tol, int so_pri, int* out_pri, unsigned* out_tol) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * N) return;
+    const long long u = i / N;
+    const int v = (int)(i - u * N);
+    const unsigned char* slab = state + u * stride;
+    out_pri[i] = slab[so_pri + v];
+    out_tol[i] = ((const unsigned*)(slab + so_tol))[v];
+}
+
 // rmax_tab[mask] = max_s sum_{b: class(b) in mask} q[s][b]
 __global__ void rmax_table_kernel(double* tab, unsigned n_masks, int P, const int* q_ptr,
                                   const int* q_cls, const double* q_val) {
@@ -1054,6 +1219,71 @@ extern "C" int nxb_export_unit(nxb_handle* h, int64_t unit, int32_t* node_pri, u
         bt[i] = g_btm[i]; be[i] = g_bcode[i] & 0xffffu;
         bk[i] = (g_bcode[i] >> 16) & 0xffu; bs[i] = g_bcode[i] >> 31;
     }
+    return NXB_OK;
+}
+
+
+extern "C" int nxb_forward_sample(nxb_handle* h, int64_t n_units, uint64_t seed, int64_t unit_offset) {
+    if (!h || n_units <= 0 || n_units > 0x7fffffffLL) return set_err(h, NXB_ERR_BAD_ARG, "bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)n_units * h->ml.N;
+    // unconstrained data: one "site" per unit, one chain (so that the units can be swept afterwards)
+    {
+        std::vector<uint64_t> pri(n, h->ml.P == 64 ? ~0ull : ((1ull << h->ml.P) - 1ull));
+        std::vector<uint32_t> tt(n, h->ml.K == 32 ? ~0u : ((1u << h->ml.K) - 1u));
+        int rc = nxb_set_data(h, n_units, pri.data(), tt.data(), tt.data());
+        if (rc) return rc;
+    }
+    if (n_units != h->n_units) {
+        cudaFree(h->d_state); cudaFree(h->d_defer[0]); cudaFree(h->d_defer[1]);
+        h->d_state = nullptr; h->d_defer[0] = h->d_defer[1] = nullptr;
+        CUDA_TRY(h, cudaMalloc(&h->d_state, (size_t)n_units * h->stride));
+        CUDA_TRY(h, cudaMalloc(&h->d_defer[0], 4 * (size_t)n_units));
+        CUDA_TRY(h, cudaMalloc(&h->d_defer[1], 4 * (size_t)n_units));
+    }
+    h->n_units = n_units; h->chains = 1; h->seed = seed; h->unit_offset = unit_offset; h->sweeps = 0;
+    const int cap_events = h->gcapB;
+    unsigned short* tmp_code = nullptr; double* tmp_time = nullptr;
+    CUDA_TRY(h, cudaMalloc(&tmp_code, 2 * (size_t)n_units * cap_events));
+    CUDA_TRY(h, cudaMalloc(&tmp_time, 8 * (size_t)n_units * cap_events));
+    NxbSweepParams p;
+    memset(&p, 0, sizeof(p));
+    p.ml = h->ml; p.sl = h->sl; p.blob = h->d_blob;
+    p.state = h->d_state; p.state_stride = h->stride;
+    p.gcapP = h->gcapP; p.gcapB = h->gcapB;
+    p.so_tol = h->so_tol; p.so_pri = h->so_pri; p.so_ptm = h->so_ptm; p.so_pcode = h->so_pcode;
+    p.so_btm = h->so_btm; p.so_bcode = h->so_bcode;
+    p.n_units = n_units; p.unit_offset = unit_offset; p.seed = seed; p.status = h->d_status;
+    const int threads = 128;
+    cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->ml.bytes);
+    forward_kernel<<<(unsigned)((n_units + threads - 1) / threads), threads, h->ml.bytes, h->stream>>>(
+        p, cap_events, tmp_code, tmp_time);
+    CUDA_TRY(h, cudaGetLastError());
+    int hs[4];
+    CUDA_TRY(h, cudaMemcpyAsync(hs, h->d_status, 16, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(tmp_code); cudaFree(tmp_time);
+    if (hs[0] != 0) {
+        cudaMemsetAsync(h->d_status, 0, 16, h->stream);
+        return set_err(h, hs[0], "forward sample outgrew the slab capacity; re-create the handle with a larger cap_scale");
+    }
+    return NXB_OK;
+}
+
+extern "C" int nxb_read_node_states(nxb_handle* h, int32_t* node_pri, uint32_t* node_tol) {
+    if (!h || !h->d_state || !node_pri || !node_tol) return set_err(h, NXB_ERR_BAD_ARG, "bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n_units * h->ml.N;
+    int* d_pri = nullptr; unsigned* d_tol = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_pri, 4 * n));
+    CUDA_TRY(h, cudaMalloc(&d_tol, 4 * n));
+    node_states_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+        h->d_state, h->stride, h->n_units, h->ml.N, h->so_tol, h->so_pri, d_pri, d_tol);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(node_pri, d_pri, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(node_tol, d_tol, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_pri); cudaFree(d_tol);
     return NXB_OK;
 }
 

@@ -88,6 +88,17 @@ class BlinkSampler(object):
         self.chains = int(chains)
         self.n_units = self.data.n_sites * self.chains
 
+    def forward_sample(self, n_units, seed=0, unit_offset=0):
+        """Prior simulation of ``n_units`` trajectories on the device (fwdsample.py:67-262).
+        Returns (node_pri [n, N] state indices, node_tol [n, N] bit masks)."""
+        self._check(self.lib.nxb_forward_sample(self._h, int(n_units), int(seed), int(unit_offset)))
+        self.chains, self.n_units = 1, int(n_units)
+        self.data = None
+        node_pri = np.zeros((self.n_units, self.pm.n_nodes), dtype=np.int32)
+        node_tol = np.zeros((self.n_units, self.pm.n_nodes), dtype=np.uint32)
+        self._check(self.lib.nxb_read_node_states(self._h, node_pri.ctypes.data, node_tol.ctypes.data))
+        return node_pri, node_tol
+
     def sweep(self, n_sweeps=1, accumulate=True):
         self._check(self.lib.nxb_sweep(self._h, int(n_sweeps), 1 if accumulate else 0))
 

@@ -1,0 +1,86 @@
+"""Device forward sampler (nxblink/fwdsample.py:67-262 on the GPU) and the prior/posterior
+consistency check it enables: with no data the Rao-Teh chain must leave the prior invariant, so
+statistics of forward-simulated trajectories and of the same trajectories after Gibbs sweeps
+must agree -- at the p53 shape, where no exact answer exists."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from oracle.dense_oracle import DensePosterior
+from nxblink_b200 import toymodel, toydata, p53, packing
+from test_gpu_toy_exact import _flatten, _flatten_exact
+
+pytestmark = pytest.mark.gpu
+
+
+def test_forward_statistics_match_exact_prior(nb):
+    M = toymodel.BlinkModelB
+    runs = []
+    for seed in range(6):
+        s = nb.BlinkSampler(M)
+        node_pri, node_tol = s.forward_sample(40000, seed=seed)
+        assert node_pri.shape == (40000, 6)
+        # own class is on at every node of every sampled trajectory
+        own = s.pm.state_class[node_pri]
+        assert (((node_tol >> own.astype(np.uint32)) & 1) == 1).all()
+        s.reset_summary()
+        s.summarize_current()
+        sm = s.summary()
+        assert sm.nsamples == 40000
+        runs.append(_flatten(sm, s.pm))
+        pm = s.pm
+        s.close()
+    exact = _flatten_exact(DensePosterior(M, toydata.DataA).expected_summary(), pm)
+    worst = (0.0, None)
+    for key, ex in exact.items():
+        vals = np.array([r[key] for r in runs])
+        se = vals.std(ddof=1) / np.sqrt(len(runs))
+        z = abs(vals.mean() - ex) / (5 * se + 2e-3)
+        if z > worst[0]:
+            worst = (z, (key, vals.mean(), ex, se))
+    assert worst[0] <= 1.0, worst
+
+
+def test_prior_is_invariant_under_the_sweep_p53_shape(nb):
+    pm = packing.PackedModel(p53.p53_model())
+    fwd, mcmc = [], []
+    for seed in range(4):
+        s = nb.BlinkSampler(pm, validate=True)
+        s.forward_sample(16384, seed=100 + seed)
+        s.reset_summary()
+        s.summarize_current()
+        fwd.append(gu.scalar_functionals(s.summary()))
+        s.reset_summary()
+        s.sweep(6, accumulate=True)              # also validates every invariant after every phase
+        sm = s.summary()
+        assert sm.nsamples == 16384 * 6
+        mcmc.append(gu.scalar_functionals(sm))
+        s.close()
+    for name in fwd[0]:
+        a = np.array([r[name] for r in fwd])
+        b = np.array([r[name] for r in mcmc])
+        se = np.hypot(a.std(ddof=1), b.std(ddof=1)) / np.sqrt(len(a))
+        assert abs(a.mean() - b.mean()) <= 5 * se + 2e-3 * max(1.0, abs(a.mean())), (name, a.mean(), b.mean(), se)
+    # stationary blink flux: 2 on off / (on + off) per class and unit of (rate * length)
+    flux = (np.mean([r['off_xon_trans'] for r in fwd]) + np.mean([r['xon_off_trans'] for r in fwd]))
+    expect = 19 * (pm.blen * pm.rate).sum() * 2 * 1.5 * 0.5 / 2.0
+    assert abs(flux - expect) < 0.02 * expect
+
+
+def test_forward_sampled_alignment_can_be_analysed(nb):
+    """Synthetic data straight from the blink process: sample, read the leaves, condition on them."""
+    m = p53.p53_model()
+    pm = packing.PackedModel(m)
+    s = nb.BlinkSampler(pm)
+    node_pri, node_tol = s.forward_sample(64, seed=5)
+    s.close()
+    is_leaf = np.ones(pm.n_nodes, dtype=bool)
+    is_leaf[pm.parent[1:]] = False
+    leaf_states = np.where(is_leaf[None, :], node_pri, -1)
+    data = packing.pack_alignment(pm, leaf_states)
+    s = nb.BlinkSampler(pm, validate=True)
+    s.set_data(data)
+    s.init_chains(chains=4, seed=1)
+    s.sweep(5, accumulate=True)
+    assert s.summary().nsamples == 64 * 4 * 5
+    s.close()
