@@ -44,6 +44,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     c.p0_pri = (const double*)(smem + ml.off_p0_pri);
     c.lam_blk = (const double*)(smem + ml.off_lam_blk);
     c.p0_blk = (const double*)(smem + ml.off_p0_blk);
+    c.gsc_blk = (const float*)(smem + ml.off_gsc_blk);
     c.qval = (const double*)(smem + ml.off_qval);
     c.qinfo = (const unsigned short*)(smem + ml.off_qinfo);
     c.qptr = (const unsigned short*)(smem + ml.off_qptr);
@@ -800,6 +801,12 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         ml.off_p0_pri = put(p0_pri.data(), 8 * E, 8);
         ml.off_lam_blk = put(lam_blk.data(), 8 * E, 8);
         ml.off_p0_blk = put(p0_blk.data(), 8 * E, 8);
+        {
+            std::vector<float> gsc(E, 0.f);
+            for (int e = 0; e < E; ++e)
+                if (rate[e] > 0.0 && len[e] > 0.0) gsc[e] = (float)(0.6931471805599453 / (2.0 * M * rate[e]));
+            ml.off_gsc_blk = put(gsc.data(), 4 * E, 4);
+        }
         ml.off_qval = put(d->q_val, 8 * nnz, 8);
         std::vector<unsigned short> qinfo(nnz), qptr(P + 1);
         for (int i = 0; i < nnz; ++i)

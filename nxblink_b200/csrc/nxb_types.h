@@ -51,6 +51,7 @@ struct NxbModelLayout {
     int off_p0_pri;     // f64    [E]   exp(-lam_pri)
     int off_lam_blk;    // f64    [E]   dominating Poisson mean, one blink track
     int off_p0_blk;     // f64    [E]   exp(-lam_blk)
+    int off_gsc_blk;    // f32    [E]   ln2 / (dominating blink rate of the edge), 0 if inactive
     int off_qval;       // f64    [nnz] normalised primary rates (CSR values)
     int off_qinfo;      // u16    [nnz] column | class(column) << 8
     int off_qptr;       // u16    [P+1]

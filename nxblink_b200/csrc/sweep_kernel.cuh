@@ -44,6 +44,7 @@ struct Ctx {
     // model tables (shared memory)
     const int* parent; const int* slot;
     const double *tma, *len, *rate, *lam_pri, *p0_pri, *lam_blk, *p0_blk, *qval, *pi, *qm;
+    const float* gsc_blk;
     const unsigned short *qinfo, *qptr;
     const unsigned char* cls;
     const unsigned long long* clsmask;
@@ -697,7 +698,6 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         const unsigned long long thr_w0 = (unsigned long long)(ml.acc_blk[2] * 4294967296.0);
         const unsigned long long thr_w1 = (unsigned long long)(ml.acc_blk[3] * 4294967296.0);
         const double a_on = ml.a_on, a_off = ml.a_off;
-        const float gap_scale = (float)(0.6931471805599453 / (2.0 * fmax(ml.rate_on, ml.rate_off)));
         int e = trk ? E - 1 : -1;
         int io = ohi - 1;              // cursor into the retained events (descending)
         unsigned inited = 0u;          // live accumulator slots of this lane
@@ -725,10 +725,9 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     xold = (c.node_tol[vb] >> k) & 1u;
                     ip = poff[e + 1] - 1; ip0 = poff[e];
                     // dominating rate of the edge: 2 * max(on, off) * rate_e per unit time
-                    draw_gap = rate > 0.0 && tcur > tma;
-                    gsc = draw_gap ? gap_scale / (float)rate : 0.f;
-                    tcand = tcur;
-                    if (!draw_gap) tcand = -NXB_INF;
+                    gsc = c.gsc_blk[e];
+                    draw_gap = gsc > 0.f;
+                    tcand = draw_gap ? tcur : -NXB_INF;
                     fresh = false;
                 }
                 if (draw_gap) {
