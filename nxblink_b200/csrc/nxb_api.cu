@@ -21,7 +21,7 @@ namespace nxb {
 template <typename MSG>
 __global__ void __launch_bounds__(NXB_MAX_THREADS, 1)
 sweep_kernel(const __grid_constant__ NxbSweepParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned char* const smem = nxb_smem;
     const NxbModelLayout& ml = p.ml;
     const NxbWarpLayout& wl = p.wl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -35,47 +35,47 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     Ctx c;
     c.p = &p;
     c.N = ml.N; c.E = ml.E; c.P = ml.P; c.K = ml.K; c.lane = lane;
-    c.parent = (const int*)(smem + ml.off_parent);
-    c.slot = (const int*)(smem + ml.off_slot);
-    c.tma = (const double*)(smem + ml.off_tma);
-    c.len = (const double*)(smem + ml.off_len);
-    c.rate = (const double*)(smem + ml.off_rate);
-    c.lam_pri = (const double*)(smem + ml.off_lam_pri);
-    c.p0_pri = (const double*)(smem + ml.off_p0_pri);
-    c.lam_blk = (const double*)(smem + ml.off_lam_blk);
-    c.p0_blk = (const double*)(smem + ml.off_p0_blk);
-    c.gsc_blk = (const float*)(smem + ml.off_gsc_blk);
-    c.qval = (const double*)(smem + ml.off_qval);
-    c.qinfo = (const unsigned short*)(smem + ml.off_qinfo);
-    c.qptr = (const unsigned short*)(smem + ml.off_qptr);
-    c.cls = (const unsigned char*)(smem + ml.off_cls);
-    c.pi = (const double*)(smem + ml.off_pi);
-    c.qm = (const double*)(smem + ml.off_qm);
-    c.clsmask = (const unsigned long long*)(smem + ml.off_clsmask);
-    c.ell_info = smem + ml.off_ell_info;
-    c.ell_q = smem + ml.off_ell_q;
-    c.s_off_on = stats;
-    c.s_on_off = stats + ml.E;
-    c.s_root_pri = stats + 2 * ml.E;
-    c.s_root_misc = stats + 2 * ml.E + ml.P;
-    c.s_root_on_cls = stats + 2 * ml.E + ml.P + 4;
-    c.wbase = smem + p.smem_warp0 + (size_t)warp * wl.bytes;
+    c.parent.off = ml.off_parent;
+    c.slot.off = ml.off_slot;
+    c.tma.off = ml.off_tma;
+    c.len.off = ml.off_len;
+    c.rate.off = ml.off_rate;
+    c.lam_pri.off = ml.off_lam_pri;
+    c.p0_pri.off = ml.off_p0_pri;
+    c.lam_blk.off = ml.off_lam_blk;
+    c.p0_blk.off = ml.off_p0_blk;
+    c.gsc_blk.off = ml.off_gsc_blk;
+    c.qval.off = ml.off_qval;
+    c.qinfo.off = ml.off_qinfo;
+    c.qptr.off = ml.off_qptr;
+    c.cls.off = ml.off_cls;
+    c.pi.off = ml.off_pi;
+    c.qm.off = ml.off_qm;
+    c.clsmask.off = ml.off_clsmask;
+    c.ell_info = ml.off_ell_info;
+    c.ell_q = ml.off_ell_q;
+    c.s_off_on.off = ml.off_stats;
+    c.s_on_off.off = ml.off_stats + 8 * ml.E;
+    c.s_root_pri.off = ml.off_stats + 8 * (2 * ml.E);
+    c.s_root_misc.off = ml.off_stats + 8 * (2 * ml.E + ml.P);
+    c.s_root_on_cls.off = ml.off_stats + 8 * (2 * ml.E + ml.P + 4);
+    c.wbase = (unsigned)(p.smem_warp0 + warp * wl.bytes);
     c.gbase = p.gscratch + ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * p.gscratch_stride;
-    c.node_tol = (unsigned*)(c.wbase + wl.off_node_tol);
-    c.node_pri = (unsigned char*)(c.wbase + wl.off_node_pri);
-    c.ptm = (double*)(c.wbase + wl.off_ptm);
-    c.pcode = (unsigned*)(c.wbase + wl.off_pcode);
-    c.btm = (double*)(c.wbase + wl.off_btm);
-    c.bcode = (unsigned*)(c.wbase + wl.off_bcode);
-    c.boff = (int*)(c.wbase + wl.off_boff);
-    c.poff = (int*)(c.wbase + wl.off_poff);
-    c.tmpa = (int*)(c.wbase + wl.off_tmpa);
-    c.tmpb = (int*)(c.wbase + wl.off_tmpb);
-    c.tmpc = (int*)(c.wbase + wl.off_tmpc);
-    unsigned long long* d_pri = (unsigned long long*)(c.wbase + wl.off_dpri);
-    unsigned* d_tt = (unsigned*)(c.wbase + wl.off_dtt);
-    unsigned* d_tf = (unsigned*)(c.wbase + wl.off_dtf);
-    c.pri_ok = d_pri; c.tt_ok = d_tt; c.tf_ok = d_tf;
+    c.node_tol.off = c.wbase + wl.off_node_tol;
+    c.node_pri.off = c.wbase + wl.off_node_pri;
+    c.ptm.off = c.wbase + wl.off_ptm;
+    c.pcode.off = c.wbase + wl.off_pcode;
+    c.btm.off = c.wbase + wl.off_btm;
+    c.bcode.off = c.wbase + wl.off_bcode;
+    c.boff.off = c.wbase + wl.off_boff;
+    c.poff.off = c.wbase + wl.off_poff;
+    c.tmpa.off = c.wbase + wl.off_tmpa;
+    c.tmpb.off = c.wbase + wl.off_tmpb;
+    c.tmpc.off = c.wbase + wl.off_tmpc;
+    unsigned long long* d_pri = sm_ptr<unsigned long long>(c.wbase + wl.off_dpri);
+    unsigned* d_tt = sm_ptr<unsigned>(c.wbase + wl.off_dtt);
+    unsigned* d_tf = sm_ptr<unsigned>(c.wbase + wl.off_dtf);
+    c.pri_ok.off = c.wbase + wl.off_dpri; c.tt_ok.off = c.wbase + wl.off_dtt; c.tf_ok.off = c.wbase + wl.off_dtf;
     c.k0 = (unsigned)(p.seed & 0xffffffffull);
     c.k1 = (unsigned)(p.seed >> 32);
     const int N = ml.N;
@@ -141,7 +141,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
                 // streaming (evict-first) accesses: the slab is touched once per launch and must
                 // not displace the L2-resident scratch of the resident warps
                 for (int v = lane; v < N; v += 32) c.node_tol[v] = __ldcs(g_tol + v);
-                for (int v = lane; v < (N + 3) / 4; v += 32) ((unsigned*)c.node_pri)[v] = __ldcs(g_npri + v);
+                for (int v = lane; v < (N + 3) / 4; v += 32) sm_ptr<unsigned>(c.node_pri.off)[v] = __ldcs(g_npri + v);
                 const double* g_ptm = (const double*)(slab + p.so_ptm);
                 const unsigned* g_pcode = (const unsigned*)(slab + p.so_pcode);
                 for (int i = lane; i < c.nP; i += 32) { c.ptm[i] = __ldcs(g_ptm + i); c.pcode[i] = __ldcs(g_pcode + i); }
@@ -204,7 +204,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
                     unsigned* g_tol = (unsigned*)(slab + p.so_tol);
                     unsigned* g_npri = (unsigned*)(slab + p.so_pri);
                     for (int v = lane; v < N; v += 32) __stcs(g_tol + v, c.node_tol[v]);
-                    for (int v = lane; v < (N + 3) / 4; v += 32) __stcs(g_npri + v, ((unsigned*)c.node_pri)[v]);
+                    for (int v = lane; v < (N + 3) / 4; v += 32) __stcs(g_npri + v, sm_ptr<unsigned>(c.node_pri.off)[v]);
                     double* g_ptm = (double*)(slab + p.so_ptm);
                     unsigned* g_pcode = (unsigned*)(slab + p.so_pcode);
                     for (int i = lane; i < c.nP; i += 32) { __stcs(g_ptm + i, c.ptm[i]); __stcs(g_pcode + i, c.pcode[i]); }

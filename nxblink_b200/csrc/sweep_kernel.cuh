@@ -38,28 +38,41 @@ enum { RC_OK = 0, RC_DEFER = 1, RC_ERROR = 2 };
 
 __constant__ double c_inv_n[64];
 
+// Everything a warp touches in shared memory is addressed as a 32-bit offset from the one dynamic
+// shared array, so that the compiler keeps shared-space (LDS/STS) addressing with 32-bit
+// arithmetic instead of rebuilding 64-bit generic pointers inside the hot loops.
+extern __shared__ __align__(16) unsigned char nxb_smem[];
+template <typename T> struct SPtr {
+    unsigned off;
+    __device__ __forceinline__ T& operator[](int i) const { return reinterpret_cast<T*>(nxb_smem + off)[i]; }
+    __device__ __forceinline__ T* ptr() const { return reinterpret_cast<T*>(nxb_smem + off); }
+};
+template <typename T> __device__ __forceinline__ T* sm_ptr(unsigned off) {
+    return reinterpret_cast<T*>(nxb_smem + off);
+}
+
 struct Ctx {
     const NxbSweepParams* p;
     int N, E, P, K, lane;
     // model tables (shared memory)
-    const int* parent; const int* slot;
-    const double *tma, *len, *rate, *lam_pri, *p0_pri, *lam_blk, *p0_blk, *qval, *pi, *qm;
-    const float* gsc_blk;
-    const unsigned short *qinfo, *qptr;
-    const unsigned char* cls;
-    const unsigned long long* clsmask;
-    const void* ell_info; const void* ell_q;
+    SPtr<const int> parent, slot;
+    SPtr<const double> tma, len, rate, lam_pri, p0_pri, lam_blk, p0_blk, qval, pi, qm;
+    SPtr<const float> gsc_blk;
+    SPtr<const unsigned short> qinfo, qptr;
+    SPtr<const unsigned char> cls;
+    SPtr<const unsigned long long> clsmask;
+    unsigned ell_info, ell_q;          // shared-memory offsets of the ELL tables
     // CTA-level statistic partials (shared memory)
-    unsigned long long *s_off_on, *s_on_off, *s_root_pri, *s_root_misc, *s_root_on_cls;
+    SPtr<unsigned long long> s_off_on, s_on_off, s_root_pri, s_root_misc, s_root_on_cls;
     // per-warp persistent state (shared memory)
-    unsigned char* wbase;
+    unsigned wbase;           // shared-memory offset of this warp's region
     unsigned char* gbase;     // this warp slot's scratch in global memory
-    unsigned* node_tol; unsigned char* node_pri;
-    double* ptm; unsigned* pcode; double* btm; unsigned* bcode;
+    SPtr<unsigned> node_tol; SPtr<unsigned char> node_pri;
+    SPtr<double> ptm; SPtr<unsigned> pcode; SPtr<double> btm; SPtr<unsigned> bcode;
     int nP, nB;
-    int *boff, *poff, *tmpa, *tmpb, *tmpc;
+    SPtr<int> boff, poff, tmpa, tmpb, tmpc;
     // site data
-    const unsigned long long* pri_ok; const unsigned* tt_ok; const unsigned* tf_ok;
+    SPtr<const unsigned long long> pri_ok; SPtr<const unsigned> tt_ok, tf_ok;
     // rng
     unsigned k0, k1, unit32, sweep;
     long long unit;       // local unit index
@@ -191,7 +204,7 @@ __device__ __noinline__ double rmax_compute(const unsigned short* qptr, const un
 // max over ALL source states (poisson.py:88-90 / util.py:13-17)
 __device__ __forceinline__ double rmax_lookup(const Ctx& c, unsigned mask) {
     if (c.p->rmax_tab) return __ldg(c.p->rmax_tab + mask);
-    return rmax_compute(c.qptr, c.qinfo, c.qval, c.P, mask);
+    return rmax_compute(c.qptr.ptr(), c.qinfo.ptr(), c.qval.ptr(), c.P, mask);
 }
 
 __device__ __forceinline__ void fail(const Ctx& c, int code, int detail) {
@@ -237,22 +250,22 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     const int E = c.E, N = c.N, P = c.P, K = c.K, lane = c.lane;
     const unsigned ALLK = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
 
-    unsigned short* bord = (unsigned short*)(c.wbase + wl.off_bord);
-    double* rtm = (double*)(c.wbase + wl.off_rtm);
-    unsigned* rmask = (unsigned*)(c.wbase + wl.off_rmask);
-    double* ftm = (double*)(c.wbase + wl.off_ftm);
-    unsigned* fmask = (unsigned*)(c.wbase + wl.off_fmask);
-    unsigned short* fedge = (unsigned short*)(c.wbase + wl.off_fedge);
-    int* nchunk = (int*)(c.wbase + wl.off_nchunk);
-    int* jump = (int*)(c.wbase + wl.off_jump);
-    unsigned short* par = (unsigned short*)(c.wbase + wl.off_par);
-    unsigned* toland = (unsigned*)(c.wbase + wl.off_toland);
-    unsigned long long* callow = (unsigned long long*)(c.wbase + wl.off_callow);
-    unsigned char* cstate = (unsigned char*)(c.wbase + wl.off_cstate);
+    const SPtr<unsigned short> bord = {c.wbase + wl.off_bord};
+    const SPtr<double> rtm = {c.wbase + wl.off_rtm};
+    const SPtr<unsigned> rmask = {c.wbase + wl.off_rmask};
+    const SPtr<double> ftm = {c.wbase + wl.off_ftm};
+    const SPtr<unsigned> fmask = {c.wbase + wl.off_fmask};
+    const SPtr<unsigned short> fedge = {c.wbase + wl.off_fedge};
+    const SPtr<int> nchunk = {c.wbase + wl.off_nchunk};
+    const SPtr<int> jump = {c.wbase + wl.off_jump};
+    const SPtr<unsigned short> par = {c.wbase + wl.off_par};
+    const SPtr<unsigned> toland = {c.wbase + wl.off_toland};
+    const SPtr<unsigned long long> callow = {c.wbase + wl.off_callow};
+    const SPtr<unsigned char> cstate = {c.wbase + wl.off_cstate};
     MSG* msg = (MSG*)(c.gbase + p.g_off_msg);          // chunk messages: global (L2)
-    MSG* srow = (MSG*)(c.wbase + wl.off_msg);           // staging row of the chunk being pushed up
-    int* boff = c.boff; int* poff = c.poff;
-    int* mE = c.tmpa; int* rbase = c.tmpb; int* foff = c.tmpc;
+    const SPtr<MSG> srow = {c.wbase + wl.off_msg};           // staging row of the chunk being pushed up
+    const SPtr<int> boff = c.boff, poff = c.poff;
+    const SPtr<int> mE = c.tmpa, rbase = c.tmpb, foff = c.tmpc;
 
     phase_sync(c);
     // ---- P0: edge-major, time-sorted view of the retained blink events ----------
@@ -458,8 +471,8 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     phase_sync(c);
     // ---- P3: upward pass over the chunk tree ------------------------------------------
     // Hoisted, lane-parallel: per-event 1/(2*Rmax(mask)) and the uniforms of the backward pass.
-    MSG* finv = (MSG*)(c.wbase + wl.off_finv);
-    double* fu = (double*)(c.wbase + wl.off_fu);
+    const SPtr<MSG> finv = {c.wbase + wl.off_finv};
+    const SPtr<double> fu = {c.wbase + wl.off_fu};
     {
         int bad = 0;
         for (int j = lane; j <= F; j += 32) {
@@ -475,8 +488,8 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     }
     for (int i = lane; i < (F + 1) * NXB_PPAD; i += 32) msg[i] = (MSG)1.0;
     __syncwarp();
-    const unsigned short* ell_info = (const unsigned short*)(c.ell_info);
-    const MSG* ell_q = (const MSG*)(c.ell_q);
+    const SPtr<const unsigned short> ell_info = {c.ell_info};
+    const SPtr<const MSG> ell_q = {c.ell_q};
     const int W = p.ml.ell_w;
     const bool two = P > 32;
     for (int j = F - 1; j >= 0; --j) {
@@ -658,9 +671,9 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     double* ctm = (double*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
     float2* cell = (float2*)(c.gbase + p.g_off_cell) + (size_t)lane * TCAP;  // (OFF, ON) message below the event
     unsigned short* cedge = (unsigned short*)(c.gbase + p.g_off_cedge) + (size_t)lane * TCAP;
-    double* acc = (double*)(c.wbase + wl.off_acc);              // [slot][K][3]: u0, u1, penalty
-    unsigned* newtol = (unsigned*)(c.wbase + wl.off_newtol);
-    int* poff = c.poff;
+    const SPtr<double> acc = {c.wbase + wl.off_acc};              // [slot][K][3]: u0, u1, penalty
+    const SPtr<unsigned> newtol = {c.wbase + wl.off_newtol};
+    const SPtr<int> poff = c.poff;
 
     phase_sync(c);
     build_poff(c);
@@ -716,8 +729,8 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     tma = c.tma[e]; rate = c.rate[e]; tcur = tma + c.len[e];
                     u0 = 1.0; u1 = 1.0; pen = 0.0;
                     if (sb_slot >= 0 && ((inited >> sb_slot) & 1u)) {
-                        const double* a = acc + (sb_slot * K + k) * 3;
-                        u0 = a[0]; u1 = a[1]; pen = a[2];
+                        const int ai = (sb_slot * K + k) * 3;
+                        u0 = acc[ai]; u1 = acc[ai + 1]; pen = acc[ai + 2];
                     }
                     if (!((c.tt_ok[vb] >> k) & 1u)) u1 = 0.0;
                     if (!((c.tf_ok[vb] >> k) & 1u)) u0 = 0.0;
@@ -746,13 +759,13 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                 tcur = tnext;
                 if (tp == -NXB_INF && tf == -NXB_INF) {
                     // top of the edge: fold into the parent's accumulator (one normalisation)
-                    double* a = acc + (sa_slot * K + k) * 3;
+                    const int ai = (sa_slot * K + k) * 3;
                     double n0 = u0, n1 = u1, np = pen;
-                    if ((inited >> sa_slot) & 1u) { n0 *= a[0]; n1 *= a[1]; np += a[2]; }
+                    if ((inited >> sa_slot) & 1u) { n0 *= acc[ai]; n1 *= acc[ai + 1]; np += acc[ai + 2]; }
                     double m2 = fmax(n0, n1);
                     if (!(m2 > 0.0)) { bad = 1; m2 = 1.0; }
                     const double r2 = pow2_rescale(m2);
-                    a[0] = n0 * r2; a[1] = n1 * r2; a[2] = np;
+                    acc[ai] = n0 * r2; acc[ai + 1] = n1 * r2; acc[ai + 2] = np;
                     inited |= 1u << sa_slot;
                     if (sb_slot >= 0) inited &= ~(1u << sb_slot);
                     --e;
@@ -799,9 +812,9 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     // ---- root draw (prior: toymodel.py:17-27 get_blink_distn) ----------------------------------------
     unsigned x = 0u;
     if (trk) {
-        const double* a = acc + (c.slot[0] * K + k) * 3;
-        double w1 = a[1] * exp(-a[2]) * ml.p_on;
-        double w0 = a[0] * ml.p_off;
+        const int ai = (c.slot[0] * K + k) * 3;
+        double w1 = acc[ai + 1] * exp(-acc[ai + 2]) * ml.p_on;
+        double w0 = acc[ai] * ml.p_off;
         if (!((c.tt_ok[0] >> k) & 1u)) w1 = 0.0;
         if (!((c.tf_ok[0] >> k) & 1u)) w0 = 0.0;
         if (c.cls[c.node_pri[0]] == k) w0 = 0.0;
@@ -903,7 +916,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         atomicAdd(&c.s_root_on_cls[c.cls[c.node_pri[0]]], (unsigned long long)on);
         atomicAdd(&c.s_root_misc[2], 1ull);
     }
-    double* obtm = c.btm; unsigned* obcode = c.bcode;
+    double* obtm = c.btm.ptr(); unsigned* obcode = c.bcode.ptr();
     const bool spill = total > wl.capB;
     if (spill) {
         // The sweep is complete and its statistics are booked; only the shared-memory
@@ -980,7 +993,7 @@ __device__ __forceinline__ int init_blink(Ctx& c) {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int validate_unit(Ctx& c) {
     const int E = c.E, N = c.N, K = c.K, lane = c.lane;
-    unsigned short* bord = (unsigned short*)(c.wbase + c.p->wl.off_bord);
+    const SPtr<unsigned short> bord = {c.wbase + c.p->wl.off_bord};
     int bad = 0;
     // primary events sorted by (edge, time); blink events by (track, edge, time)
     for (int i = lane; i + 1 < c.nP; i += 32) {
