@@ -847,6 +847,18 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         ml.off_ell_info = put(ell_info.data(), 2 * W * NXB_PPAD, 2);
         ml.off_ell_q = h->msg_f64 ? put(ell_q64.data(), 8 * W * NXB_PPAD, 8)
                                   : put(ell_q32.data(), 4 * W * NXB_PPAD, 8);
+        // dense transposed copy for the one-hot shortcut of the upward pass
+        {
+            std::vector<float> qdt32((size_t)NXB_PPAD * NXB_PPAD, 0.f);
+            std::vector<double> qdt64((size_t)NXB_PPAD * NXB_PPAD, 0.0);
+            for (int s = 0; s < P; ++s)
+                for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i) {
+                    qdt32[(size_t)d->q_col[i] * NXB_PPAD + s] = (float)d->q_val[i];
+                    qdt64[(size_t)d->q_col[i] * NXB_PPAD + s] = d->q_val[i];
+                }
+            ml.off_qdt = h->msg_f64 ? put(qdt64.data(), 8 * NXB_PPAD * NXB_PPAD, 8)
+                                    : put(qdt32.data(), 4 * NXB_PPAD * NXB_PPAD, 8);
+        }
         blob.resize(align_up((int)blob.size(), 16));
         ml.bytes = (int)blob.size();
         ml.off_stats = ml.bytes;

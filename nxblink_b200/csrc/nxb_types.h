@@ -62,6 +62,7 @@ struct NxbModelLayout {
     int ell_w;          // padded row width of the ELL copy of Q (max out-degree)
     int off_ell_info;   // u16    [ell_w*64] column | class << 8, transposed: [w][row]
     int off_ell_q;      // f32 or f64 (message type) [ell_w*64] rates, 0 in the padding
+    int off_qdt;        // message type [64*64] dense transposed rates: qdt[b*64 + a] = q[a -> b]
     int bytes;
     double rate_on, rate_off;
     double inv_omega_pri;   // 1 / (2 * Rmax(all classes on))

@@ -490,6 +490,7 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     __syncwarp();
     const SPtr<const unsigned short> ell_info = {c.ell_info};
     const SPtr<const MSG> ell_q = {c.ell_q};
+    const SPtr<const MSG> qdt = {(unsigned)p.ml.off_qdt};
     const int W = p.ml.ell_w;
     const bool two = P > 32;
     for (int j = F - 1; j >= 0; --j) {
@@ -499,6 +500,27 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         const MSG inv = finv[j];
         MSG* mc = msg + ci * NXB_PPAD;
         MSG* mp = msg + pi_ * NXB_PPAD;
+        if (__popcll(allow) == 1) {
+            // One feasible state o in the child chunk (it holds an observed leaf): the message is
+            // one-hot, so P . L is column o of the uniformized matrix -- a lookup, not a mat-vec.
+            const int o = __ffsll((long long)allow) - 1;
+            if (!((MSG)mc[o] > (MSG)0)) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
+            MSG qo = 0;
+            if (lane < W) {
+                const unsigned info = ell_info[lane * NXB_PPAD + o];
+                if ((fm >> (info >> 8)) & 1u) qo = ell_q[lane * NXB_PPAD + o];
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) qo += __shfl_xor_sync(FULL, qo, d);     // R_o(mask)
+            const MSG c0 = (lane == o) ? (MSG)1 - inv * qo : inv * qdt[o * NXB_PPAD + lane];
+            mp[lane] *= c0;
+            if (two) {
+                const MSG c1 = (lane + 32 == o) ? (MSG)1 - inv * qo : inv * qdt[o * NXB_PPAD + lane + 32];
+                mp[lane + 32] *= c1;
+            }
+            __syncwarp();
+            continue;
+        }
         // each lane reads back exactly the two entries it wrote itself (program order)
         MSG v0 = ((allow >> lane) & 1ull) ? mc[lane] : (MSG)0;
         MSG v1 = (two && ((allow >> (lane + 32)) & 1ull)) ? mc[lane + 32] : (MSG)0;
@@ -548,6 +570,14 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     __syncwarp();
     for (int j = 0; j < F; ++j) {
         const int ci = j + 1;
+        {
+            const unsigned long long allow = callow[ci];
+            if (__popcll(allow) == 1) {      // one feasible state: nothing to sample
+                if (lane == 0) cstate[ci] = (unsigned char)(__ffsll((long long)allow) - 1);
+                __syncwarp();
+                continue;
+            }
+        }
         const int a = cstate[par[ci]];
         const unsigned fm = fmask[j];
         const MSG inv = finv[j];
