@@ -223,9 +223,11 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     __syncthreads();
     // ---- flush the CTA's statistic partials ----
     const NxbSummaryLayout& sl = p.sl;
+    // per edge one packed word: low 32 bits off->on transitions, high 32 bits on->off
     for (int i = tid; i < ml.E; i += blockDim.x) {
-        if (stats[i]) atomicAdd(p.counts + sl.c_off_on + i, stats[i]);
-        if (stats[ml.E + i]) atomicAdd(p.counts + sl.c_on_off + i, stats[ml.E + i]);
+        const unsigned long long w = stats[i];
+        if (w & 0xffffffffull) atomicAdd(p.counts + sl.c_off_on + i, w & 0xffffffffull);
+        if (w >> 32) atomicAdd(p.counts + sl.c_on_off + i, w >> 32);
     }
     for (int i = tid; i < ml.P; i += blockDim.x)
         if (c.s_root_pri[i]) atomicAdd(p.counts + sl.c_root_pri + i, c.s_root_pri[i]);
@@ -985,8 +987,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             int o = 0;
             h->g_off_msg = o; o += (h->msg_f64 ? 8 : 4) * (h->gcapF + 1) * NXB_PPAD;
             o = align_up(o, 16);
-            h->g_off_ctm = o; o += 8 * h->gcapC * 32;      // one region per lane (track)
-            h->g_off_cell = o; o += 8 * h->gcapC * 32;     // float2 per live event
+            h->g_off_ctm = o; o += 16 * h->gcapC * 32;     // one region per lane (track), 16 B records
+            h->g_off_cell = o;
             h->g_off_cedge = o; o += 2 * h->gcapC * 32;
             h->gscratch_stride = align_up(o, 256);
             cudaError_t e1 = cudaMalloc(&h->d_gscratch, (size_t)h->gscratch_stride * max_w * h->num_sms);

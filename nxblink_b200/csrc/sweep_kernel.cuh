@@ -686,6 +686,10 @@ __device__ __forceinline__ double pow2_rescale(double m) {
     return __longlong_as_double((0x7fdLL << 52) - (bits & (0x7ffLL << 52)));
 }
 
+// max / min without the NaN handling of fmax / fmin (event times and messages are never NaN)
+__device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a : b; }
+
 #define CE_EDGE 0x3fffu
 #define CE_NEW1 0x4000u     // (survivors only) new state of the surviving event
 
@@ -698,8 +702,9 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     // live foreground events of this sweep: global (L2-resident) scratch, one fixed region per
     // track, filled by the upward pass and consumed backwards by the downward pass
     const int TCAP = p.gcapC;
-    double* ctm = (double*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
-    float2* cell = (float2*)(c.gbase + p.g_off_cell) + (size_t)lane * TCAP;  // (OFF, ON) message below the event
+    // one 16-byte record per live event: time, (OFF, ON) message below the event
+    struct __align__(16) LiveEv { double t; float l0, l1; };
+    LiveEv* cev = (LiveEv*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
     unsigned short* cedge = (unsigned short*)(c.gbase + p.g_off_cedge) + (size_t)lane * TCAP;
     const SPtr<double> acc = {c.wbase + wl.off_acc};              // [slot][K][3]: u0, u1, penalty
     const SPtr<unsigned> newtol = {c.wbase + wl.off_newtol};
@@ -736,10 +741,12 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     // to the local rate (poisson.py:111-116).  Only accepted ("live") events are stored.
     int cnt = 0;                       // live events pushed by this lane
     {
-        const unsigned long long thr_o0 = (unsigned long long)(ml.acc_blk[0] * 4294967296.0);
-        const unsigned long long thr_o1 = (unsigned long long)(ml.acc_blk[1] * 4294967296.0);
-        const unsigned long long thr_w0 = (unsigned long long)(ml.acc_blk[2] * 4294967296.0);
-        const unsigned long long thr_w1 = (unsigned long long)(ml.acc_blk[3] * 4294967296.0);
+        // thinning acceptance as integer thresholds: accept iff u32 <= thr (an acceptance
+        // probability of exactly 1 becomes 1 - 2^-32)
+        const unsigned thr_o0 = (unsigned)fmin(ml.acc_blk[0] * 4294967296.0, 4294967295.0);
+        const unsigned thr_o1 = (unsigned)fmin(ml.acc_blk[1] * 4294967296.0, 4294967295.0);
+        const unsigned thr_w0 = (unsigned)fmin(ml.acc_blk[2] * 4294967296.0, 4294967295.0);
+        const unsigned thr_w1 = (unsigned)fmin(ml.acc_blk[3] * 4294967296.0, 4294967295.0);
         const double a_on = ml.a_on, a_off = ml.a_off;
         int e = trk ? E - 1 : -1;
         int io = ohi - 1;              // cursor into the retained events (descending)
@@ -780,8 +787,8 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                 const double tp = (ip >= ip0) ? c.ptm[ip] : -NXB_INF;
                 const bool haso = (io >= olo) && ((c.bcode[io] & 0xffffu) == (unsigned)e);
                 const double to = haso ? c.btm[io] : -NXB_INF;
-                const double tf = fmax(to, tcand);
-                const double tnext = fmax(fmax(tp, tf), tma);
+                const double tf = dmax2(to, tcand);
+                const double tnext = dmax2(dmax2(tp, tf), tma);
                 const bool own = (c.cls[s] == k);
                 // chunking.py:67-79: own class forces ON; ON pays the rate into class k
                 pen += c.qm[s * K + k] * rate * (tcur - tnext);
@@ -792,7 +799,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     const int ai = (sa_slot * K + k) * 3;
                     double n0 = u0, n1 = u1, np = pen;
                     if ((inited >> sa_slot) & 1u) { n0 *= acc[ai]; n1 *= acc[ai + 1]; np += acc[ai + 2]; }
-                    double m2 = fmax(n0, n1);
+                    double m2 = dmax2(n0, n1);
                     if (!(m2 > 0.0)) { bad = 1; m2 = 1.0; }
                     const double r2 = pow2_rescale(m2);
                     acc[ai] = n0 * r2; acc[ai + 1] = n1 * r2; acc[ai + 2] = np;
@@ -804,21 +811,22 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     bool live = true;
                     if (to > tcand) { xold ^= 1u; --io; }
                     else {
-                        const unsigned long long thr = own ? (xold ? thr_w1 : thr_w0) : (xold ? thr_o1 : thr_o0);
+                        const unsigned thr = own ? (xold ? thr_w1 : thr_w0) : (xold ? thr_o1 : thr_o0);
                         // (a candidate that ties with a retained event is dropped: probability ~2^-50)
-                        live = ((unsigned long long)nxb_xo_next(xo) < thr) && (tcand != to);
+                        live = (nxb_xo_next(xo) < thr) && (tcand != to);
                         // next arrival of the dominating process (rootward)
                         tcand -= exp_gap(xo, gsc);
                         if (!(tcand > tma)) tcand = -NXB_INF;
                     }
                     if (live) {
                         if (pen != 0.0) { u1 *= (double)expf((float)(-pen)); pen = 0.0; }
-                        double mx = fmax(u0, u1);
+                        double mx = dmax2(u0, u1);
                         if (!(mx > 0.0)) { bad = 1; mx = 1.0; }
                         const double r = pow2_rescale(mx);
                         const double l1 = u1 * r, l0 = u0 * r;       // scale-free message below the event
                         if (cnt < TCAP) {
-                            ctm[cnt] = tnext; cell[cnt] = make_float2((float)l0, (float)l1);
+                            LiveEv ev; ev.t = tnext; ev.l0 = (float)l0; ev.l1 = (float)l1;
+                            cev[cnt] = ev;
                             cedge[cnt] = (unsigned short)e;
                         } else bad = 2;
                         ++cnt;
@@ -872,8 +880,9 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         bool fresh = true;
         int s = 0, ip = 0, ipe = 0, vb = 0, n_on = 0, n_off = 0;
         double tmb = 0.0, tcur = 0.0, offtime = 0.0;
-        double pf_t = NXB_INF; unsigned pf_e = 0xffffu; float2 pf_l = make_float2(0.f, 0.f);
-        if (ir >= 0) { pf_t = ctm[ir]; pf_e = cedge[ir]; pf_l = cell[ir]; }
+        LiveEv pf; pf.t = NXB_INF; pf.l0 = 0.f; pf.l1 = 0.f;
+        unsigned pf_e = 0xffffu;
+        if (ir >= 0) { pf = cev[ir]; pf_e = cedge[ir]; }
         while (__any_sync(FULL, e < E)) {
             if (e < E) {
                 if (fresh) {
@@ -887,15 +896,15 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     fresh = false;
                 }
                 const double tp = (ip < ipe) ? c.ptm[ip] : NXB_INF;
-                const double tc = (pf_e == (unsigned)e) ? pf_t : NXB_INF;
-                const double tnext = fmin(fmin(tp, tc), tmb);
+                const double tc = (pf_e == (unsigned)e) ? pf.t : NXB_INF;
+                const double tnext = dmin2(dmin2(tp, tc), tmb);
                 if (!x) offtime += tnext - tcur;
                 tcur = tnext;
                 if (tc < tp) {
-                    const float l0 = pf_l.x, l1 = pf_l.y;
+                    const float l0 = pf.l0, l1 = pf.l1;
                     --ir;
-                    if (ir >= 0) { pf_t = ctm[ir]; pf_e = cedge[ir]; pf_l = cell[ir]; }
-                    else { pf_t = NXB_INF; pf_e = 0xffffu; }
+                    if (ir >= 0) { pf = cev[ir]; pf_e = cedge[ir]; }
+                    else { pf.t = NXB_INF; pf_e = 0xffffu; }
                     const bool own = (c.cls[s] == k);
                     const float p1 = own ? (x ? 1.f : 0.5f) : (x ? a_off1_f : a_on_f);
                     const float w1 = p1 * l1, w0 = (1.f - p1) * l0;
@@ -903,7 +912,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     const float u = (float)(nxb_xo_next(xo) >> 8) * (1.0f / 16777216.0f);
                     const unsigned xn = (u * (w0 + w1) < w1) ? 1u : 0u;
                     if (xn != x) {
-                        ctm[wtop] = tc;
+                        cev[wtop].t = tc;
                         cedge[wtop] = (unsigned short)(e | (xn ? CE_NEW1 : 0u));
                         --wtop;
                         if (xn) ++n_on; else ++n_off;
@@ -912,16 +921,14 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                 } else {
                     // primary event or the bottom of the edge: close the OFF-time segment
                     if (accumulate && offtime > 0.0)
-                        atomicAdd(p.dwell + sl.d_off + ((long long)e * P + s) * K + k, offtime);
+                        atomicAdd(p.dwell + (sl.d_off + (e * P + s) * K + k), offtime);
                     offtime = 0.0;
                     if (tp != NXB_INF) {
                         s = (c.pcode[ip] >> 24) & 0xffu;
                         ++ip;
                     } else {
-                        if (accumulate) {
-                            if (n_on) atomicAdd(&c.s_off_on[e], (unsigned long long)n_on);
-                            if (n_off) atomicAdd(&c.s_on_off[e], (unsigned long long)n_off);
-                        }
+                        if (accumulate && (n_on | n_off))
+                            atomicAdd(&c.s_off_on[e], ((unsigned long long)n_off << 32) | (unsigned)n_on);
                         if (x) atomicOr(&newtol[vb], 1u << k);
                         ++e;
                         fresh = true;
@@ -960,7 +967,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     for (int q = 0; q < n_mine; ++q) {
         const int src = TCAP - 1 - q;          // first survivor (rootmost, earliest) sits at the top
         const unsigned ce = cedge[src];
-        obtm[dst + q] = ctm[src];
+        obtm[dst + q] = cev[src].t;
         obcode[dst + q] = (unsigned)(ce & CE_EDGE) | ((unsigned)k << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);
     }
     __syncwarp();
