@@ -808,6 +808,14 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             for (int e = 0; e < E; ++e)
                 if (rate[e] > 0.0 && len[e] > 0.0) gsc[e] = (float)(0.6931471805599453 / (2.0 * M * rate[e]));
             ml.off_gsc_blk = put(gsc.data(), 4 * E, 4);
+            std::vector<NxbEdgeRec> recs(E);
+            for (int e = 0; e < E; ++e) {
+                recs[e].tma = tma[e]; recs[e].tmb = tma[e] + len[e]; recs[e].rate = rate[e];
+                recs[e].gsc = gsc[e]; recs[e].va = (unsigned short)parent[e];
+                recs[e].sa_slot = (signed char)slot[parent[e]];
+                recs[e].sb_slot = (signed char)slot[e + 1];
+            }
+            ml.off_edgerec = put(recs.data(), (int)(sizeof(NxbEdgeRec) * E), 16);
         }
         ml.off_qval = put(d->q_val, 8 * nnz, 8);
         std::vector<unsigned short> qinfo(nnz), qptr(P + 1);

@@ -52,6 +52,7 @@ struct NxbModelLayout {
     int off_lam_blk;    // f64    [E]   dominating Poisson mean, one blink track
     int off_p0_blk;     // f64    [E]   exp(-lam_blk)
     int off_gsc_blk;    // f32    [E]   ln2 / (dominating blink rate of the edge), 0 if inactive
+    int off_edgerec;    // NxbEdgeRec [E]  the per-edge constants of the blink walks, one 32-byte record
     int off_qval;       // f64    [nnz] normalised primary rates (CSR values)
     int off_qinfo;      // u16    [nnz] column | class(column) << 8
     int off_qptr;       // u16    [P+1]
@@ -69,6 +70,15 @@ struct NxbModelLayout {
     double acc_blk[4];      // thinning acceptance [own][fg state]
     double a_on, a_off;     // off-diagonal entries of the uniformized 2x2 blink matrix
     double p_on, p_off;     // blink prior at the root
+};
+
+// Per-edge constants read at every edge boundary of the tolerance walks.
+struct __align__(16) NxbEdgeRec {
+    double tma, tmb;        // times at the rootward / leafward end
+    double rate;            // edge rate scaling factor
+    float gsc;              // ln2 / dominating blink rate (0: no events possible on this edge)
+    unsigned short va;      // parent node (the child node is e + 1)
+    signed char sa_slot, sb_slot;   // accumulator slots of parent and child (-1: leaf)
 };
 
 // Per-warp shared-memory layout (bytes from the warp's base), chosen by the host

@@ -708,6 +708,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     unsigned short* cedge = (unsigned short*)(c.gbase + p.g_off_cedge) + (size_t)lane * TCAP;
     const SPtr<double> acc = {c.wbase + wl.off_acc};              // [slot][K][3]: u0, u1, penalty
     const SPtr<unsigned> newtol = {c.wbase + wl.off_newtol};
+    const SPtr<const NxbEdgeRec> erec = {(unsigned)ml.off_edgerec};
     const SPtr<int> poff = c.poff;
 
     phase_sync(c);
@@ -761,9 +762,10 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
             if (e >= 0) {
                 bool draw_gap = false;
                 if (fresh) {
-                    const int vb = e + 1, va = c.parent[e];
-                    sb_slot = c.slot[vb]; sa_slot = c.slot[va];
-                    tma = c.tma[e]; rate = c.rate[e]; tcur = tma + c.len[e];
+                    const NxbEdgeRec er = erec[e];
+                    const int vb = e + 1;
+                    sb_slot = er.sb_slot; sa_slot = er.sa_slot;
+                    tma = er.tma; rate = er.rate; tcur = er.tmb;
                     u0 = 1.0; u1 = 1.0; pen = 0.0;
                     if (sb_slot >= 0 && ((inited >> sb_slot) & 1u)) {
                         const int ai = (sb_slot * K + k) * 3;
@@ -775,7 +777,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     xold = (c.node_tol[vb] >> k) & 1u;
                     ip = poff[e + 1] - 1; ip0 = poff[e];
                     // dominating rate of the edge: 2 * max(on, off) * rate_e per unit time
-                    gsc = c.gsc_blk[e];
+                    gsc = er.gsc;
                     draw_gap = gsc > 0.f;
                     tcand = draw_gap ? tcur : -NXB_INF;
                     fresh = false;
@@ -886,12 +888,13 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         while (__any_sync(FULL, e < E)) {
             if (e < E) {
                 if (fresh) {
+                    const NxbEdgeRec er = erec[e];
                     vb = e + 1;
-                    const int va = c.parent[e];
+                    const int va = er.va;
                     x = (newtol[va] >> k) & 1u;
                     s = c.node_pri[va];
                     ip = poff[e]; ipe = poff[e + 1];
-                    tcur = c.tma[e]; tmb = tcur + c.len[e];
+                    tcur = er.tma; tmb = er.tmb;
                     offtime = 0.0; n_on = 0; n_off = 0;
                     fresh = false;
                 }
