@@ -1,0 +1,111 @@
+"""Shapes the reference's fixtures never reach: a 150-node random tree with polytomies and
+zero-length branches, 30 primary states in 8 classes; and the limits K = 32 classes / P = 64
+states.  No exact answer exists, so the checks are the trajectory invariants after every phase,
+the conservation laws, and prior invariance under the sweep (forward-simulated vs swept
+statistics agree)."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from nxblink_b200.summary import WeightGraph
+from nxblink_b200.toymodel import Tree
+from nxblink_b200 import packing
+
+pytestmark = pytest.mark.gpu
+
+
+class BigModel(object):
+    def __init__(self, n_nodes=150, P=30, K=8, seed=0, deg=3):
+        rng = np.random.default_rng(seed)
+        self.P, self.K = P, K
+        self.code = dict((s, 'c%02d' % (s % K)) for s in range(P))
+        w = rng.random(P) + 0.3
+        self.distn = dict((i, float(x)) for i, x in enumerate(w / w.sum()))
+        pairs = set((i, (i + 1) % P) for i in range(P))
+        while len(pairs) < deg * P // 2 + P:
+            a, b = rng.integers(0, P, size=2)
+            if a != b and (int(b), int(a)) not in pairs:
+                pairs.add((int(a), int(b)))
+        self.Q = {}
+        for a, b in sorted(pairs):
+            sym = float(rng.random() + 0.2)
+            self.Q[a, b] = sym * self.distn[b] * P
+            self.Q[b, a] = sym * self.distn[a] * P
+        self.edges, self.rates, self.blens = [], {}, {}
+        for v in range(1, n_nodes):
+            par = int(rng.integers(max(0, v - 12), v))      # polytomies and long chains both occur
+            e = ('n%d' % par, 'n%d' % v)
+            self.edges.append(e)
+            self.rates[e] = 0.0 if rng.random() < 0.05 else float(rng.random() * 0.3)
+            self.blens[e] = 0.0 if rng.random() < 0.03 else float(0.5 + rng.random())
+
+    def get_rate_on(self):
+        return 0.9
+
+    def get_rate_off(self):
+        return 1.7
+
+    def get_blink_distn(self):
+        return {0: 1.7 / 2.6, 1: 0.9 / 2.6}
+
+    def get_primary_to_tol(self):
+        return dict(self.code)
+
+    def get_T_and_root(self):
+        T = Tree()
+        for a, b in self.edges:
+            T.setdefault(a, []).append(b)
+            T.setdefault(b, [])
+        return T, 'n0'
+
+    def get_edge_to_blen(self):
+        return dict(self.blens)
+
+    def get_edge_to_rate(self):
+        return dict(self.rates)
+
+    def get_primary_distn(self):
+        return dict(self.distn)
+
+    def get_Q_primary(self):
+        Q = WeightGraph()
+        for (a, b), r in sorted(self.Q.items()):
+            Q.add_edge(a, b, r)
+        return Q
+
+
+def _prior_invariance(nb, M, n_units, sweeps):
+    pm = packing.PackedModel(M)
+    fwd, mcmc = [], []
+    for seed in range(4):
+        s = nb.BlinkSampler(pm, validate=True)
+        s.forward_sample(n_units, seed=seed)
+        s.reset_summary(); s.summarize_current()
+        sm = s.summary()
+        fwd.append(gu.scalar_functionals(sm))
+        E, K = pm.n_nodes - 1, pm.n_classes
+        np.testing.assert_allclose(sm.flat['T'].sum(axis=1), pm.blen[1:] * sm.nsamples, rtol=1e-10, atol=1e-9)
+        s.reset_summary()
+        s.sweep(sweeps, accumulate=True)
+        sm = s.summary()
+        assert sm.nsamples == n_units * sweeps
+        assert sm.root_on_total + sm.root_off_count == K * sm.nsamples
+        mcmc.append(gu.scalar_functionals(sm))
+        st = s.stats()
+        s.close()
+    for name in fwd[0]:
+        a = np.array([r[name] for r in fwd]); b = np.array([r[name] for r in mcmc])
+        se = np.hypot(a.std(ddof=1), b.std(ddof=1)) / np.sqrt(len(a))
+        assert abs(a.mean() - b.mean()) <= 5 * se + 3e-3 * max(1.0, abs(a.mean())), (name, a.mean(), b.mean(), se)
+    return st
+
+
+def test_large_irregular_tree(nb):
+    st = _prior_invariance(nb, BigModel(), n_units=4096, sweeps=5)
+    assert st['warps_per_cta'] >= 2
+
+
+def test_maximum_classes_and_states(nb):
+    """K = 32 tolerance classes (every lane a track, full-width masks), P = 64 states."""
+    M = BigModel(n_nodes=20, P=64, K=32, seed=3, deg=2)
+    _prior_invariance(nb, M, n_units=2048, sweeps=4)
