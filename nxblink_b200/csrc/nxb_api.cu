@@ -87,6 +87,9 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     const int group = warp / GW, wing = warp - group * GW;
     const bool lockstep = GW > 1;
     c.bar_id = 1 + group;
+    c.wing = wing;
+    c.gwbase = (unsigned)(p.smem_warp0 + (group * GW) * wl.bytes);
+    c.ggbase = p.gscratch + ((long long)blockIdx.x * (blockDim.x >> 5) + group * GW) * p.gscratch_stride;
     c.bar_threads = lockstep ? GW * 32 : 32;
     c.nbar = 0;
     unsigned long long* s_batch = (unsigned long long*)(smem + ml.off_stats) + ml.stats_words;
@@ -171,7 +174,8 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             c.sweep = init ? NXB_SWEEP_INIT : hdr.sweeps_done;
             const bool accum = !init && hdr.sweeps_done >= p.accum_from;
             c.nbar = 0;
-            c.sync_mask = blink_turn ? (p.sync_mask >> NXB_NBAR_PRIMARY) : p.sync_mask;
+            // the barriers of the tolerance update are not optional: its lanes work on other warps' units
+            c.sync_mask = blink_turn ? 0xffffffffu : p.sync_mask;
             if (!blink_turn) {
                 if (active && init) rc = init_blink(c);
                 if (active && rc == RC_OK) {
@@ -180,12 +184,16 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
                 }
                 phase_drain(c, NXB_NBAR_PRIMARY);
             } else {
-                if (active) {
-                    rc = blink_phase(c, accum);
-                    if (rc == RC_DEFER && c.nB < 0) {     // sweep complete, blink list spilled to HBM
-                        hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
-                        spilled = true;
-                    } else if (rc == RC_OK) { hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++; }
+                // every warp of a lockstep group takes part: its lanes carry tracks of other units
+                if (active || lockstep) {
+                    const int brc = blink_phase(c, accum, active);
+                    if (active) {
+                        rc = brc;
+                        if (rc == RC_DEFER && c.nB < 0) {     // sweep complete, blink list spilled to HBM
+                            hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
+                            spilled = true;
+                        } else if (rc == RC_OK) { hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++; }
+                    }
                 }
                 phase_drain(c, NXB_NBAR_BLINK);
             }
@@ -615,6 +623,7 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     wl->off_tmpa = take(4 * (E + 1), 4);
     wl->off_tmpb = take(4 * (E + 1), 4);
     wl->off_tmpc = take(4 * (E + 1), 4);
+    wl->off_uhdr = take(4 * (8 + 32), 4);
     const int scratch0 = align_up(o, 16);
     // primary-phase scratch
     o = scratch0;
@@ -644,6 +653,20 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     // between phases, when either scratch is dead.
     const int end_blk = o;
     wl->bytes = align_up(std::max(end_pri, end_blk), 16);
+}
+
+// Warps per lockstep group.  Several small groups per CTA drift out of phase, so the walks of
+// one group's tolerance update (few, fully populated warps) overlap another group's primary
+// update; measured on the p53 shape with 20 warps: 5 -> 11.8, 10 -> 11.6, 4 -> 11.3, 20 -> 11.1
+// M unit-sweeps/s.  Automatic choice: 5, 4 or 6, whichever leaves the fewest warps unused.
+static int group_warps_for(const nxb_handle* h, int warps) {
+    if (h->lockstep == 0 || warps < 2) return 1;
+    if (h->lockstep > 0) return std::min(warps, h->lockstep);
+    if (warps < 8) return warps;
+    int best = 5;
+    for (int g : {5, 4, 6})
+        if (warps / g * g > warps / best * best) best = g;
+    return best;
 }
 
 extern "C" int nxb_device_count(void) {
@@ -699,7 +722,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     h->validate = d->validate;
     if (getenv("NXB_SYNC_MASK")) h->sync_mask = (unsigned)strtoul(getenv("NXB_SYNC_MASK"), nullptr, 0);
     // default: one group of up to 20 warps (measured best at the p53 shape); negative switches it off
-    h->lockstep = d->lockstep_warps == 0 ? 20 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);
+    h->lockstep = d->lockstep_warps == 0 ? -1 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);   // -1: automatic
 #define CUDA_TRY_C(call)                                                                  \
     do {                                                                                  \
         cudaError_t e_ = (call);                                                          \
@@ -1096,7 +1119,7 @@ static int run_tiers(nxb_handle* h, unsigned target, unsigned accum_from, int in
         p.defer_list = h->d_defer[t & 1]; p.defer_count = h->d_defer_count;
         p.seed = h->seed; p.target_sweeps = target; p.accum_from = accum_from;
         p.init = (init && t == 0) ? 1 : 0;
-        p.group_warps = (t == 0 && h->lockstep) ? std::min(tier.warps, h->lockstep) : 1;
+        p.group_warps = (t == 0) ? group_warps_for(h, tier.warps) : 1;
         p.begin_sweeps = h->sweeps;
         p.sync_mask = h->sync_mask;
         p.validate = h->validate;
@@ -1109,7 +1132,7 @@ static int run_tiers(nxb_handle* h, unsigned target, unsigned accum_from, int in
         CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
         CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
         const long long n_work = list ? n_list : h->n_units;
-        const int gw = (t == 0 && h->lockstep) ? std::min(tier.warps, h->lockstep) : 1;
+        const int gw = p.group_warps;
         const int launch_warps = tier.warps / gw * gw;       // whole groups only
         int grid = (int)std::min<long long>(h->num_sms, (n_work + launch_warps - 1) / launch_warps);
         grid = std::max(grid, 1);

@@ -98,6 +98,7 @@ struct NxbWarpLayout {
         off_finv, off_fu;
     // blink-phase scratch
     int off_ctm, off_cell, off_cedge, off_toff, off_acc, off_newtol;
+    int off_uhdr;           // int[8 + 32]: unit header read by the lane jobs of other warps (persistent region)
     int bytes;
 };
 

@@ -82,6 +82,9 @@ struct Ctx {
     // its code is fetched once per SM instead of once per warp (the kernel is several times
     // larger than the instruction cache and instruction fetch was the top limiter)
     int bar_id, bar_threads, nbar;
+    int wing;                 // warp index within its lockstep group
+    unsigned gwbase;          // shared-memory offset of the group's first warp region
+    unsigned char* ggbase;    // global scratch of the group's first warp slot
     unsigned sync_mask;       // which of the sync points actually wait (bit = nbar index)
 };
 
@@ -693,34 +696,68 @@ __device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a :
 #define CE_EDGE 0x3fffu
 #define CE_NEW1 0x4000u     // (survivors only) new state of the surviving event
 
-__device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
+__device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active) {
     const NxbSweepParams& p = *c.p;
     const NxbWarpLayout& wl = p.wl;
     const NxbModelLayout& ml = p.ml;
     const int E = c.E, N = c.N, P = c.P, K = c.K, lane = c.lane;
-
-    // live foreground events of this sweep: global (L2-resident) scratch, one fixed region per
-    // track, filled by the upward pass and consumed backwards by the downward pass
     const int TCAP = p.gcapC;
     // one 16-byte record per live event: time, (OFF, ON) message below the event
     struct __align__(16) LiveEv { double t; float l0, l1; };
-    LiveEv* cev = (LiveEv*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
-    unsigned short* cedge = (unsigned short*)(c.gbase + p.g_off_cedge) + (size_t)lane * TCAP;
-    const SPtr<double> acc = {c.wbase + wl.off_acc};              // [slot][K][3]: u0, u1, penalty
-    const SPtr<unsigned> newtol = {c.wbase + wl.off_newtol};
     const SPtr<const NxbEdgeRec> erec = {(unsigned)ml.off_edgerec};
-    const SPtr<int> poff = c.poff;
 
+    // ---- S0 (own warp): index of the primary events, unit header for the lane jobs ----------------
     phase_sync(c);
-    build_poff(c);
+    const SPtr<int> uhdr_own = {c.wbase + wl.off_uhdr};        // [0] active [2] nB [3] unit32 [4] bad [5] sweep [6] accumulate, [8+k] survivors
+    const SPtr<unsigned> newtol_own = {c.wbase + wl.off_newtol};
+    if (active) {
+        build_poff(c);
+        for (int v = lane; v < N; v += 32) newtol_own[v] = 0u;
+    }
+    if (lane == 0) {
+        uhdr_own[0] = active ? 1 : 0; uhdr_own[2] = c.nB; uhdr_own[3] = (int)c.unit32; uhdr_own[4] = 0;
+        uhdr_own[5] = (int)c.sweep; uhdr_own[6] = accumulate ? 1 : 0;
+    }
+    __syncwarp();
 
-    const bool trk = lane < K;
-    const int k = trk ? lane : 0;
+    // ---- lane jobs.  Lane j of the lockstep group carries track j % K of unit j / K of the group
+    // (any unit resident in this CTA's shared memory), so every lane of the busy warps walks a
+    // track; with lane = track only K of 32 lanes would (20 of 32 at the p53 shape) and the
+    // remaining warps of the group skip the walks altogether.
+    const int GW = c.bar_threads >> 5;                 // 1 when the warps run independently
+    const int n_jobs = GW * K;
+    const int job = c.wing * 32 + lane;
+    const bool has_job = job < n_jobs;
+    const int ju = has_job ? job / K : 0;
+    const int k = has_job ? job - ju * K : 0;
+    const unsigned ub = c.gwbase + (unsigned)(ju * wl.bytes);             // unit ju's shared-memory region
+    unsigned char* const ugb = c.ggbase + (long long)ju * p.gscratch_stride;
+    // live foreground events of this sweep: global (L2-resident) scratch, one fixed region per
+    // (unit, track), filled by the upward pass and consumed backwards by the downward pass
+    LiveEv* cev = (LiveEv*)(ugb + p.g_off_ctm) + (size_t)k * TCAP;
+    unsigned short* cedge = (unsigned short*)(ugb + p.g_off_cedge) + (size_t)k * TCAP;
+    const SPtr<int> uhdr = {ub + wl.off_uhdr};
+    const SPtr<double> acc = {ub + wl.off_acc};                 // [slot][K][3]: u0, u1, penalty
+    const SPtr<unsigned> newtol = {ub + wl.off_newtol};
+    const SPtr<int> poff = {ub + wl.off_poff};
+    const SPtr<unsigned> u_node_tol = {ub + wl.off_node_tol};
+    const SPtr<unsigned char> u_node_pri = {ub + wl.off_node_pri};
+    const SPtr<double> u_ptm = {ub + wl.off_ptm};
+    const SPtr<unsigned> u_pcode = {ub + wl.off_pcode};
+    const SPtr<double> u_btm = {ub + wl.off_btm};
+    const SPtr<unsigned> u_bcode = {ub + wl.off_bcode};
+    const SPtr<const unsigned> u_tt_ok = {ub + wl.off_dtt}, u_tf_ok = {ub + wl.off_dtf};
+    tick(c, T_B0);
+    phase_sync(c);            // (a named barrier orders shared memory across the group)
+
+    const bool trk = has_job && uhdr[0] != 0;
+    const int nB_u = trk ? uhdr[2] : 0;
+    const bool accum_u = trk && uhdr[6] != 0;
     // retained events of track k are the contiguous run [olo, ohi) of the (track, edge, time)
     // sorted list
     int olo = 0, ohi = 0;
-    for (int i = 0; i < c.nB; ++i) {
-        const int kt = (int)((c.bcode[i] >> 16) & 0xffu);
+    for (int i = 0; i < nB_u; ++i) {
+        const int kt = (int)((u_bcode[i] >> 16) & 0xffu);
         olo += kt < k;
         ohi += kt <= k;
     }
@@ -728,11 +765,9 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     // per-track sequential stream: candidate gaps, thinning and backward-sampling decisions
     NxbXo xo;
     {
-        NxbU4 r = rng(c, NXB_STREAM_BLK_FFBS | ((unsigned)k << 16), 0u);
+        NxbU4 r = philox_call((unsigned)uhdr[3], (unsigned)uhdr[5], NXB_STREAM_BLK_FFBS | ((unsigned)k << 16), 0u, c.k0, c.k1);
         xo.s0 = r.x; xo.s1 = r.y; xo.s2 = r.z; xo.s3 = r.w | 1u;
     }
-    tick(c, T_B0);
-    phase_sync(c);
 
     // ---- B1: upward pass.  Every lane walks its own track through the edges in descending
     // index (children before parents), one boundary per iteration: a retained event of the old
@@ -771,10 +806,10 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                         const int ai = (sb_slot * K + k) * 3;
                         u0 = acc[ai]; u1 = acc[ai + 1]; pen = acc[ai + 2];
                     }
-                    if (!((c.tt_ok[vb] >> k) & 1u)) u1 = 0.0;
-                    if (!((c.tf_ok[vb] >> k) & 1u)) u0 = 0.0;
-                    s = c.node_pri[vb];
-                    xold = (c.node_tol[vb] >> k) & 1u;
+                    if (!((u_tt_ok[vb] >> k) & 1u)) u1 = 0.0;
+                    if (!((u_tf_ok[vb] >> k) & 1u)) u0 = 0.0;
+                    s = u_node_pri[vb];
+                    xold = (u_node_tol[vb] >> k) & 1u;
                     ip = poff[e + 1] - 1; ip0 = poff[e];
                     // dominating rate of the edge: 2 * max(on, off) * rate_e per unit time
                     gsc = er.gsc;
@@ -786,9 +821,9 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     tcand -= exp_gap(xo, gsc);
                     if (!(tcand > tma)) tcand = -NXB_INF;
                 }
-                const double tp = (ip >= ip0) ? c.ptm[ip] : -NXB_INF;
-                const bool haso = (io >= olo) && ((c.bcode[io] & 0xffffu) == (unsigned)e);
-                const double to = haso ? c.btm[io] : -NXB_INF;
+                const double tp = (ip >= ip0) ? u_ptm[ip] : -NXB_INF;
+                const bool haso = (io >= olo) && ((u_bcode[io] & 0xffffu) == (unsigned)e);
+                const double to = haso ? u_btm[io] : -NXB_INF;
                 const double tf = dmax2(to, tcand);
                 const double tnext = dmax2(dmax2(tp, tf), tma);
                 const bool own = (c.cls[s] == k);
@@ -840,7 +875,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                         }
                     }
                 } else {
-                    s = (c.pcode[ip] >> 16) & 0xffu;     // rootward: the state before the event
+                    s = (u_pcode[ip] >> 16) & 0xffu;     // rootward: the state before the event
                     --ip;
                 }
             }
@@ -855,19 +890,13 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
         const int ai = (c.slot[0] * K + k) * 3;
         double w1 = acc[ai + 1] * exp(-acc[ai + 2]) * ml.p_on;
         double w0 = acc[ai] * ml.p_off;
-        if (!((c.tt_ok[0] >> k) & 1u)) w1 = 0.0;
-        if (!((c.tf_ok[0] >> k) & 1u)) w0 = 0.0;
-        if (c.cls[c.node_pri[0]] == k) w0 = 0.0;
+        if (!((u_tt_ok[0] >> k) & 1u)) w1 = 0.0;
+        if (!((u_tf_ok[0] >> k) & 1u)) w0 = 0.0;
+        if (c.cls[u_node_pri[0]] == k) w0 = 0.0;
         if (!(w0 + w1 > 0.0)) bad = 1;
         x = (nxb_u32(nxb_xo_next(xo)) * (w0 + w1) < w1) ? 1u : 0u;
     }
-    {
-        const int worst = __reduce_max_sync(FULL, bad);
-        if (worst == 2) { fail(c, NXB_ERR_SCRATCH_CAP, cnt); return RC_ERROR; }
-        if (worst) { fail(c, NXB_ERR_INFEASIBLE, -2); return RC_ERROR; }
-        unsigned bal = __ballot_sync(FULL, x);
-        for (int v = lane; v < N; v += 32) newtol[v] = (v == 0) ? bal : 0u;
-    }
+    if (trk && x) atomicOr(&newtol[0], 1u << k);
     __syncwarp();
 
     // ---- B2: downward sampling, edges in ascending index: the live events are read back in
@@ -892,13 +921,13 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     vb = e + 1;
                     const int va = er.va;
                     x = (newtol[va] >> k) & 1u;
-                    s = c.node_pri[va];
+                    s = u_node_pri[va];
                     ip = poff[e]; ipe = poff[e + 1];
                     tcur = er.tma; tmb = er.tmb;
                     offtime = 0.0; n_on = 0; n_off = 0;
                     fresh = false;
                 }
-                const double tp = (ip < ipe) ? c.ptm[ip] : NXB_INF;
+                const double tp = (ip < ipe) ? u_ptm[ip] : NXB_INF;
                 const double tc = (pf_e == (unsigned)e) ? pf.t : NXB_INF;
                 const double tnext = dmin2(dmin2(tp, tc), tmb);
                 if (!x) offtime += tnext - tcur;
@@ -923,14 +952,14 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
                     }
                 } else {
                     // primary event or the bottom of the edge: close the OFF-time segment
-                    if (accumulate && offtime > 0.0)
+                    if (accum_u && offtime > 0.0)
                         atomicAdd(p.dwell + (sl.d_off + (e * P + s) * K + k), offtime);
                     offtime = 0.0;
                     if (tp != NXB_INF) {
-                        s = (c.pcode[ip] >> 24) & 0xffu;
+                        s = (u_pcode[ip] >> 24) & 0xffu;
                         ++ip;
                     } else {
-                        if (accumulate && (n_on | n_off))
+                        if (accum_u && (n_on | n_off))
                             atomicAdd(&c.s_off_on[e], ((unsigned long long)n_off << 32) | (unsigned)n_on);
                         if (x) atomicOr(&newtol[vb], 1u << k);
                         ++e;
@@ -940,17 +969,27 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
             }
         }
     }
-    __syncwarp();
-    if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
+    if (trk) {
+        uhdr[8 + k] = TCAP - 1 - wtop;                  // survivors of this track
+        if (bad) atomicOr(&uhdr[4], bad);
+    }
     tick(c, T_B2);
     phase_sync(c);
 
-    // ---- write back: new retained blink events, (track, edge, time) order -----------------------------
-    int n_mine = trk ? (TCAP - 1 - wtop) : 0, total;
+    // ---- S3 (own warp): write back the new retained blink events, (track, edge, time) order ------------
+    if (!active) return RC_OK;
+    {
+        const int flags = uhdr_own[4];
+        if (flags & 2) { fail(c, NXB_ERR_SCRATCH_CAP, 0); return RC_ERROR; }
+        if (flags & 1) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
+    }
+    LiveEv* cev_own = (LiveEv*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
+    unsigned short* cedge_own = (unsigned short*)(c.gbase + p.g_off_cedge) + (size_t)lane * TCAP;
+    int n_mine = (lane < K) ? uhdr_own[8 + lane] : 0, total;
     int dst = warp_excl_scan(n_mine, lane, total);
-    for (int v = lane; v < N; v += 32) c.node_tol[v] = newtol[v];
+    for (int v = lane; v < N; v += 32) c.node_tol[v] = newtol_own[v];
     if (accumulate && lane == 0) {
-        int on = __popc(newtol[0]);
+        int on = __popc(newtol_own[0]);
         atomicAdd(&c.s_root_misc[0], (unsigned long long)on);
         atomicAdd(&c.s_root_misc[1], (unsigned long long)(K - on));
         atomicAdd(&c.s_root_on_cls[c.cls[c.node_pri[0]]], (unsigned long long)on);
@@ -969,9 +1008,9 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate) {
     }
     for (int q = 0; q < n_mine; ++q) {
         const int src = TCAP - 1 - q;          // first survivor (rootmost, earliest) sits at the top
-        const unsigned ce = cedge[src];
-        obtm[dst + q] = cev[src].t;
-        obcode[dst + q] = (unsigned)(ce & CE_EDGE) | ((unsigned)k << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);
+        const unsigned ce = cedge_own[src];
+        obtm[dst + q] = cev_own[src].t;
+        obcode[dst + q] = (unsigned)(ce & CE_EDGE) | ((unsigned)lane << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);
     }
     __syncwarp();
     tick(c, T_BW);
