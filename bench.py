@@ -268,6 +268,13 @@ def run_gpu_arm(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max, e2e_ms_max = [float(x) for x in t.tolist()]
+    # per-rank device time and SM clock, for reading the scaling numbers
+    mine = torch.tensor([dev_ms / args.steps, float(clock_info.get('sm_mhz') or 0.0)],
+            dtype=torch.float64, device='cuda')
+    per_rank = [mine.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    per_rank = [[round(float(v), 4) for v in x.tolist()] for x in per_rank]
 
     if rank == 0:
         total_units = n_units * world
@@ -331,6 +338,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                 'sample': '%d host processes x 1 p53-shaped site x 1 chain x %d sweeps (after 1 '
                     'burn-in), %.1f s wall' % (cores, args.cpu_sweeps, cpu_wall)},
             'allreduce_ms': allreduce_ms,
+            'per_rank_ms_and_sm_mhz': per_rank,
         }
         print(json.dumps(out))
     sampler.close()
