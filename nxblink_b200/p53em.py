@@ -7,8 +7,7 @@ M-step: the reference's objective -- minus (get_ll_root + get_ll_dwell + get_ll_
 of nxblink/em.py over log-parameters (kappa, omega, A, C, G, T, blink on, blink off, one
 rate per edge; p53em.py:143-185) -- minimised with L-BFGS-B.  The reference differentiates
 it with algopy forward-mode AD; here the objective is evaluated vectorised on the flat
-device statistics and the gradient is analytic where it is cheap (blink and edge rates)
-and finite-difference for the six codon-model parameters.
+device statistics together with its closed-form gradient (``MStep.neg_ll_and_grad``).
 """
 from __future__ import division, print_function
 
@@ -97,6 +96,54 @@ class MStep(object):
                 + np.dot(self.trans_total, np.log(rates / expected_rate)))
         return -(ll_root + ll_dwell + ll_trans) / self.n
 
+    def neg_ll_and_grad(self, log_params):
+        """``neg_ll`` and its exact gradient in the log-parameters (closed form; the reference
+        gets the same numbers from algopy forward-mode AD, p53em.py:39-56,94-140).
+
+        With q_i = nt[to_i] kappa^[ts_i] omega^[non_i], D_e = sum_i dwell_ei q_i + on*offdwell_e
+        + off*ondwell_e, A = sum_e rate_e D_e, TT = sum_e transitions_e and
+        ER = sum_i distn[row_i] q_i:
+            n*LL = root_pri.log(distn) + root_off log p_off + root_xon log p_on - A/ER
+                   + sum_ei trans_ei log q_i + OffOn log on + OnOff log off
+                   + sum_e transitions_e (log rate_e - log ER).
+        """
+        kappa, omega, nt, on, off, rates, _ = unpack_params(log_params)
+        q = self.pre_Q(kappa, omega, nt)
+        distn = self.distn(nt)
+        P = len(distn)
+        rowsum = np.bincount(self.rows, weights=q, minlength=P)
+        ER = np.dot(rowsum, distn)
+        p_off, p_on = off / (on + off), on / (on + off)
+        D = self.pri_dwell.dot(q) + self.off_xon_dwell * on + self.xon_off_dwell * off
+        A = np.dot(D, rates)
+        TT = self.trans_total.sum()
+        with np.errstate(divide='ignore'):
+            logq = np.log(q)
+        ll = (np.dot(self.root_pri, np.log(distn)) + self.root_off * np.log(p_off)
+                + self.root_xon * np.log(p_on) - A / ER
+                + self.pri_trans.dot(logq).sum() + self.off_on.sum() * np.log(on)
+                + self.on_off.sum() * np.log(off)
+                + np.dot(self.trans_total, np.log(rates / ER)))
+        g = np.zeros(len(log_params))
+        dER = A / ER ** 2 - TT / ER                      # d(n LL) / d ER
+        # d / d log q_i: direct terms + through ER
+        G = -rates.dot(self.pri_dwell) * q / ER + self.pri_trans.sum(axis=0) \
+                + dER * distn[self.rows] * q
+        g[0] = G[self.is_ts].sum()
+        g[1] = G[self.is_non].sum()
+        # nucleotide frequencies enter through q and through the codon distribution
+        dlogdistn = self.root_pri + dER * rowsum * distn           # d(n LL) / d log distn_s
+        cbar = distn.dot(self.nt_counts)
+        h = np.bincount(self.nt_to, weights=G, minlength=4) \
+                + dlogdistn.dot(self.nt_counts - cbar[None, :])
+        g[2:6] = h - nt * h.sum()
+        g[6] = (-self.root_off * p_on + self.root_xon * p_off
+                - np.dot(rates, self.off_xon_dwell) * on / ER + self.off_on.sum())
+        g[7] = (self.root_off * p_on - self.root_xon * p_off
+                - np.dot(rates, self.xon_off_dwell) * off / ER + self.on_off.sum())
+        g[8:] = -rates * D / ER + self.trans_total
+        return -ll / self.n, -g / self.n
+
     def closed_form_edge_rates(self, kappa, omega, nt, on, off):
         """Stationary point in the edge rates: rate_e = ER * transitions_e / dwell_e."""
         q = self.pre_Q(kappa, omega, nt)
@@ -113,7 +160,7 @@ def maximization_step(mstep, kappa, omega, A, C, G, T, blink_on, blink_off, edge
     import scipy.optimize
     rates = np.maximum(np.asarray(edge_rates, dtype=float), 1e-12)
     x0 = np.log(np.concatenate([[kappa, omega, A, C, G, T, blink_on, blink_off], rates]))
-    res = scipy.optimize.minimize(mstep.neg_ll, x0, method='L-BFGS-B', jac='2-point',
+    res = scipy.optimize.minimize(mstep.neg_ll_and_grad, x0, method='L-BFGS-B', jac=True,
             options=dict(maxiter=maxiter))
     kappa, omega, nt, on, off, rates, penalty = unpack_params(res.x)
     return dict(kappa=kappa, omega=omega, A=nt[0], C=nt[1], G=nt[2], T=nt[3], rate_on=on,
