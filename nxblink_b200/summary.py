@@ -16,10 +16,14 @@ Device primitives -> reference statistics
 """
 from __future__ import division, print_function
 
+import math
 from collections import defaultdict
 from io import StringIO
 
 import numpy as np
+
+__all__ = ['WeightGraph', 'Summary', 'gen_segments', 'get_ell_init_contrib',
+        'get_ell_dwell_contrib', 'get_ell_trans_contrib', 'mean_ell_contribs']
 
 
 class WeightGraph(dict):
@@ -157,12 +161,7 @@ class Summary(object):
                         self.edge_to_off_xon_trans[edge] += 1
                     else:
                         raise Exception('blink self transition')
-            va, vb = edge
-            state = dict((t.name, t.history[va]) for t in tracks)
-            seq = sorted(((ev.tm, i, ev) for i, ev in enumerate(
-                ev for t in tracks for ev in t.events[edge])), key=lambda x: x[:2])
-            tm = self._node_to_tm[va]
-            for tm_next, ev in [(a, c) for a, b, c in seq] + [(self._node_to_tm[vb], None)]:
+            for tm, tm_next, state in gen_segments(edge, self._node_to_tm, tracks):
                 elapsed = tm_next - tm
                 sa = state[primary_track.name]
                 for sb in self._Q_primary[sa]:
@@ -176,11 +175,6 @@ class Summary(object):
                             self.edge_to_xon_off_dwell[edge] += elapsed
                         else:
                             self.edge_to_off_xon_dwell[edge] += elapsed
-                if ev is not None:
-                    if state[ev.track.name] != ev.sa:
-                        raise Exception('incompatible transition')
-                    state[ev.track.name] = ev.sb
-                    tm = tm_next
 
     def __str__(self):
         """Same report as summary.py:133-182."""
@@ -212,3 +206,138 @@ class Summary(object):
                 for sb in sorted(pri_dwell[sa]):
                     print('      ', sa, '->', sb, ':', pri_dwell[sa][sb]['weight'], file=s)
         return s.getvalue()
+
+
+# -- per-sample functionals of exported tracks ---------------------------------------------------
+
+def gen_segments(edge, node_to_tm, tracks):
+    """navigation.py:14-46 (golden vector: nxblink/tests/test_navigation.py:30-37): the maximal
+    pieces of an edge on which no track changes, as ``(tm, tm_next, {track name: state})``.
+    Like the reference, the SAME mutable dict is yielded every time."""
+    va, vb = edge
+    state = dict((t.name, t.history[va]) for t in tracks)
+    seq = sorted(((ev.tm, i, ev) for i, ev in enumerate(
+        ev for t in tracks for ev in t.events[edge])), key=lambda x: x[:2])
+    tm = node_to_tm[va]
+    for tm_next, i, ev in seq:
+        yield tm, tm_next, state
+        if state[ev.track.name] != ev.sa:
+            raise Exception('incompatible transition')
+        state[ev.track.name] = ev.sb
+        tm = tm_next
+    yield tm, node_to_tm[vb], state
+
+
+def _rate(G, a, b):
+    """G[a][b]['weight'] of an nx.DiGraph-like table, or None."""
+    row = G[a] if a in G else None
+    if row is None or b not in row:
+        return None
+    w = row[b]
+    return w['weight'] if isinstance(w, dict) else w
+
+
+def _edges_of(T):
+    return list(T.edges()) if hasattr(T, 'edges') else [(a, b) for a in T for b in T[a]]
+
+
+def get_ell_init_contrib(root, primary_distn, blink_distn,
+        primary_track, tolerance_tracks, primary_to_tol):
+    """summary.py:247-261: log prior of the root state of one sampled trajectory (the own
+    class of the root's primary state is forced ON and contributes nothing)."""
+    primary_state = primary_track.history[root]
+    own = primary_to_tol[primary_state]
+    ll = math.log(primary_distn[primary_state])
+    for t in tolerance_tracks:
+        if t.name != own:
+            ll += math.log(blink_distn[t.history[root]])
+    return ll
+
+
+def get_ell_dwell_contrib(T, root, node_to_tm, edge_to_rate, Q_primary, Q_blink, Q_meta,
+        primary_track, tolerance_tracks, primary_to_tol):
+    """summary.py:265-317: per edge, minus (edge rate x total exit rate x time) summed over the
+    all-constant segments of one sampled trajectory.  ``Q_primary`` is used as given (the
+    reference does not rescale it here: SURVEY quirk 5)."""
+    tracks = [primary_track] + list(tolerance_tracks)
+    rate_off, rate_on = _rate(Q_blink, True, False), _rate(Q_blink, False, True)
+    out = {}
+    for edge in _edges_of(T):
+        contrib = 0
+        for tma, tmb, state in gen_segments(edge, node_to_tm, tracks):
+            pri = state[primary_track.name]
+            own = primary_to_tol[pri]
+            rate = 0
+            for t in tolerance_tracks:
+                into = _rate(Q_meta, pri, t.name)
+                if t.name == own:
+                    if into is not None:
+                        rate += into
+                elif state[t.name]:
+                    rate += rate_off
+                    if into is not None:
+                        rate += into
+                else:
+                    rate += rate_on
+            contrib += -(edge_to_rate[edge] * rate * (tmb - tma))
+        out[edge] = contrib
+    return out
+
+
+def get_ell_trans_contrib(T, root, edge_to_rate, Q_primary, Q_blink,
+        primary_track, tolerance_tracks):
+    """summary.py:321-348: per edge, the sum of log(edge rate x transition rate) over the
+    events of one sampled trajectory."""
+    out = {}
+    for edge in _edges_of(T):
+        contrib = 0
+        for ev in primary_track.events[edge]:
+            rate = _rate(Q_primary, ev.sa, ev.sb)
+            if rate is None:
+                raise Exception('primary transition that the rate matrix does not have')
+            contrib += math.log(edge_to_rate[edge] * rate)
+        for t in tolerance_tracks:
+            for ev in t.events[edge]:
+                if bool(ev.sa) == bool(ev.sb):
+                    raise Exception('blink self transition')
+                contrib += math.log(edge_to_rate[edge] * _rate(Q_blink, ev.sa, ev.sb))
+        out[edge] = contrib
+    return out
+
+
+def mean_ell_contribs(summary, pm, edge_to_rate, Q_primary, rate_on, rate_off,
+        primary_distn, blink_distn):
+    """Per-sample AVERAGES of the three functionals above, from the statistics the sweep
+    kernel reduced on the device -- what examples/codon2x3/toymodel-stochastic.py:137-196
+    obtains by calling them on every sample in a Python loop.
+
+    summary : ``Summary.from_device`` result; pm : its ``PackedModel``.
+    Returns ``(ell_init, {edge: ell_dwell}, {edge: ell_trans})``.
+    """
+    f, n = summary.flat, float(summary.nsamples)
+    P, K = pm.n_states, pm.n_classes
+    q = np.array([_rate(Q_primary, pm.states[a], pm.states[b]) or 0.0
+        for a, b in zip(pm.q_row, pm.q_col)], dtype=float)
+    qmeta = np.zeros((P, K))
+    np.add.at(qmeta, (pm.q_row, pm.state_class[pm.q_col]), q)
+    rates = np.array([edge_to_rate[e] for e in pm.edges], dtype=float)
+    # exit rate of a segment = sum_k Qmeta[s][k] [k ON] + off * #(non-own ON) + on * #OFF
+    exit_time = (f['T'] * qmeta.sum(axis=1)[None, :]).sum(axis=1) \
+            - (f['Doff'] * qmeta[None, :, :]).sum(axis=(1, 2)) \
+            + rate_off * f['xon_off_dwell'] + rate_on * f['off_xon_dwell']
+    dwell = -rates * exit_time / n
+    with np.errstate(divide='ignore'):
+        logq, logr = np.log(q), np.log(rates)
+    ntrans = f['pri_trans'].sum(axis=1) + f['off_on'] + f['on_off']
+    trans = np.where(ntrans > 0, ntrans * np.where(ntrans > 0, logr, 0.0), 0.0) \
+            + np.where(f['pri_trans'] > 0, f['pri_trans'] * np.where(f['pri_trans'] > 0, logq, 0.0),
+                    0.0).sum(axis=1) \
+            + f['off_on'] * math.log(rate_on) + f['on_off'] * math.log(rate_off)
+    trans = trans / n
+    pd = np.array([primary_distn.get(st, 0.0) if hasattr(primary_distn, 'get') else primary_distn[st]
+        for st in pm.states], dtype=float)
+    with np.errstate(divide='ignore'):
+        lp = np.where(f['root_pri'] > 0, f['root_pri'] * np.log(np.where(pd > 0, pd, 1.0)), 0.0)
+    init = (lp.sum() + summary.root_off_count * math.log(blink_distn[0])
+            + summary.root_xon_intended * math.log(blink_distn[1])) / n
+    return (init, dict(zip(pm.edges, dwell.tolist())), dict(zip(pm.edges, trans.tolist())))

@@ -6,6 +6,7 @@ TEST INFRASTRUCTURE ONLY.  Usage (from the repo root, where /root/reference exis
     python -m oracle.refcompat.make_golden toy      # tests/golden/ref_toy.json
     python -m oracle.refcompat.make_golden p53 0    # tests/golden/ref_p53_site0.json
     python -m oracle.refcompat.make_golden mg94     # tests/golden/ref_mg94.json
+    python -m oracle.refcompat.make_golden ell      # tests/golden/ref_ell_contrib.json
 
 The sampled statistics are single recorded runs of the reference sampler (its RNG
 is the global numpy.random, seeded here, but its consumption order depends on
@@ -222,6 +223,58 @@ def make_p53(site, nsamples=600, nburnin=30):
     print('p53 site', site, 'done in %.1fs' % rec['seconds'])
 
 
+def make_ell(nsamples=6, nburnin=5):
+    """Trajectories sampled by the reference together with the reference's own per-sample
+    functionals of them (summary.py:247-348 as driven by toymodel-stochastic.py:137-196)."""
+    loader.load()
+    from nxblink.toymodel import BlinkModelB, BlinkModelC
+    from nxblink.toydata import DataA, DataC
+    from nxblink.raoteh import gen_samples
+    from nxblink.model import get_Q_meta
+    from nxblink.util import get_node_to_tm
+    from nxblink.navigation import gen_segments
+    from nxblink.summary import (get_ell_init_contrib, get_ell_dwell_contrib,
+            get_ell_trans_contrib)
+    out = {}
+    for M, D in ((BlinkModelB, DataC), (BlinkModelC, DataA)):
+        np.random.seed(4242)
+        T, root = M.get_T_and_root()
+        edges = list(T.edges())
+        node_to_tm = get_node_to_tm(T, root, M.get_edge_to_blen())
+        edge_to_rate = M.get_edge_to_rate()
+        primary_to_tol = M.get_primary_to_tol()
+        Q_primary = M.get_Q_primary()
+        Q_blink = M.get_Q_blink()
+        Q_meta = get_Q_meta(Q_primary, primary_to_tol)
+        samples = []
+        for pri, tols in gen_samples(M, D, nburnin, nsamples):
+            tracks = []
+            for t in [pri] + tols:
+                tracks.append(dict(name=t.name,
+                    history=dict((v, int(x)) for v, x in t.history.items()),
+                    events=[[list(e), [[float(ev.tm), int(ev.sa), int(ev.sb)] for ev in t.events[e]]]
+                        for e in edges]))
+            d = get_ell_dwell_contrib(T, root, node_to_tm, edge_to_rate, Q_primary, Q_blink,
+                    Q_meta, pri, tols, primary_to_tol)
+            tr = get_ell_trans_contrib(T, root, edge_to_rate, Q_primary, Q_blink, pri, tols)
+            segs = [[float(a), float(b), sorted((str(k), int(v)) for k, v in st.items())]
+                    for a, b, st in gen_segments(edges[0], node_to_tm, [pri] + tols)]
+            samples.append(dict(tracks=tracks,
+                ell_init=float(get_ell_init_contrib(root, M.get_primary_distn(),
+                    M.get_blink_distn(), pri, tols, primary_to_tol)),
+                ell_dwell=[[list(e), float(d[e])] for e in edges],
+                ell_trans=[[list(e), float(tr[e])] for e in edges],
+                segments_edge0=segs))
+        out['%s/%s' % (M.__name__, D.__name__)] = dict(
+                samples=samples,
+                # gen_samples normalised this graph in place (raoteh.py:101-102); record what
+                # the functionals above actually saw
+                Q_primary=[[int(a), int(b), float(Q_primary[a][b]['weight'])]
+                    for a, b in Q_primary.edges()])
+    with open(os.path.join(GOLDEN, 'ref_ell_contrib.json'), 'w') as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 def make_mg94():
     """MG94 tables from the reference's create_mg94.py, for the packing test."""
     loader.load()
@@ -248,3 +301,5 @@ if __name__ == '__main__':
         make_p53(int(sys.argv[2]))
     elif what == 'mg94':
         make_mg94()
+    elif what == 'ell':
+        make_ell()
