@@ -140,6 +140,13 @@ int nxb_profile(nxb_handle* h, int32_t enable, uint64_t* cycles12);
  * Host buffers: Q[n*n], t[batch], out[batch*n*n]. */
 int nxb_expm_batched(int device, int32_t n, int32_t batch, const double* Q, const double* t,
                      double* out);
+/* expm(Q t_b) and its Frechet derivative in direction E_b,
+ *   L_b = int_0^1 exp(Q t_b s) E_b exp(Q t_b (1 - s)) ds,
+ * for b < batch.  Replaces scipy.linalg.expm_frechet of nxblink/denseutil.py:148-176
+ * (compute_edge_expectation / compute_dwell_times) and toymodel-analytic.py:159-226.
+ * Host buffers: Q[n*n], t[batch], E[batch*n*n], outP[batch*n*n] (may be NULL), outL[batch*n*n]. */
+int nxb_expm_frechet_batched(int device, int32_t n, int32_t batch, const double* Q, const double* t,
+                             const double* E, double* outP, double* outL);
 /* Pruning log-likelihood per site.  Replaces nxmctree.dynamic_fset_lhood.get_lhood,
  * toymodel-analytic.py:123-126.  parent[v] < v, root 0; P[e] is the n x n transition
  * matrix of the edge into node e+1; masks[s*n_nodes+v] bit i: state i feasible at node v

@@ -102,6 +102,95 @@ __global__ void __launch_bounds__(256) expm_kernel(int n, const double* __restri
     for (int i = tid; i < n * n; i += blockDim.x) o[i] = X[(i / n) * ND + (i % n)];
 }
 
+// C (+)= A * B, as matmul64; with ACC the product is added to C.
+template <bool ACC>
+__device__ void matmul64x(const double* A, const double* B, double* C, int warp, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    for (int jt = 0; jt < ND / 8; ++jt) {
+        double* cp = C + (warp * 8 + r) * ND + jt * 8 + 2 * q;
+        double c0 = ACC ? cp[0] : 0.0, c1 = ACC ? cp[1] : 0.0;
+#pragma unroll 4
+        for (int k0 = 0; k0 < ND; k0 += 4) {
+            const double a = A[(warp * 8 + r) * ND + k0 + q];
+            const double b = B[(k0 + q) * ND + jt * 8 + r];
+            dmma(c0, c1, a, b);
+        }
+        cp[0] = c0; cp[1] = c1;
+    }
+}
+
+// One CTA per (matrix, direction): P_b = expm(A) and the Frechet derivative
+//     L_b = int_0^1 exp(A s) E_b exp(A (1 - s)) ds,      A = Q t_b,
+// i.e. the top-right block of expm([[A, E], [0, A]]), computed on the blocks: Horner's rule
+// for the degree-13 Taylor polynomial of the scaled pair (X <- I + A X / k,
+// Xl <- (A Xl + E X) / k), then s squarings (Xl <- X Xl + Xl X, X <- X X).
+// Replaces scipy.linalg.expm_frechet of nxblink/denseutil.py:148-176.
+__global__ void __launch_bounds__(256) frechet_kernel(int n, const double* __restrict__ Q,
+        const double* __restrict__ t, const double* __restrict__ E,
+        double* __restrict__ outP, double* __restrict__ outL) {
+    extern __shared__ __align__(16) double sm[];
+    double* A = sm;                       // Q t / 2^s
+    double* D = sm + ND * ND;             // E / 2^s
+    double* X = sm + 2 * ND * ND;
+    double* Xl = sm + 3 * ND * ND;
+    double* Y = sm + 4 * ND * ND;
+    double* Yl = sm + 5 * ND * ND;
+    __shared__ double s_norm;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double tb = t[blockIdx.x];
+    const double* Eb = E + (size_t)blockIdx.x * n * n;
+    if (tid == 0) s_norm = 0.0;
+    __syncthreads();
+    for (int j = tid; j < n; j += blockDim.x) {
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) acc += fabs(Q[i * n + j]);
+        atomicMax((unsigned long long*)&s_norm, (unsigned long long)__double_as_longlong(acc * fabs(tb)));
+    }
+    __syncthreads();
+    int s = 0;
+    {
+        double nrm = s_norm;
+        while (nrm > 0.5 && s < 60) { nrm *= 0.5; ++s; }
+    }
+    const double scale = ldexp(tb, -s), escale = ldexp(1.0, -s);
+    for (int i = tid; i < ND * ND; i += blockDim.x) {
+        const int r = i / ND, c = i % ND;
+        const bool in = r < n && c < n;
+        A[i] = in ? Q[r * n + c] * scale : 0.0;
+        D[i] = in ? Eb[r * n + c] * escale : 0.0;
+        X[i] = (r == c) ? 1.0 : 0.0;
+        Xl[i] = 0.0;
+    }
+    __syncthreads();
+    for (int k = 13; k >= 1; --k) {
+        matmul64x<false>(A, X, Y, warp, lane);
+        matmul64x<false>(A, Xl, Yl, warp, lane);
+        matmul64x<true>(D, X, Yl, warp, lane);        // each warp re-reads only its own rows of Yl
+        __syncthreads();
+        const double inv = 1.0 / (double)k;
+        for (int i = tid; i < ND * ND; i += blockDim.x) {
+            const int r = i / ND, c = i % ND;
+            X[i] = Y[i] * inv + ((r == c) ? 1.0 : 0.0);
+            Xl[i] = Yl[i] * inv;
+        }
+        __syncthreads();
+    }
+    for (int q = 0; q < s; ++q) {
+        matmul64x<false>(X, Xl, Yl, warp, lane);
+        matmul64x<true>(Xl, X, Yl, warp, lane);
+        matmul64x<false>(X, X, Y, warp, lane);
+        __syncthreads();
+        for (int i = tid; i < ND * ND; i += blockDim.x) { X[i] = Y[i]; Xl[i] = Yl[i]; }
+        __syncthreads();
+    }
+    if (outP) {
+        double* o = outP + (size_t)blockIdx.x * n * n;
+        for (int i = tid; i < n * n; i += blockDim.x) o[i] = X[(i / n) * ND + (i % n)];
+    }
+    double* o = outL + (size_t)blockIdx.x * n * n;
+    for (int i = tid; i < n * n; i += blockDim.x) o[i] = Xl[(i / n) * ND + (i % n)];
+}
+
 // Pruning likelihood.  One CTA (256 threads) per tile of ST sites; the tree recursion runs
 // inside the CTA with node messages [ND states x ST sites] in reusable shared-memory slots
 // (edges in descending index: children before parents; parent[v] < v).  Per edge the
@@ -226,6 +315,32 @@ extern "C" int nxb_expm_batched(int device, int32_t n, int32_t batch, const doub
     DTRY(cudaGetLastError());
     DTRY(cudaMemcpy(out, dout, sizeof(double) * (size_t)batch * n * n, cudaMemcpyDeviceToHost));
     cudaFree(dQ); cudaFree(dt); cudaFree(dout);
+    return NXB_OK;
+}
+
+extern "C" int nxb_expm_frechet_batched(int device, int32_t n, int32_t batch, const double* Q,
+                                        const double* t, const double* E, double* outP, double* outL) {
+    if (n < 1 || n > ND || batch < 1 || !Q || !t || !E || !outL) { g_dense_err = "bad argument (need 1 <= n <= 64)"; return NXB_ERR_BAD_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { g_dense_err = "no CUDA device available (there is no CPU fallback)"; return NXB_ERR_CUDA; }
+    DTRY(cudaSetDevice(device));
+    const size_t mat = sizeof(double) * (size_t)batch * n * n;
+    double *dQ = nullptr, *dt = nullptr, *dE = nullptr, *dP = nullptr, *dL = nullptr;
+    DTRY(cudaMalloc(&dQ, sizeof(double) * n * n));
+    DTRY(cudaMalloc(&dt, sizeof(double) * batch));
+    DTRY(cudaMalloc(&dE, mat));
+    DTRY(cudaMalloc(&dL, mat));
+    if (outP) DTRY(cudaMalloc(&dP, mat));
+    DTRY(cudaMemcpy(dQ, Q, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    DTRY(cudaMemcpy(dt, t, sizeof(double) * batch, cudaMemcpyHostToDevice));
+    DTRY(cudaMemcpy(dE, E, mat, cudaMemcpyHostToDevice));
+    const size_t smem = sizeof(double) * 6 * ND * ND;
+    DTRY(cudaFuncSetAttribute(nxbd::frechet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nxbd::frechet_kernel<<<batch, 256, smem>>>(n, dQ, dt, dE, dP, dL);
+    DTRY(cudaGetLastError());
+    DTRY(cudaMemcpy(outL, dL, mat, cudaMemcpyDeviceToHost));
+    if (outP) DTRY(cudaMemcpy(outP, dP, mat, cudaMemcpyDeviceToHost));
+    cudaFree(dQ); cudaFree(dt); cudaFree(dE); cudaFree(dP); cudaFree(dL);
     return NXB_OK;
 }
 

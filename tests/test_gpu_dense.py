@@ -80,3 +80,49 @@ def test_infeasible_site_is_minus_infinity(nb):
     data = packing.pack_data(cp.pm, [toydata.DataB, Impossible])
     ll = cp.loglik(data)
     assert np.isfinite(ll[0]) and ll[1] == -np.inf
+
+
+def test_expm_frechet_batched_matches_scipy(nb):
+    """nxb_expm_frechet_batched against scipy.linalg.expm_frechet, the numerical authority
+    of nxblink/denseutil.py:148-176 (tolerance 1e-10 relative to the largest entry)."""
+    rng = np.random.RandomState(5)
+    for n, scale in ((5, 1.0), (24, 1.0), (48, 4.0), (64, 0.3)):
+        Q = rng.gamma(1.0, 1.0, size=(n, n)) * (rng.uniform(size=(n, n)) < 0.3)
+        np.fill_diagonal(Q, 0.0)
+        Q -= np.diag(Q.sum(axis=1))
+        t = np.array([0.0, 1e-6, 0.1, 1.0, scale * 3.0])
+        E = rng.randn(len(t), n, n)
+        P, L = dense.expm_frechet_batched(Q, t, E)
+        for b, tb in enumerate(t):
+            Pe, Le = scipy.linalg.expm_frechet(Q * tb, E[b])
+            assert_allclose(P[b], Pe, rtol=1e-10, atol=1e-13)
+            assert_allclose(L[b], Le, rtol=0, atol=1e-10 * np.abs(Le).max())
+        L2 = dense.expm_frechet_batched(Q, t, E, compute_expm=False)
+        assert (L2 == L).all()
+
+
+@pytest.mark.parametrize('D', [toydata.DataA, toydata.DataB, toydata.DataC, toydata.DataD],
+        ids=lambda d: d.__name__)
+@pytest.mark.parametrize('M', [toymodel.BlinkModelA, toymodel.BlinkModelB, toymodel.BlinkModelC],
+        ids=lambda m: m.__name__)
+def test_expected_summary_matches_dense_oracle(nb, M, D):
+    """toymodel-analytic.py:128-226 on the device path (one Frechet derivative per edge)
+    against the restated oracle (one scipy expm_frechet per edge and statistic)."""
+    cp = dense.CompoundProcess(M)
+    data = packing.pack_data(cp.pm, [D])
+    got = cp.expected_summary(data)
+    dp = DensePosterior(M, D)
+    exact = dp.expected_summary()
+    assert_allclose(got['likelihood'], dp.likelihood, rtol=1e-10)
+    for s, v in exact['root_pri_to_count'].items():
+        assert_allclose(got['root_pri_to_count'][s], v, rtol=1e-9, atol=1e-12)
+    for key in ('root_on_total', 'root_off_count', 'root_xon_intended'):
+        assert_allclose(got[key], exact[key], rtol=1e-9, atol=1e-12)
+    for edge in cp.pm.edges:
+        for key in ('edge_to_off_xon_trans', 'edge_to_xon_off_trans', 'edge_to_off_xon_dwell',
+                'edge_to_xon_off_dwell'):
+            assert_allclose(got[key][edge], exact[key][edge], rtol=1e-9, atol=1e-11, err_msg=key)
+        for key in ('edge_to_pri_trans', 'edge_to_pri_dwell'):
+            for sa in exact[key][edge]:
+                for sb, v in exact[key][edge][sa].items():
+                    assert_allclose(got[key][edge][sa][sb], v, rtol=1e-9, atol=1e-11, err_msg=key)
