@@ -121,6 +121,12 @@ int nxb_export_unit(nxb_handle* h, int64_t unit, int32_t* node_pri, uint32_t* no
  * then be summarised (nxb_summarize_current), exported (nxb_export_unit, nxb_read_node_states:
  * synthetic alignments) or swept.  Replaces any data previously set with unconstrained data. */
 int nxb_forward_sample(nxb_handle* h, int64_t n_units, uint64_t seed, int64_t unit_offset);
+/* Same, with the root state of every trajectory given by the caller, as
+ * fwdsample.gen_forward_samples(model, seq_of_track_to_root_state) takes it (fwdsample.py:67,145-160):
+ * root_pri[n_units] state indices, root_tol[n_units] bit masks of the classes that are ON
+ * (the class of the root's primary state is forced ON).  Both NULL: draw roots from the prior. */
+int nxb_forward_sample_rooted(nxb_handle* h, int64_t n_units, uint64_t seed, int64_t unit_offset,
+                              const int32_t* root_pri, const uint32_t* root_tol);
 /* Node states of every unit: node_pri[n_units*N], node_tol[n_units*N] (bit k: class k on). */
 int nxb_read_node_states(nxb_handle* h, int32_t* node_pri, uint32_t* node_tol);
 

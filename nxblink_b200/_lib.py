@@ -64,7 +64,7 @@ EXPORTS = (
     'nxb_summarize_current', 'nxb_export_unit', 'nxb_get_stats',
     'nxb_last_kernel_ms', 'nxb_profile', 'nxb_philox4x32_10',
     'nxb_expm_batched', 'nxb_expm_frechet_batched', 'nxb_pruning_loglik', 'nxb_dense_last_error',
-    'nxb_forward_sample', 'nxb_read_node_states',
+    'nxb_forward_sample', 'nxb_forward_sample_rooted', 'nxb_read_node_states',
 )
 
 _lib = None
@@ -106,6 +106,7 @@ def load():
             C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.nxb_dense_last_error.restype = C.c_char_p
     lib.nxb_forward_sample.argtypes = [H, C.c_int64, C.c_uint64, C.c_int64]
+    lib.nxb_forward_sample_rooted.argtypes = [H, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.nxb_read_node_states.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.nxb_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nxb_philox4x32_10.restype = None

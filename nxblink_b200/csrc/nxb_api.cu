@@ -340,7 +340,8 @@ __global__ void summarize_kernel(const __grid_constant__ NxbSweepParams p) {
 // SURVEY.md component 13).  Root: primary ~ prior, own class ON, other classes ~ blink prior.
 // ---------------------------------------------------------------------------
 __global__ void forward_kernel(const __grid_constant__ NxbSweepParams p, int cap_events,
-                               unsigned short* __restrict__ tmp_code, double* __restrict__ tmp_time) {
+                               unsigned short* __restrict__ tmp_code, double* __restrict__ tmp_time,
+                               const int* __restrict__ root_pri, const unsigned* __restrict__ root_tol) {
     extern __shared__ __align__(16) unsigned char smem[];
     const NxbModelLayout& ml = p.ml;
     for (int i = threadIdx.x * 16; i < ml.bytes; i += blockDim.x * 16)
@@ -385,6 +386,10 @@ __global__ void forward_kernel(const __grid_constant__ NxbSweepParams p, int cap
     unsigned m0 = 0u;
     for (int k = 0; k < K; ++k)
         if (k == cls[s0] || unif() < ml.p_on) m0 |= 1u << k;
+    if (root_pri) {           // caller-given root state (fwdsample.py:145-160)
+        s0 = root_pri[u];
+        m0 = root_tol[u] | (1u << cls[s0]);
+    }
     g_npri[0] = (unsigned char)s0;
     g_tol[0] = m0;
     int nP = 0, nB = 0;
@@ -1275,8 +1280,25 @@ extern "C" int nxb_export_unit(nxb_handle* h, int64_t unit, int32_t* node_pri, u
 }
 
 
+extern "C" int nxb_forward_sample_rooted(nxb_handle* h, int64_t n_units, uint64_t seed, int64_t unit_offset,
+                                         const int32_t* root_pri, const uint32_t* root_tol);
+
 extern "C" int nxb_forward_sample(nxb_handle* h, int64_t n_units, uint64_t seed, int64_t unit_offset) {
+    return nxb_forward_sample_rooted(h, n_units, seed, unit_offset, nullptr, nullptr);
+}
+
+extern "C" int nxb_forward_sample_rooted(nxb_handle* h, int64_t n_units, uint64_t seed, int64_t unit_offset,
+                                         const int32_t* root_pri, const uint32_t* root_tol) {
     if (!h || n_units <= 0 || n_units > 0x7fffffffLL) return set_err(h, NXB_ERR_BAD_ARG, "bad argument");
+    if ((root_pri == nullptr) != (root_tol == nullptr))
+        return set_err(h, NXB_ERR_BAD_ARG, "give both root_pri and root_tol, or neither");
+    if (root_pri)
+        for (int64_t u = 0; u < n_units; ++u) {
+            if (root_pri[u] < 0 || root_pri[u] >= h->ml.P)
+                return set_err(h, NXB_ERR_BAD_ARG, "root primary state out of range");
+            if (h->ml.K < 32 && (root_tol[u] >> h->ml.K))
+                return set_err(h, NXB_ERR_BAD_ARG, "root tolerance mask has bits beyond n_classes");
+        }
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t n = (size_t)n_units * h->ml.N;
     // unconstrained data: one "site" per unit, one chain (so that the units can be swept afterwards)
@@ -1308,13 +1330,20 @@ extern "C" int nxb_forward_sample(nxb_handle* h, int64_t n_units, uint64_t seed,
     p.n_units = n_units; p.unit_offset = unit_offset; p.seed = seed; p.status = h->d_status;
     const int threads = 128;
     cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->ml.bytes);
+    int* d_rpri = nullptr; unsigned* d_rtol = nullptr;
+    if (root_pri) {
+        CUDA_TRY(h, cudaMalloc(&d_rpri, 4 * (size_t)n_units));
+        CUDA_TRY(h, cudaMalloc(&d_rtol, 4 * (size_t)n_units));
+        CUDA_TRY(h, cudaMemcpyAsync(d_rpri, root_pri, 4 * (size_t)n_units, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(d_rtol, root_tol, 4 * (size_t)n_units, cudaMemcpyHostToDevice, h->stream));
+    }
     forward_kernel<<<(unsigned)((n_units + threads - 1) / threads), threads, h->ml.bytes, h->stream>>>(
-        p, cap_events, tmp_code, tmp_time);
+        p, cap_events, tmp_code, tmp_time, d_rpri, d_rtol);
     CUDA_TRY(h, cudaGetLastError());
     int hs[4];
     CUDA_TRY(h, cudaMemcpyAsync(hs, h->d_status, 16, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(tmp_code); cudaFree(tmp_time);
+    cudaFree(tmp_code); cudaFree(tmp_time); cudaFree(d_rpri); cudaFree(d_rtol);
     if (hs[0] != 0) {
         cudaMemsetAsync(h->d_status, 0, 16, h->stream);
         return set_err(h, hs[0], "forward sample outgrew the slab capacity; re-create the handle with a larger cap_scale");

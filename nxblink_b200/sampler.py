@@ -88,10 +88,20 @@ class BlinkSampler(object):
         self.chains = int(chains)
         self.n_units = self.data.n_sites * self.chains
 
-    def forward_sample(self, n_units, seed=0, unit_offset=0):
+    def forward_sample(self, n_units, seed=0, unit_offset=0, root_pri=None, root_tol=None):
         """Prior simulation of ``n_units`` trajectories on the device (fwdsample.py:67-262).
+        ``root_pri`` (state indices) and ``root_tol`` (bit masks of ON classes) fix the root
+        states; by default they are drawn from the stationary prior.
         Returns (node_pri [n, N] state indices, node_tol [n, N] bit masks)."""
-        self._check(self.lib.nxb_forward_sample(self._h, int(n_units), int(seed), int(unit_offset)))
+        if root_pri is None:
+            self._check(self.lib.nxb_forward_sample(self._h, int(n_units), int(seed), int(unit_offset)))
+        else:
+            rp = np.ascontiguousarray(root_pri, dtype=np.int32)
+            rt = np.ascontiguousarray(root_tol, dtype=np.uint32)
+            if rp.shape != (int(n_units),) or rt.shape != (int(n_units),):
+                raise NxbError(5, 'root_pri and root_tol must have one entry per unit')
+            self._check(self.lib.nxb_forward_sample_rooted(self._h, int(n_units), int(seed),
+                    int(unit_offset), rp.ctypes.data, rt.ctypes.data))
         self.chains, self.n_units = 1, int(n_units)
         self.data = None
         node_pri = np.zeros((self.n_units, self.pm.n_nodes), dtype=np.int32)

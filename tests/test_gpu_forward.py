@@ -84,3 +84,69 @@ def test_forward_sampled_alignment_can_be_analysed(nb):
     s.sweep(5, accumulate=True)
     assert s.summary().nsamples == 64 * 4 * 5
     s.close()
+
+
+def test_rooted_forward_samples_follow_the_transition_matrix(nb):
+    """fwdsample.gen_forward_samples takes the root states from the caller: with the root
+    fixed, the joint (primary, tolerance) state at a child of the root is distributed as
+    the row of expm(Q_compound * rate * blen) (scipy.linalg.expm, the reference's authority)."""
+    import scipy.linalg
+    from nxblink_b200 import dense
+    M = toymodel.BlinkModelB
+    cp = dense.CompoundProcess(M)
+    pm = cp.pm
+    n = 60000
+    root_state = (2, (1, 1, 0))                   # primary 2 (class T1) with T0 on, T2 off
+    r = cp.states.index(root_state)
+    s = nb.BlinkSampler(pm)
+    rp = np.full(n, root_state[0], dtype=np.int32)
+    rt = np.full(n, sum(b << k for k, b in enumerate(root_state[1])), dtype=np.uint32)
+    node_pri, node_tol = s.forward_sample(n, seed=9, root_pri=rp, root_tol=rt)
+    s.close()
+    assert (node_pri[:, 0] == root_state[0]).all() and (node_tol[:, 0] == rt[0]).all()
+    idx = dict((c, i) for i, c in enumerate(cp.states))
+    for v in range(1, pm.n_nodes):
+        if pm.parent[v] != 0:
+            continue
+        t = pm.blen[v] * pm.rate[v]
+        exact = scipy.linalg.expm(cp.Q * t)[r]
+        counts = np.zeros(len(cp.states))
+        codes = node_pri[:, v].astype(np.int64) * 8 + node_tol[:, v]
+        for code, c in zip(*np.unique(codes, return_counts=True)):
+            p, m = int(code) // 8, int(code) % 8
+            counts[idx[(p, tuple((m >> k) & 1 for k in range(3)))]] = c
+        freq = counts / n
+        se = np.sqrt(exact * (1 - exact) / n)
+        assert (np.abs(freq - exact) <= 5 * se + 1e-4).all(), (v, freq, exact)
+
+
+def test_gen_forward_samples_facade(nb):
+    from nxblink_b200 import fwdsample
+    M = toymodel.BlinkModelA
+    roots = [{'PRIMARY': 0, 'T0': 1, 'T1': 0, 'T2': 1}, {'PRIMARY': 5, 'T0': 0, 'T1': 0, 'T2': 1},
+            {'PRIMARY': 3, 'T0': 1, 'T1': 1, 'T2': 1}]
+    T, root = M.get_T_and_root()
+    p2t = M.get_primary_to_tol()
+    out = list(fwdsample.gen_forward_samples(M, roots, seed=4))
+    assert len(out) == 3
+    for want, (pri, tols) in zip(roots, out):
+        assert pri.history[root] == want['PRIMARY']
+        for t in tols:
+            assert bool(t.history[root]) == bool(want[t.name])
+        assert set(pri.history) == set(T)
+        # every event is a move the model allows, in time order along its edge
+        for edge in T.edges():
+            state = dict((t.name, bool(t.history[edge[0]])) for t in tols)
+            cur = pri.history[edge[0]]
+            evs = sorted([ev for tr in [pri] + tols for ev in tr.events[edge]], key=lambda e: e.tm)
+            for ev in evs:
+                if ev.track is pri:
+                    assert ev.sa == cur and state[p2t[ev.sb]] and M.get_Q_primary().has_edge(ev.sa, ev.sb)
+                    cur = ev.sb
+                else:
+                    assert bool(ev.sa) == state[ev.track.name] and bool(ev.sb) != bool(ev.sa)
+                    assert ev.sb or ev.track.name != p2t[cur]      # own class never switches off
+                    state[ev.track.name] = bool(ev.sb)
+            assert cur == pri.history[edge[1]]
+    with pytest.raises(Exception):
+        list(fwdsample.gen_forward_samples(M, [{'PRIMARY': 0, 'T0': 0, 'T1': 1, 'T2': 1}]))
