@@ -652,7 +652,7 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     o = scratch0;
     wl->off_ctm = wl->off_cell = wl->off_cedge = 0;            // candidate pool is global
     wl->off_toff = take(4 * (K + 1), 4);
-    wl->off_acc = take(8 * 3 * K * ml.nslots, 8);
+    wl->off_acc = take(4 * 3 * K * ml.nslots, 4);
     wl->off_newtol = take(4 * N, 4);
     // validate_unit needs bord while the persistent state is live; it is only called
     // between phases, when either scratch is dead.

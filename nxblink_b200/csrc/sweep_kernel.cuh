@@ -696,50 +696,67 @@ __device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a :
 #define CE_EDGE 0x3fffu
 #define CE_NEW1 0x4000u     // (survivors only) new state of the surviving event
 
-__device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active) {
-    const NxbSweepParams& p = *c.p;
-    const NxbWarpLayout& wl = p.wl;
-    const NxbModelLayout& ml = p.ml;
-    const int E = c.E, N = c.N, P = c.P, K = c.K, lane = c.lane;
-    const int TCAP = p.gcapC;
-    // one 16-byte record per live event: time, (OFF, ON) message below the event
-    struct __align__(16) LiveEv { double t; float l0, l1; };
-    const SPtr<const NxbEdgeRec> erec = {(unsigned)ml.off_edgerec};
+// one 16-byte record per live event: time, (OFF, ON) message below the event
+struct __align__(16) LiveEv { double t; float l0, l1; };
 
-    // ---- S0 (own warp): index of the primary events, unit header for the lane jobs ----------------
-    phase_sync(c);
-    const SPtr<int> uhdr_own = {c.wbase + wl.off_uhdr};        // [0] active [2] nB [3] unit32 [4] bad [5] sweep [6] accumulate, [8+k] survivors
+// ---- S0 (the warp that owns the unit): index of the primary events, offsets of the retained
+// events per track, and the unit header that the lane jobs of other warps read
+//   uhdr: [0] active [2] nB [3] unit32 [4] bad [5] sweep [6] accumulate, [8 + k] survivors of track k
+__device__ __forceinline__ void blink_setup(Ctx& c, bool accumulate, bool active) {
+    const NxbWarpLayout& wl = c.p->wl;
+    const int N = c.N, K = c.K, lane = c.lane;
+    const SPtr<int> uhdr_own = {c.wbase + wl.off_uhdr};
     const SPtr<unsigned> newtol_own = {c.wbase + wl.off_newtol};
+    const SPtr<int> toff_own = {c.wbase + wl.off_toff};
     if (active) {
         build_poff(c);
         for (int v = lane; v < N; v += 32) newtol_own[v] = 0u;
+        // toff[k] = number of retained events on tracks < k (K <= 32: one scan)
+        if (lane <= K) toff_own[lane] = 0;
+        if (K == 32 && lane == 0) toff_own[32] = 0;
+        __syncwarp();
+        for (int i = lane; i < c.nB; i += 32) atomicAdd(&toff_own[(c.bcode[i] >> 16) & 0xffu], 1);
+        __syncwarp();
+        int total;
+        const int cnt = lane < K ? toff_own[lane] : 0;
+        const int ex = warp_excl_scan(cnt, lane, total);
+        __syncwarp();
+        if (lane < K) toff_own[lane] = ex;
+        if (lane == 0) toff_own[K] = total;
     }
     if (lane == 0) {
         uhdr_own[0] = active ? 1 : 0; uhdr_own[2] = c.nB; uhdr_own[3] = (int)c.unit32; uhdr_own[4] = 0;
         uhdr_own[5] = (int)c.sweep; uhdr_own[6] = accumulate ? 1 : 0;
     }
     __syncwarp();
+}
 
-    // ---- lane jobs.  Lane j of the lockstep group carries track j % K of unit j / K of the group
-    // (any unit resident in this CTA's shared memory), so every lane of the busy warps walks a
-    // track; with lane = track only K of 32 lanes would (20 of 32 at the p53 shape) and the
-    // remaining warps of the group skip the walks altogether.
-    const int GW = c.bar_threads >> 5;                 // 1 when the warps run independently
-    const int n_jobs = GW * K;
-    const int job = c.wing * 32 + lane;
+// ---- lane job: the whole update of ONE tolerance track of ONE unit (upward pass, root draw,
+// downward pass).  Job j works on track j % K of unit j / K of a pool of units resident in this
+// CTA's shared memory (regions ub0 + u * wl.bytes, global scratch gb0 + u * gscratch_stride), so
+// that every lane of the busy warps walks a track; with lane = track only K of 32 lanes would
+// (20 of 32 at the p53 shape).
+__device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned ub0, unsigned char* gb0) {
+    const NxbSweepParams& p = *c.p;
+    const NxbWarpLayout& wl = p.wl;
+    const NxbModelLayout& ml = p.ml;
+    const int E = c.E, P = c.P, K = c.K;
+    const int TCAP = p.gcapC;
+    const SPtr<const NxbEdgeRec> erec = {(unsigned)ml.off_edgerec};
     const bool has_job = job < n_jobs;
     const int ju = has_job ? job / K : 0;
     const int k = has_job ? job - ju * K : 0;
-    const unsigned ub = c.gwbase + (unsigned)(ju * wl.bytes);             // unit ju's shared-memory region
-    unsigned char* const ugb = c.ggbase + (long long)ju * p.gscratch_stride;
+    const unsigned ub = ub0 + (unsigned)(ju * wl.bytes);             // unit ju's shared-memory region
+    unsigned char* const ugb = gb0 + (long long)ju * p.gscratch_stride;
     // live foreground events of this sweep: global (L2-resident) scratch, one fixed region per
     // (unit, track), filled by the upward pass and consumed backwards by the downward pass
     LiveEv* cev = (LiveEv*)(ugb + p.g_off_ctm) + (size_t)k * TCAP;
     unsigned short* cedge = (unsigned short*)(ugb + p.g_off_cedge) + (size_t)k * TCAP;
     const SPtr<int> uhdr = {ub + wl.off_uhdr};
-    const SPtr<double> acc = {ub + wl.off_acc};                 // [slot][K][3]: u0, u1, penalty
+    const SPtr<float> acc = {ub + wl.off_acc};                  // [slot][K][3]: u0, u1, penalty
     const SPtr<unsigned> newtol = {ub + wl.off_newtol};
     const SPtr<int> poff = {ub + wl.off_poff};
+    const SPtr<const int> toff = {ub + wl.off_toff};
     const SPtr<unsigned> u_node_tol = {ub + wl.off_node_tol};
     const SPtr<unsigned char> u_node_pri = {ub + wl.off_node_pri};
     const SPtr<double> u_ptm = {ub + wl.off_ptm};
@@ -747,20 +764,12 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active)
     const SPtr<double> u_btm = {ub + wl.off_btm};
     const SPtr<unsigned> u_bcode = {ub + wl.off_bcode};
     const SPtr<const unsigned> u_tt_ok = {ub + wl.off_dtt}, u_tf_ok = {ub + wl.off_dtf};
-    tick(c, T_B0);
-    phase_sync(c);            // (a named barrier orders shared memory across the group)
 
     const bool trk = has_job && uhdr[0] != 0;
-    const int nB_u = trk ? uhdr[2] : 0;
     const bool accum_u = trk && uhdr[6] != 0;
     // retained events of track k are the contiguous run [olo, ohi) of the (track, edge, time)
-    // sorted list
-    int olo = 0, ohi = 0;
-    for (int i = 0; i < nB_u; ++i) {
-        const int kt = (int)((u_bcode[i] >> 16) & 0xffu);
-        olo += kt < k;
-        ohi += kt <= k;
-    }
+    // sorted list (offsets per track: blink_setup)
+    const int olo = trk ? toff[k] : 0, ohi = trk ? toff[k + 1] : 0;
     int bad = 0;
     // per-track sequential stream: candidate gaps, thinning and backward-sampling decisions
     NxbXo xo;
@@ -804,7 +813,7 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active)
                     u0 = 1.0; u1 = 1.0; pen = 0.0;
                     if (sb_slot >= 0 && ((inited >> sb_slot) & 1u)) {
                         const int ai = (sb_slot * K + k) * 3;
-                        u0 = acc[ai]; u1 = acc[ai + 1]; pen = acc[ai + 2];
+                        u0 = (double)acc[ai]; u1 = (double)acc[ai + 1]; pen = (double)acc[ai + 2];
                     }
                     if (!((u_tt_ok[vb] >> k) & 1u)) u1 = 0.0;
                     if (!((u_tf_ok[vb] >> k) & 1u)) u0 = 0.0;
@@ -835,11 +844,11 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active)
                     // top of the edge: fold into the parent's accumulator (one normalisation)
                     const int ai = (sa_slot * K + k) * 3;
                     double n0 = u0, n1 = u1, np = pen;
-                    if ((inited >> sa_slot) & 1u) { n0 *= acc[ai]; n1 *= acc[ai + 1]; np += acc[ai + 2]; }
+                    if ((inited >> sa_slot) & 1u) { n0 *= (double)acc[ai]; n1 *= (double)acc[ai + 1]; np += (double)acc[ai + 2]; }
                     double m2 = dmax2(n0, n1);
                     if (!(m2 > 0.0)) { bad = 1; m2 = 1.0; }
                     const double r2 = pow2_rescale(m2);
-                    acc[ai] = n0 * r2; acc[ai + 1] = n1 * r2; acc[ai + 2] = np;
+                    acc[ai] = (float)(n0 * r2); acc[ai + 1] = (float)(n1 * r2); acc[ai + 2] = (float)np;
                     inited |= 1u << sa_slot;
                     if (sb_slot >= 0) inited &= ~(1u << sb_slot);
                     --e;
@@ -888,8 +897,8 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active)
     unsigned x = 0u;
     if (trk) {
         const int ai = (c.slot[0] * K + k) * 3;
-        double w1 = acc[ai + 1] * exp(-acc[ai + 2]) * ml.p_on;
-        double w0 = acc[ai] * ml.p_off;
+        double w1 = (double)acc[ai + 1] * exp(-(double)acc[ai + 2]) * ml.p_on;
+        double w0 = (double)acc[ai] * ml.p_off;
         if (!((u_tt_ok[0] >> k) & 1u)) w1 = 0.0;
         if (!((u_tf_ok[0] >> k) & 1u)) w0 = 0.0;
         if (c.cls[u_node_pri[0]] == k) w0 = 0.0;
@@ -974,10 +983,17 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active)
         if (bad) atomicOr(&uhdr[4], bad);
     }
     tick(c, T_B2);
-    phase_sync(c);
+}
 
-    // ---- S3 (own warp): write back the new retained blink events, (track, edge, time) order ------------
-    if (!active) return RC_OK;
+// ---- S3 (the warp that owns the unit): write back the new retained blink events
+__device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
+    const NxbSweepParams& p = *c.p;
+    const NxbWarpLayout& wl = p.wl;
+    const int N = c.N, K = c.K, lane = c.lane;
+    const int TCAP = p.gcapC;
+    const SPtr<int> uhdr_own = {c.wbase + wl.off_uhdr};
+    const SPtr<unsigned> newtol_own = {c.wbase + wl.off_newtol};
+    // (track, edge, time) order
     {
         const int flags = uhdr_own[4];
         if (flags & 2) { fail(c, NXB_ERR_SCRATCH_CAP, 0); return RC_ERROR; }
@@ -1017,6 +1033,21 @@ __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active)
     if (spill) { c.nB = -total; return RC_DEFER; }
     c.nB = total;
     return RC_OK;
+}
+
+
+// TOLERANCE UPDATE of the fused kernel: the warps of a lockstep group set up their own units,
+// then carry the group's (unit, track) jobs, then write their own units back.
+__device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active) {
+    phase_sync(c);
+    blink_setup(c, accumulate, active);
+    tick(c, T_B0);
+    phase_sync(c);            // (a named barrier orders shared memory across the group)
+    const int GW = c.bar_threads >> 5;                 // 1 when the warps run independently
+    blink_job(c, c.wing * 32 + c.lane, GW * c.K, c.gwbase, c.ggbase);
+    phase_sync(c);
+    if (!active) return RC_OK;
+    return blink_finish(c, accumulate);
 }
 
 // ---------------------------------------------------------------------------
