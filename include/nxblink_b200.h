@@ -49,7 +49,9 @@ typedef struct {
     int32_t validate;        /* 1: check trajectory invariants after every phase */
     int32_t max_warps;       /* 0 = auto */
     int32_t lockstep_warps;  /* warps per phase-lockstep group (instruction-cache sharing);
-                                0 = default (10), negative = independent warps */
+                                0 = automatic, negative = independent warps */
+    int32_t split_phases;    /* 0 = default: primary and tolerance updates run as two alternating
+                                kernels; negative = one fused kernel.  Results are identical. */
 } nxb_model_desc;
 
 /* Sizes of the flat statistic buffers (see nxb_summary_read). */

@@ -33,6 +33,7 @@ class ModelDesc(C.Structure):
         ('cap_scale', C.c_double),
         ('validate', C.c_int32), ('max_warps', C.c_int32),
         ('lockstep_warps', C.c_int32),
+        ('split_phases', C.c_int32),
     ]
 
 

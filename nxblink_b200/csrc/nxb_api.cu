@@ -12,27 +12,22 @@
 #include "sweep_kernel.cuh"
 
 #define NXB_MAX_THREADS 640
+#define NXB_BLINK_THREADS 736      /* blink_kernel needs 88 registers: 23 warps */
 
 namespace nxb {
 
 // ---------------------------------------------------------------------------
 // persistent sweep kernel: one CTA per SM, one warp per unit
 // ---------------------------------------------------------------------------
-template <typename MSG>
-__global__ void __launch_bounds__(NXB_MAX_THREADS, 1)
-sweep_kernel(const __grid_constant__ NxbSweepParams p) {
+// model blob -> shared memory, statistic partials zeroed, model-level fields of the context
+__device__ __forceinline__ void cta_prologue(Ctx& c, const NxbSweepParams& p, int tid, int lane) {
     unsigned char* const smem = nxb_smem;
     const NxbModelLayout& ml = p.ml;
-    const NxbWarpLayout& wl = p.wl;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
     for (int i = tid * 16; i < ml.bytes; i += blockDim.x * 16)
         *(uint4*)(smem + i) = *(const uint4*)(p.blob + i);
     unsigned long long* stats = (unsigned long long*)(smem + ml.off_stats);
     for (int i = tid; i < ml.stats_words; i += blockDim.x) stats[i] = 0ull;
     __syncthreads();
-
-    Ctx c;
     c.p = &p;
     c.N = ml.N; c.E = ml.E; c.P = ml.P; c.K = ml.K; c.lane = lane;
     c.parent.off = ml.off_parent;
@@ -59,6 +54,47 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     c.s_root_pri.off = ml.off_stats + 8 * (2 * ml.E);
     c.s_root_misc.off = ml.off_stats + 8 * (2 * ml.E + ml.P);
     c.s_root_on_cls.off = ml.off_stats + 8 * (2 * ml.E + ml.P + 4);
+    c.k0 = (unsigned)(p.seed & 0xffffffffull);
+    c.k1 = (unsigned)(p.seed >> 32);
+    c.t_last = clock64();
+}
+
+// flush the CTA's statistic partials
+__device__ __forceinline__ void cta_epilogue(Ctx& c, const NxbSweepParams& p, int tid) {
+    const NxbModelLayout& ml = p.ml;
+    const NxbSummaryLayout& sl = p.sl;
+    const unsigned long long* stats = (const unsigned long long*)(nxb_smem + ml.off_stats);
+    __syncthreads();
+    // per edge one packed word: low 32 bits off->on transitions, high 32 bits on->off
+    for (int i = tid; i < ml.E; i += blockDim.x) {
+        const unsigned long long w = stats[i];
+        if (w & 0xffffffffull) atomicAdd(p.counts + sl.c_off_on + i, w & 0xffffffffull);
+        if (w >> 32) atomicAdd(p.counts + sl.c_on_off + i, w >> 32);
+    }
+    for (int i = tid; i < ml.P; i += blockDim.x)
+        if (c.s_root_pri[i]) atomicAdd(p.counts + sl.c_root_pri + i, c.s_root_pri[i]);
+    for (int i = tid; i < ml.K; i += blockDim.x)
+        if (c.s_root_on_cls[i]) atomicAdd(p.counts + sl.c_root_on_cls + i, c.s_root_on_cls[i]);
+    if (tid == 0) {
+        if (c.s_root_misc[0]) atomicAdd(p.counts + sl.c_root_on, c.s_root_misc[0]);
+        if (c.s_root_misc[1]) atomicAdd(p.counts + sl.c_root_off, c.s_root_misc[1]);
+        if (c.s_root_misc[2]) atomicAdd(p.counts + sl.c_nsamples, c.s_root_misc[2]);
+    }
+}
+
+// PRIMARY_ONLY: the kernel runs the primary update of one sweep and leaves the tolerance update
+// to blink_kernel (the two alternate, one launch each per sweep); otherwise both are fused and a
+// launch runs every unit up to p.target_sweeps.
+template <typename MSG, bool PRIMARY_ONLY>
+__global__ void __launch_bounds__(NXB_MAX_THREADS, 1)
+sweep_kernel(const __grid_constant__ NxbSweepParams p) {
+    unsigned char* const smem = nxb_smem;
+    const NxbModelLayout& ml = p.ml;
+    const NxbWarpLayout& wl = p.wl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    Ctx c;
+    cta_prologue(c, p, tid, lane);
     c.wbase = (unsigned)(p.smem_warp0 + warp * wl.bytes);
     c.gbase = p.gscratch + ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * p.gscratch_stride;
     c.node_tol.off = c.wbase + wl.off_node_tol;
@@ -76,11 +112,8 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     unsigned* d_tt = sm_ptr<unsigned>(c.wbase + wl.off_dtt);
     unsigned* d_tf = sm_ptr<unsigned>(c.wbase + wl.off_dtf);
     c.pri_ok.off = c.wbase + wl.off_dpri; c.tt_ok.off = c.wbase + wl.off_dtt; c.tf_ok.off = c.wbase + wl.off_dtf;
-    c.k0 = (unsigned)(p.seed & 0xffffffffull);
-    c.k1 = (unsigned)(p.seed >> 32);
     const int N = ml.N;
     const long long n_work = p.unit_list ? (long long)p.n_list : p.n_units;
-    c.t_last = clock64();
     // Lockstep groups: GW consecutive warps take a batch of GW units and run every sub-phase
     // together (named barrier per group).  GW == 1: independent warps (deferral tiers).
     const int GW = p.group_warps > 1 ? p.group_warps : 1;
@@ -94,6 +127,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     c.nbar = 0;
     unsigned long long* s_batch = (unsigned long long*)(smem + ml.off_stats) + ml.stats_words;
     const unsigned n_steps = p.init ? 1u : (p.target_sweeps - p.begin_sweeps);
+    const unsigned n_iter = PRIMARY_ONLY ? (p.validate_only ? 0u : 1u) : 2u * n_steps;   // phases per unit and launch
 
     while (true) {
         unsigned long long widx = 0;
@@ -122,7 +156,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             slab = p.state + u * p.state_stride;
             hdr = *(const NxbUnitHeader*)slab;
             if (p.init) { hdr.sweeps_done = 0; hdr.n_pri = 0; hdr.n_blk = 0; hdr.phase = NXB_PHASE_INIT; hdr.pad = 0; }
-            const bool off_schedule = lockstep && !p.init &&
+            const bool off_schedule = (lockstep || PRIMARY_ONLY) && !p.init &&
                 (hdr.phase != NXB_PHASE_PRIMARY || hdr.sweeps_done != p.begin_sweeps);
             if ((int)hdr.n_pri > wl.capP || (int)hdr.n_blk > wl.capB || off_schedule) {
                 // does not fit this tier's shared-memory arrays: untouched, next tier
@@ -154,6 +188,8 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             }
             __syncwarp();
         }
+        // split mode: the tolerance update ran in another kernel; check its result on arrival
+        if (PRIMARY_ONLY && p.validate && has && hdr.phase != NXB_PHASE_INIT) rc = validate_unit(c);
         tick(c, T_LOAD);
         bool spilled = false;
         // One phase per iteration, so that every phase function has a single call site.  In
@@ -163,14 +199,15 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
         while (true) {
             bool active = has && rc == RC_OK && !spilled;
             const bool more = hdr.phase == NXB_PHASE_INIT || hdr.sweeps_done < p.target_sweeps;
-            if (lockstep) { if (step >= 2 * n_steps) break; }
+            if (lockstep || PRIMARY_ONLY) { if (step >= n_iter) break; }
             else if (!(active && more)) break;
             active = active && more;
             const bool init = hdr.phase == NXB_PHASE_INIT;
-            const bool blink_turn = lockstep ? ((step & 1u) != 0u && !p.init) : (hdr.phase == NXB_PHASE_BLINK);
+            const bool blink_turn = PRIMARY_ONLY ? false
+                : (lockstep ? ((step & 1u) != 0u && !p.init) : (hdr.phase == NXB_PHASE_BLINK));
             ++step;
             if (lockstep && p.init && (step & 1u) == 0u) continue;     // init: one primary pass only
-            if (lockstep && active && blink_turn != (hdr.phase == NXB_PHASE_BLINK)) active = false;
+            if ((lockstep || PRIMARY_ONLY) && active && blink_turn != (hdr.phase == NXB_PHASE_BLINK)) active = false;
             c.sweep = init ? NXB_SWEEP_INIT : hdr.sweeps_done;
             const bool accum = !init && hdr.sweeps_done >= p.accum_from;
             c.nbar = 0;
@@ -183,7 +220,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
                     if (rc == RC_OK) hdr.phase = init ? NXB_PHASE_PRIMARY : NXB_PHASE_BLINK;
                 }
                 phase_drain(c, NXB_NBAR_PRIMARY);
-            } else {
+            } else if (!PRIMARY_ONLY) {
                 // every warp of a lockstep group takes part: its lanes carry tracks of other units
                 if (active || lockstep) {
                     const int brc = blink_phase(c, accum, active);
@@ -200,7 +237,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             if (p.validate && active && rc == RC_OK) rc = validate_unit(c);
         }
         // ---- store the unit ----
-        if (has && rc != RC_ERROR) {
+        if (has && rc != RC_ERROR && !(PRIMARY_ONLY && p.validate_only)) {
             if (c.nP > p.gcapP || (!spilled && c.nB > p.gcapB)) {
                 fail(c, NXB_ERR_STATE_CAP, c.nP > p.gcapP ? c.nP : c.nB);
             } else {
@@ -228,24 +265,134 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
         }
         tick(c, T_STORE);
     }
-    __syncthreads();
-    // ---- flush the CTA's statistic partials ----
-    const NxbSummaryLayout& sl = p.sl;
-    // per edge one packed word: low 32 bits off->on transitions, high 32 bits on->off
-    for (int i = tid; i < ml.E; i += blockDim.x) {
-        const unsigned long long w = stats[i];
-        if (w & 0xffffffffull) atomicAdd(p.counts + sl.c_off_on + i, w & 0xffffffffull);
-        if (w >> 32) atomicAdd(p.counts + sl.c_on_off + i, w >> 32);
+    cta_epilogue(c, p, tid);
+}
+
+// ---------------------------------------------------------------------------
+// TOLERANCE UPDATE as its own kernel (split mode).  A CTA takes batches of U = p.batch_units
+// units (U * K <= 32 * warps) into shared memory: the warps set the units up (blink_setup),
+// every lane of the CTA then carries one (unit, track) job (blink_job), and the warps write the
+// units back (blink_finish).  Units are in phase BLINK at sweep p.begin_sweeps when it starts
+// (the primary-only sweep_kernel ran just before) and in phase PRIMARY of the next sweep after.
+// Units that are elsewhere are skipped (the primary launch listed them for the next tier);
+// units whose events do not fit the shared-memory capacities are listed here.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NXB_BLINK_THREADS, 1)
+blink_kernel(const __grid_constant__ NxbSweepParams p) {
+    const NxbModelLayout& ml = p.ml;
+    const NxbWarpLayout& wl = p.wl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    Ctx c;
+    cta_prologue(c, p, tid, lane);
+    c.bar_id = 1; c.bar_threads = 32; c.nbar = 0; c.sync_mask = 0u;     // phase_sync: no-op
+    c.wing = warp; c.gwbase = (unsigned)p.smem_warp0;
+    const int N = ml.N, K = ml.K, U = p.batch_units;
+    unsigned char* const gb0 = p.gscratch + (long long)blockIdx.x * U * p.gscratch_stride;
+    c.ggbase = gb0;
+    const long long n_work = p.unit_list ? (long long)p.n_list : p.n_units;
+    unsigned long long* s_batch = (unsigned long long*)(nxb_smem + ml.off_stats) + ml.stats_words;
+    auto bind = [&](int ui) {
+        c.wbase = (unsigned)(p.smem_warp0 + ui * wl.bytes);
+        c.gbase = gb0 + (long long)ui * p.gscratch_stride;
+        c.node_tol.off = c.wbase + wl.off_node_tol;
+        c.node_pri.off = c.wbase + wl.off_node_pri;
+        c.ptm.off = c.wbase + wl.off_ptm;
+        c.pcode.off = c.wbase + wl.off_pcode;
+        c.btm.off = c.wbase + wl.off_btm;
+        c.bcode.off = c.wbase + wl.off_bcode;
+        c.poff.off = c.wbase + wl.off_poff;
+        c.tmpa.off = c.wbase + wl.off_tmpa;
+        c.tt_ok.off = c.wbase + wl.off_dtt; c.tf_ok.off = c.wbase + wl.off_dtf;
+    };
+    while (true) {
+        if (tid == 0) s_batch[0] = atomicAdd(p.work_counter, 1ull);
+        __syncthreads();
+        const long long w0 = (long long)s_batch[0] * U;
+        __syncthreads();
+        if (w0 >= n_work) break;
+        // ---- load + set up the units of the batch ----
+        for (int ui = warp; ui < U; ui += W) {
+            bind(ui);
+            const long long widx = w0 + ui;
+            bool active = false, accum = false;
+            SPtr<int> uhdr = {c.wbase + wl.off_uhdr};
+            c.nP = 0; c.nB = 0; c.unit = 0; c.unit32 = 0u; c.sweep = 0u;
+            if (widx < n_work) {
+                const long long u = p.unit_list ? (long long)p.unit_list[widx] : widx;
+                const unsigned char* slab = p.state + u * p.state_stride;
+                const NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;
+                if (hdr.phase == NXB_PHASE_BLINK && hdr.sweeps_done == p.begin_sweeps) {
+                    if ((int)hdr.n_pri > wl.capP || (int)hdr.n_blk > wl.capB) {
+                        if (lane == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)u;
+                    } else {
+                        active = true;
+                        c.unit = u; c.unit32 = (unsigned)(p.unit_offset + u);
+                        c.nP = hdr.n_pri; c.nB = hdr.n_blk; c.sweep = hdr.sweeps_done;
+                        accum = hdr.sweeps_done >= p.accum_from;
+                        const long long site = u / p.chains;
+                        const unsigned* g_tt = p.tol_true_ok + site * N;
+                        const unsigned* g_tf = p.tol_false_ok + site * N;
+                        unsigned* d_tt = sm_ptr<unsigned>(c.wbase + wl.off_dtt);
+                        unsigned* d_tf = sm_ptr<unsigned>(c.wbase + wl.off_dtf);
+                        const unsigned* g_tol = (const unsigned*)(slab + p.so_tol);
+                        const unsigned* g_npri = (const unsigned*)(slab + p.so_pri);
+                        for (int v = lane; v < N; v += 32) {
+                            d_tt[v] = g_tt[v]; d_tf[v] = g_tf[v];
+                            c.node_tol[v] = __ldcs(g_tol + v);
+                        }
+                        for (int v = lane; v < (N + 3) / 4; v += 32) sm_ptr<unsigned>(c.node_pri.off)[v] = __ldcs(g_npri + v);
+                        const double* g_ptm = (const double*)(slab + p.so_ptm);
+                        const unsigned* g_pcode = (const unsigned*)(slab + p.so_pcode);
+                        for (int i = lane; i < c.nP; i += 32) { c.ptm[i] = __ldcs(g_ptm + i); c.pcode[i] = __ldcs(g_pcode + i); }
+                        const double* g_btm = (const double*)(slab + p.so_btm);
+                        const unsigned* g_bcode = (const unsigned*)(slab + p.so_bcode);
+                        for (int i = lane; i < c.nB; i += 32) { c.btm[i] = __ldcs(g_btm + i); c.bcode[i] = __ldcs(g_bcode + i); }
+                        __syncwarp();
+                    }
+                }
+            }
+            tick(c, T_LOAD);
+            blink_setup(c, accum, active);
+            if (lane == 0) uhdr[7] = (int)c.unit;
+            tick(c, T_B0);
+        }
+        __syncthreads();
+        // ---- one (unit, track) job per lane ----
+        blink_job(c, tid, U * K, (unsigned)p.smem_warp0, gb0);
+        __syncthreads();
+        tick(c, T_BW);          // (waiting for the slowest lane of the CTA is booked here)
+        // ---- write the units back ----
+        for (int ui = warp; ui < U; ui += W) {
+            bind(ui);
+            SPtr<int> uhdr = {c.wbase + wl.off_uhdr};
+            if (!uhdr[0]) continue;
+            c.nB = uhdr[2]; c.unit32 = (unsigned)uhdr[3]; c.sweep = (unsigned)uhdr[5];
+            c.unit = (long long)uhdr[7];
+            const bool accum = uhdr[6] != 0;
+            unsigned char* slab = p.state + c.unit * p.state_stride;
+            int rc = blink_finish(c, accum);
+            tick(c, T_BW);
+            if (rc == RC_ERROR) continue;
+            const bool spilled = (rc == RC_DEFER);
+            if (!spilled && c.nB > p.gcapB) { fail(c, NXB_ERR_STATE_CAP, c.nB); continue; }
+            NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;
+            hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
+            hdr.n_blk = (uint16_t)(spilled ? -c.nB : c.nB);
+            __syncwarp();
+            if (lane == 0) *(NxbUnitHeader*)slab = hdr;
+            unsigned* g_tol = (unsigned*)(slab + p.so_tol);
+            for (int v = lane; v < N; v += 32) __stcs(g_tol + v, c.node_tol[v]);
+            if (!spilled) {
+                double* g_btm = (double*)(slab + p.so_btm);
+                unsigned* g_bcode = (unsigned*)(slab + p.so_bcode);
+                for (int i = lane; i < c.nB; i += 32) { __stcs(g_btm + i, c.btm[i]); __stcs(g_bcode + i, c.bcode[i]); }
+            }
+            __syncwarp();
+            tick(c, T_STORE);
+        }
+        __syncthreads();
     }
-    for (int i = tid; i < ml.P; i += blockDim.x)
-        if (c.s_root_pri[i]) atomicAdd(p.counts + sl.c_root_pri + i, c.s_root_pri[i]);
-    for (int i = tid; i < ml.K; i += blockDim.x)
-        if (c.s_root_on_cls[i]) atomicAdd(p.counts + sl.c_root_on_cls + i, c.s_root_on_cls[i]);
-    if (tid == 0) {
-        if (c.s_root_misc[0]) atomicAdd(p.counts + sl.c_root_on, c.s_root_misc[0]);
-        if (c.s_root_misc[1]) atomicAdd(p.counts + sl.c_root_off, c.s_root_misc[1]);
-        if (c.s_root_misc[2]) atomicAdd(p.counts + sl.c_nsamples, c.s_root_misc[2]);
-    }
+    cta_epilogue(c, p, tid);
 }
 
 // ---------------------------------------------------------------------------
@@ -542,6 +689,10 @@ struct Tier {
     int warps;
     int smem_warp0;
     size_t smem;
+    // split mode (tier 0 only): shared-memory layout of one unit in blink_kernel
+    NxbWarpLayout bwl;
+    int blink_warps = 0, blink_units = 0;
+    size_t blink_smem = 0;
 };
 
 struct nxb_handle {
@@ -560,6 +711,7 @@ struct nxb_handle {
     int g_off_msg = 0, g_off_ctm = 0, g_off_cell = 0, g_off_cedge = 0, gcapF = 0, gcapC = 0;
     int profile = 0;
     int lockstep = 0;              // warps per lockstep group in tier 0 (0: independent warps)
+    bool split = true;             // tier 0: primary and tolerance updates as alternating kernels
     unsigned sync_mask = 0x3ffu;
     int gcapP = 0, gcapB = 0;
     int so_tol = 0, so_pri = 0, so_ptm = 0, so_pcode = 0, so_btm = 0, so_bcode = 0;
@@ -674,6 +826,31 @@ static int group_warps_for(const nxb_handle* h, int warps) {
     return best;
 }
 
+// One unit of blink_kernel: the trajectory, the tolerance data, the index arrays of the
+// tolerance update and its accumulators -- none of the primary update's scratch.
+static void build_blink_layout(const NxbModelLayout& ml, int capP, int capB, NxbWarpLayout* wl) {
+    const int N = ml.N, E = ml.E, K = ml.K;
+    memset(wl, 0, sizeof(*wl));
+    int o = 0;
+    auto take = [&](int bytes, int al) { o = align_up(o, al); int r = o; o += bytes; return r; };
+    wl->capP = capP; wl->capB = capB;
+    wl->off_ptm = take(8 * capP, 8);
+    wl->off_btm = take(8 * capB, 8);
+    wl->off_node_tol = take(4 * N, 4);
+    wl->off_node_pri = take(align_up(N, 4), 4);
+    wl->off_pcode = take(4 * capP, 4);
+    wl->off_bcode = take(4 * capB, 4);
+    wl->off_dtt = take(4 * N, 4);
+    wl->off_dtf = take(4 * N, 4);
+    wl->off_poff = take(4 * (E + 1), 4);
+    wl->off_tmpa = take(4 * (E + 1), 4);
+    wl->off_uhdr = take(4 * (8 + 32), 4);
+    wl->off_toff = take(4 * (K + 1), 4);
+    wl->off_acc = take(4 * 3 * K * ml.nslots, 4);
+    wl->off_newtol = take(4 * N, 4);
+    wl->bytes = align_up(o, 16);
+}
+
 extern "C" int nxb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -728,6 +905,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     if (getenv("NXB_SYNC_MASK")) h->sync_mask = (unsigned)strtoul(getenv("NXB_SYNC_MASK"), nullptr, 0);
     // default: one group of up to 20 warps (measured best at the p53 shape); negative switches it off
     h->lockstep = d->lockstep_warps == 0 ? -1 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);   // -1: automatic
+    h->split = d->split_phases >= 0;
 #define CUDA_TRY_C(call)                                                                  \
     do {                                                                                  \
         cudaError_t e_ = (call);                                                          \
@@ -1002,6 +1180,24 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
                 if (w < 1) break;
                 tier.warps = std::min(w, max_warps);
                 tier.smem = (size_t)fixed + (size_t)tier.warps * tier.wl.bytes;
+                if (pass == 0 && t == 0) {
+                    build_blink_layout(ml, tier.wl.capP, tier.wl.capB, &tier.bwl);
+                    const int fit = (h->max_smem - fixed) / tier.bwl.bytes;
+                    int bw = (d->max_warps > 0) ? std::min(d->max_warps, NXB_BLINK_THREADS / 32)
+                                                : NXB_BLINK_THREADS / 32;
+                    if (const char* ev = getenv("NXB_BLINK_WARPS")) bw = std::max(1, std::min(atoi(ev), NXB_BLINK_THREADS / 32));
+                    // one (unit, track) job per lane of the CTA
+                    int bu = std::min(fit, (32 * bw) / K);
+                    // prefer a batch whose jobs fill whole warps (p53: 32 units x 20 tracks = 20 warps;
+                    // measured 14.9 M unit-sweeps/s against 14.1-14.6 M with 21-23 ragged warps)
+                    for (int cand = bu; cand >= 1 && 4 * cand >= 3 * bu; --cand)
+                        if ((cand * K) % 32 == 0) { bu = cand; break; }
+                    if (bu >= 1) {
+                        tier.blink_units = bu;
+                        tier.blink_warps = std::min(bw, (bu * K + 31) / 32);
+                        tier.blink_smem = (size_t)fixed + (size_t)bu * tier.bwl.bytes;
+                    }
+                }
                 (pass == 0 ? h->tiers : h->init_tiers).push_back(tier);
             }
         }
@@ -1014,6 +1210,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             int max_w = 1;
             for (auto& t : h->tiers) max_w = std::max(max_w, t.warps);
             for (auto& t : h->init_tiers) max_w = std::max(max_w, t.warps);
+            max_w = std::max(max_w, h->tiers[0].blink_units);
             h->gcapF = std::max(8 * capF, E * d->diameter + 8);
             // live events per track and sweep: retained + accepted candidates
             {
@@ -1042,13 +1239,16 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         h->so_bcode = o; o += 4 * h->gcapB;
         h->stride = align_up(o, 16);
     }
-    for (auto& t : h->tiers) {
+    {
         cudaError_t e1 = h->msg_f64
-            ? cudaFuncSetAttribute(sweep_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
-            : cudaFuncSetAttribute(sweep_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
-        (void)t;
+            ? cudaFuncSetAttribute(sweep_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
+            : cudaFuncSetAttribute(sweep_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+        if (e1 == cudaSuccess) e1 = h->msg_f64
+            ? cudaFuncSetAttribute(sweep_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
+            : cudaFuncSetAttribute(sweep_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+        if (e1 == cudaSuccess)
+            e1 = cudaFuncSetAttribute(blink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
         if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }
-        break;
     }
     cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
     *out = h;
@@ -1100,72 +1300,131 @@ static const char* status_text(int code) {
     }
 }
 
-// Run every unit up to `target` sweeps, escalating overflowing units through the tiers.
-static int run_tiers(nxb_handle* h, unsigned target, unsigned accum_from, int init) {
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    const int* list = nullptr;
-    int n_list = 0;
-    h->last_ms = 0.f; h->last_launches = 0;
-    const std::vector<Tier>& tiers = init ? h->init_tiers : h->tiers;
-    for (size_t t = 0; t < tiers.size(); ++t) {
-        const Tier& tier = tiers[t];
-        NxbSweepParams p;
-        memset(&p, 0, sizeof(p));
-        p.ml = h->ml; p.wl = tier.wl; p.sl = h->sl;
-        p.smem_warp0 = tier.smem_warp0;
-        p.blob = h->d_blob; p.rmax_tab = h->d_rmax;
-        p.pri_ok = h->d_pri_ok; p.tol_true_ok = h->d_tt; p.tol_false_ok = h->d_tf;
-        p.state = h->d_state; p.state_stride = h->stride;
-        p.gcapP = h->gcapP; p.gcapB = h->gcapB;
-        p.so_tol = h->so_tol; p.so_pri = h->so_pri; p.so_ptm = h->so_ptm; p.so_pcode = h->so_pcode;
-        p.so_btm = h->so_btm; p.so_bcode = h->so_bcode;
-        p.n_units = h->n_units; p.unit_offset = h->unit_offset; p.chains = h->chains;
-        p.unit_list = list; p.n_list = n_list;
-        p.defer_list = h->d_defer[t & 1]; p.defer_count = h->d_defer_count;
-        p.seed = h->seed; p.target_sweeps = target; p.accum_from = accum_from;
-        p.init = (init && t == 0) ? 1 : 0;
-        p.group_warps = (t == 0) ? group_warps_for(h, tier.warps) : 1;
-        p.begin_sweeps = h->sweeps;
-        p.sync_mask = h->sync_mask;
-        p.validate = h->validate;
-        p.counts = h->d_counts; p.dwell = h->d_dwell; p.status = h->d_status;
-        p.work_counter = h->d_work;
-        p.perf = h->profile ? h->d_perf : nullptr;
-        p.gscratch = h->d_gscratch; p.gscratch_stride = h->gscratch_stride;
-        p.g_off_msg = h->g_off_msg; p.g_off_ctm = h->g_off_ctm; p.g_off_cell = h->g_off_cell;
-        p.g_off_cedge = h->g_off_cedge; p.gcapF = h->gcapF; p.gcapC = h->gcapC;
-        CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
-        CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
-        const long long n_work = list ? n_list : h->n_units;
-        const int gw = p.group_warps;
+enum { KIND_FUSED = 0, KIND_PRIMARY = 1, KIND_BLINK = 2, KIND_CHECK = 3 };
+
+// One kernel launch over `list` (or every unit): fills the defer list `out` (appending when
+// `append`), adds the kernel time, returns the number of listed units through *n_deferred.
+static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps, const int* list, int n_list,
+                      int* out, bool append, unsigned begin, unsigned target, unsigned accum_from, int init,
+                      int* n_deferred) {
+    NxbSweepParams p;
+    memset(&p, 0, sizeof(p));
+    p.ml = h->ml; p.wl = (kind == KIND_BLINK) ? tier.bwl : tier.wl; p.sl = h->sl;
+    p.smem_warp0 = tier.smem_warp0;
+    p.blob = h->d_blob; p.rmax_tab = h->d_rmax;
+    p.pri_ok = h->d_pri_ok; p.tol_true_ok = h->d_tt; p.tol_false_ok = h->d_tf;
+    p.state = h->d_state; p.state_stride = h->stride;
+    p.gcapP = h->gcapP; p.gcapB = h->gcapB;
+    p.so_tol = h->so_tol; p.so_pri = h->so_pri; p.so_ptm = h->so_ptm; p.so_pcode = h->so_pcode;
+    p.so_btm = h->so_btm; p.so_bcode = h->so_bcode;
+    p.n_units = h->n_units; p.unit_offset = h->unit_offset; p.chains = h->chains;
+    p.unit_list = list; p.n_list = n_list;
+    p.defer_list = out; p.defer_count = h->d_defer_count;
+    p.seed = h->seed; p.target_sweeps = target; p.accum_from = accum_from;
+    p.init = init;
+    p.group_warps = group_warps;
+    p.begin_sweeps = begin;
+    p.sync_mask = h->sync_mask;
+    p.validate = h->validate;
+    p.validate_only = (kind == KIND_CHECK) ? 1 : 0;
+    p.batch_units = tier.blink_units;
+    p.counts = h->d_counts; p.dwell = h->d_dwell; p.status = h->d_status;
+    p.work_counter = h->d_work;
+    p.perf = h->profile ? h->d_perf : nullptr;
+    p.gscratch = h->d_gscratch; p.gscratch_stride = h->gscratch_stride;
+    p.g_off_msg = h->g_off_msg; p.g_off_ctm = h->g_off_ctm; p.g_off_cell = h->g_off_cell;
+    p.g_off_cedge = h->g_off_cedge; p.gcapF = h->gcapF; p.gcapC = h->gcapC;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
+    if (!append) CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
+    const long long n_work = list ? n_list : h->n_units;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    if (kind == KIND_BLINK) {
+        int grid = (int)std::min<long long>(h->num_sms, (n_work + tier.blink_units - 1) / tier.blink_units);
+        blink_kernel<<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
+    } else {
+        const int gw = std::max(group_warps, 1);
         const int launch_warps = tier.warps / gw * gw;       // whole groups only
         int grid = (int)std::min<long long>(h->num_sms, (n_work + launch_warps - 1) / launch_warps);
         grid = std::max(grid, 1);
-        CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-        if (h->msg_f64) sweep_kernel<double><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
-        else sweep_kernel<float><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
-        CUDA_TRY(h, cudaGetLastError());
-        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
-        int hs[5];
-        CUDA_TRY(h, cudaMemcpyAsync(hs, h->d_status, 16, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(h, cudaMemcpyAsync(hs + 4, h->d_defer_count, 4, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-        h->last_ms += ms; h->last_launches++; h->launches_total++;
-        if (hs[0] != 0) {
-            char buf[256];
-            snprintf(buf, sizeof(buf), "%s (code %d, unit %d, detail %d, sweep %d)", status_text(hs[0]),
-                     hs[0], hs[1], hs[2], hs[3]);
-            cudaMemsetAsync(h->d_status, 0, 16, h->stream);
-            return set_err(h, hs[0], buf);
+        if (kind == KIND_FUSED) {
+            if (h->msg_f64) sweep_kernel<double, false><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
+            else sweep_kernel<float, false><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
+        } else {
+            if (h->msg_f64) sweep_kernel<double, true><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
+            else sweep_kernel<float, true><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
         }
-        if (hs[4] == 0) return NXB_OK;
-        h->deferred_total += hs[4];
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    int hs[5];
+    CUDA_TRY(h, cudaMemcpyAsync(hs, h->d_status, 16, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(hs + 4, h->d_defer_count, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->last_ms += ms; h->last_launches++; h->launches_total++;
+    if (hs[0] != 0) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s (code %d, unit %d, detail %d, sweep %d)", status_text(hs[0]),
+                 hs[0], hs[1], hs[2], hs[3]);
+        cudaMemsetAsync(h->d_status, 0, 16, h->stream);
+        return set_err(h, hs[0], buf);
+    }
+    *n_deferred = hs[4];
+    return NXB_OK;
+}
+
+// Run the units of `list` (all units when null) up to `target` sweeps with the fused kernel,
+// escalating overflowing units through the tiers from `first_tier` on.
+static int run_tiers(nxb_handle* h, unsigned target, unsigned accum_from, int init,
+                     size_t first_tier = 0, const int* list = nullptr, int n_list = 0) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const std::vector<Tier>& tiers = init ? h->init_tiers : h->tiers;
+    for (size_t t = first_tier; t < tiers.size(); ++t) {
+        const Tier& tier = tiers[t];
+        int nd = 0;
+        const int gw = (t == 0) ? group_warps_for(h, tier.warps) : 1;
+        int rc = launch_one(h, KIND_FUSED, tier, gw, list, n_list, h->d_defer[t & 1], false, h->sweeps, target,
+                            accum_from, (init && t == 0) ? 1 : 0, &nd);
+        if (rc) return rc;
+        if (nd == 0) return NXB_OK;
+        h->deferred_total += nd;
         list = h->d_defer[t & 1];
-        n_list = hs[4];
+        n_list = nd;
     }
     return set_err(h, NXB_ERR_SCRATCH_CAP, status_text(NXB_ERR_SCRATCH_CAP));
+}
+
+// Split mode: per sweep one primary-only launch and one blink_kernel launch over all units;
+// whatever they could not take (events beyond the shared-memory capacities) is finished by
+// the fused kernel of the next tiers before the following sweep starts.
+static int run_split(nxb_handle* h, unsigned target, unsigned accum_from) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const Tier& t0 = h->tiers[0];
+    // the primary-only kernel keeps every warp busy in every sub-phase: larger groups
+    const int gw = (h->lockstep < 0 && t0.warps >= 8) ? (t0.warps % 10 == 0 ? 10 : t0.warps / 2) : group_warps_for(h, t0.warps);
+    while (h->sweeps < target) {
+        int nd = 0;
+        int rc = launch_one(h, KIND_PRIMARY, t0, gw, nullptr, 0, h->d_defer[0], false, h->sweeps, h->sweeps + 1,
+                            accum_from, 0, &nd);
+        if (rc) return rc;
+        rc = launch_one(h, KIND_BLINK, t0, 1, nullptr, 0, h->d_defer[0], true, h->sweeps, h->sweeps + 1,
+                        accum_from, 0, &nd);
+        if (rc) return rc;
+        if (nd > 0) {
+            h->deferred_total += nd;
+            rc = run_tiers(h, h->sweeps + 1, accum_from, 0, 1, h->d_defer[0], nd);
+            if (rc) return rc;
+        }
+        h->sweeps++;
+    }
+    if (h->validate) {          // the last tolerance update has not been looked at yet
+        int nd = 0;
+        int rc = launch_one(h, KIND_CHECK, t0, gw, nullptr, 0, h->d_defer[0], false, h->sweeps, h->sweeps,
+                            accum_from, 0, &nd);
+        if (rc) return rc;
+    }
+    return NXB_OK;
 }
 
 extern "C" int nxb_init_chains(nxb_handle* h, int32_t chains, uint64_t seed, int64_t unit_offset) {
@@ -1183,6 +1442,7 @@ extern "C" int nxb_init_chains(nxb_handle* h, int32_t chains, uint64_t seed, int
     }
     h->n_units = n_units; h->chains = chains; h->seed = seed; h->unit_offset = unit_offset;
     h->sweeps = 0;
+    h->last_ms = 0.f; h->last_launches = 0;
     return run_tiers(h, 0u, 0xffffffffu, 1);
 }
 
@@ -1191,7 +1451,10 @@ extern "C" int nxb_sweep(nxb_handle* h, int32_t n_sweeps, int32_t accumulate) {
     if (!h->d_state) return set_err(h, NXB_ERR_BAD_ARG, "call nxb_init_chains first");
     if (n_sweeps == 0) return NXB_OK;
     const unsigned target = h->sweeps + (unsigned)n_sweeps;
-    int rc = run_tiers(h, target, accumulate ? h->sweeps : 0xffffffffu, 0);
+    const unsigned accum_from = accumulate ? h->sweeps : 0xffffffffu;
+    h->last_ms = 0.f; h->last_launches = 0;
+    if (h->split && h->tiers[0].blink_units > 0) return run_split(h, target, accum_from);
+    int rc = run_tiers(h, target, accum_from, 0);
     if (rc == NXB_OK) h->sweeps = target;
     return rc;
 }

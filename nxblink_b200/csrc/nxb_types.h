@@ -150,6 +150,8 @@ struct NxbSweepParams {
     unsigned sync_mask;                 // lockstep: bits 0-5 primary sync points, 6-9 blink sync points
     unsigned begin_sweeps;              // lockstep: every unit starts the launch at this sweep count
     int validate;                       // 1: check trajectory invariants after every phase
+    int validate_only;                  // primary-only kernel: load, check, do nothing else
+    int batch_units;                    // blink_kernel: units per CTA batch
     unsigned long long* counts;
     double* dwell;
     int* status;                        // [4]: code, unit, detail, detail

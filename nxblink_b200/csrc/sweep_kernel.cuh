@@ -968,8 +968,10 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                         s = (u_pcode[ip] >> 24) & 0xffu;
                         ++ip;
                     } else {
-                        if (accum_u && (n_on | n_off))
-                            atomicAdd(&c.s_off_on[e], ((unsigned long long)n_off << 32) | (unsigned)n_on);
+                        // packed word per edge (low: off->on, high: on->off), updated by halves with
+                        // native 32-bit shared atomics; a CTA books far fewer than 2^32 per launch
+                        if (accum_u && n_on) atomicAdd((unsigned*)&c.s_off_on[e], (unsigned)n_on);
+                        if (accum_u && n_off) atomicAdd((unsigned*)&c.s_off_on[e] + 1, (unsigned)n_off);
                         if (x) atomicOr(&newtol[vb], 1u << k);
                         ++e;
                         fresh = true;

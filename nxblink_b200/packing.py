@@ -158,7 +158,8 @@ class PackedModel(object):
                 pool[v] = pool[self.parent[v]]      # parent[v] < v: already final
         return pool
 
-    def desc(self, msg_f64=False, cap_scale=1.0, validate=False, max_warps=0, lockstep_warps=0):
+    def desc(self, msg_f64=False, cap_scale=1.0, validate=False, max_warps=0, lockstep_warps=0,
+            split_phases=0):
         d = _lib.ModelDesc()
         d.n_nodes, d.n_states, d.n_classes, d.nnz = (
                 self.n_nodes, self.n_states, self.n_classes, self.nnz)
@@ -177,6 +178,7 @@ class PackedModel(object):
         d.validate = 1 if validate else 0
         d.max_warps = int(max_warps)
         d.lockstep_warps = int(lockstep_warps)
+        d.split_phases = int(split_phases)
         return d
 
 

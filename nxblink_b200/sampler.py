@@ -40,12 +40,13 @@ class Track(object):
 
 class BlinkSampler(object):
     def __init__(self, model, device=0, msg_f64=False, cap_scale=1.0,
-            validate=False, max_warps=0, lockstep_warps=0):
+            validate=False, max_warps=0, lockstep_warps=0, split_phases=0):
         self.lib = _lib.load()
         self.pm = model if isinstance(model, PackedModel) else PackedModel(model)
         self._h = C.c_void_p()
         desc = self.pm.desc(msg_f64=msg_f64, cap_scale=cap_scale,
-                validate=validate, max_warps=max_warps, lockstep_warps=lockstep_warps)
+                validate=validate, max_warps=max_warps, lockstep_warps=lockstep_warps,
+                split_phases=split_phases)
         rc = self.lib.nxb_create(C.byref(desc), int(device), C.byref(self._h))
         if rc:
             msg = self.lib.nxb_last_error(None).decode()

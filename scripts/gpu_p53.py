@@ -16,12 +16,13 @@ ap.add_argument('--f64', type=int, default=0)
 ap.add_argument('--cap', type=float, default=1.0)
 ap.add_argument('--warps', type=int, default=0)
 ap.add_argument('--lockstep', type=int, default=0)
+ap.add_argument('--split', type=int, default=0)
 a = ap.parse_args()
 m = p53.p53_model()
 pm = packing.PackedModel(m)
 ls, tt, tf = p53.synthetic_alignment(pm, a.sites, seed=0, reference_leaf=pm.node_index[m.name_to_leaf['Has']])
 d = packing.pack_alignment(pm, ls, tt, tf)
-s = nb.BlinkSampler(pm, validate=bool(a.validate), msg_f64=bool(a.f64), cap_scale=a.cap, max_warps=a.warps, lockstep_warps=a.lockstep)
+s = nb.BlinkSampler(pm, validate=bool(a.validate), msg_f64=bool(a.f64), cap_scale=a.cap, max_warps=a.warps, lockstep_warps=a.lockstep, split_phases=a.split)
 s.set_data(d)
 t0 = time.time(); s.init_chains(chains=a.chains, seed=7); print('init %.3fs kernel %s' % (time.time() - t0, s.last_kernel_ms()))
 print(s.stats())

@@ -49,7 +49,14 @@ def test_capacity_tiers_and_geometry_do_not_change_results(nb):
     small = _run(nb, pm, data, chains=8, cap_scale=0.55)  # forces the deferral path
     assert small[2]['deferred_units'] > 0
     few = _run(nb, pm, data, chains=8, max_warps=3)
-    for other in (small, few):
+    # one fused kernel instead of the alternating primary / tolerance kernels, with and
+    # without lockstep groups, and the fused kernel under capacity pressure
+    fused = _run(nb, pm, data, chains=8, split_phases=-1, validate=True)
+    fused_free = _run(nb, pm, data, chains=8, split_phases=-1, lockstep_warps=-1)
+    fused_small = _run(nb, pm, data, chains=8, split_phases=-1, cap_scale=0.55)
+    assert fused_small[2]['deferred_units'] > 0
+    assert fused[2]['kernel_launches'] < base[2]['kernel_launches']
+    for other in (small, few, fused, fused_free, fused_small):
         assert (base[0] == other[0]).all()
         np.testing.assert_allclose(base[1], other[1], rtol=1e-11, atol=1e-9)
         assert base[2]['n_blk_events'] == other[2]['n_blk_events']
