@@ -12,7 +12,7 @@
 #include "sweep_kernel.cuh"
 
 #define NXB_MAX_THREADS 640
-#define NXB_BLINK_THREADS 736      /* blink_kernel needs 88 registers: 23 warps */
+#define NXB_BLINK_THREADS 736      /* register cap 88; 25 warps at 72 registers measured slower (spills) */
 
 namespace nxb {
 
@@ -691,7 +691,7 @@ struct Tier {
     size_t smem;
     // split mode (tier 0 only): shared-memory layout of one unit in blink_kernel
     NxbWarpLayout bwl;
-    int blink_warps = 0, blink_units = 0;
+    int blink_warps = 0, blink_units = 0, blink_warp0 = 0;
     size_t blink_smem = 0;
 };
 
@@ -1000,20 +1000,11 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
                 delete h; return NXB_ERR_BAD_ARG;
             }
         }
-        ml.off_parent = put(parent.data(), 4 * E, 4);
-        ml.off_slot = put(slot.data(), 4 * N, 4);
-        ml.off_tma = put(tma.data(), 8 * E, 8);
-        ml.off_len = put(len.data(), 8 * E, 8);
-        ml.off_rate = put(rate.data(), 8 * E, 8);
-        ml.off_lam_pri = put(lam_pri.data(), 8 * E, 8);
-        ml.off_p0_pri = put(p0_pri.data(), 8 * E, 8);
-        ml.off_lam_blk = put(lam_blk.data(), 8 * E, 8);
-        ml.off_p0_blk = put(p0_blk.data(), 8 * E, 8);
+        // ---- tables of the tolerance update first: blink_kernel stages only this prefix ----
+        std::vector<float> gsc(E, 0.f);
+        for (int e = 0; e < E; ++e)
+            if (rate[e] > 0.0 && len[e] > 0.0) gsc[e] = (float)(0.6931471805599453 / (2.0 * M * rate[e]));
         {
-            std::vector<float> gsc(E, 0.f);
-            for (int e = 0; e < E; ++e)
-                if (rate[e] > 0.0 && len[e] > 0.0) gsc[e] = (float)(0.6931471805599453 / (2.0 * M * rate[e]));
-            ml.off_gsc_blk = put(gsc.data(), 4 * E, 4);
             std::vector<NxbEdgeRec> recs(E);
             for (int e = 0; e < E; ++e) {
                 recs[e].tma = tma[e]; recs[e].tmb = tma[e] + len[e]; recs[e].rate = rate[e];
@@ -1023,6 +1014,27 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             }
             ml.off_edgerec = put(recs.data(), (int)(sizeof(NxbEdgeRec) * E), 16);
         }
+        ml.off_slot = put(slot.data(), 4 * N, 4);
+        std::vector<unsigned char> cls(P);
+        for (int s = 0; s < P; ++s) cls[s] = (unsigned char)d->state_class[s];
+        ml.off_cls = put(cls.data(), P, 1);
+        std::vector<double> qm((size_t)P * K, 0.0);
+        for (int s = 0; s < P; ++s)
+            for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i)
+                qm[(size_t)s * K + d->state_class[d->q_col[i]]] += d->q_val[i];
+        ml.off_qm = put(qm.data(), 8 * P * K, 8);
+        blob.resize(align_up((int)blob.size(), 16));
+        ml.blink_bytes = (int)blob.size();
+        // ---- the rest: primary update ----
+        ml.off_parent = put(parent.data(), 4 * E, 4);
+        ml.off_tma = put(tma.data(), 8 * E, 8);
+        ml.off_len = put(len.data(), 8 * E, 8);
+        ml.off_rate = put(rate.data(), 8 * E, 8);
+        ml.off_lam_pri = put(lam_pri.data(), 8 * E, 8);
+        ml.off_p0_pri = put(p0_pri.data(), 8 * E, 8);
+        ml.off_lam_blk = put(lam_blk.data(), 8 * E, 8);
+        ml.off_p0_blk = put(p0_blk.data(), 8 * E, 8);
+        ml.off_gsc_blk = put(gsc.data(), 4 * E, 4);
         ml.off_qval = put(d->q_val, 8 * nnz, 8);
         std::vector<unsigned short> qinfo(nnz), qptr(P + 1);
         for (int i = 0; i < nnz; ++i)
@@ -1030,15 +1042,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         for (int s = 0; s <= P; ++s) qptr[s] = (unsigned short)d->q_ptr[s];
         ml.off_qinfo = put(qinfo.data(), 2 * nnz, 2);
         ml.off_qptr = put(qptr.data(), 2 * (P + 1), 2);
-        std::vector<unsigned char> cls(P);
-        for (int s = 0; s < P; ++s) cls[s] = (unsigned char)d->state_class[s];
-        ml.off_cls = put(cls.data(), P, 1);
         ml.off_pi = put(d->prior, 8 * P, 8);
-        std::vector<double> qm((size_t)P * K, 0.0);
-        for (int s = 0; s < P; ++s)
-            for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i)
-                qm[(size_t)s * K + d->state_class[d->q_col[i]]] += d->q_val[i];
-        ml.off_qm = put(qm.data(), 8 * P * K, 8);
         std::vector<unsigned long long> clsmask(K, 0ull);
         for (int s = 0; s < P; ++s) clsmask[d->state_class[s]] |= 1ull << s;
         ml.off_clsmask = put(clsmask.data(), 8 * K, 8);
@@ -1182,7 +1186,9 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
                 tier.smem = (size_t)fixed + (size_t)tier.warps * tier.wl.bytes;
                 if (pass == 0 && t == 0) {
                     build_blink_layout(ml, tier.wl.capP, tier.wl.capB, &tier.bwl);
-                    const int fit = (h->max_smem - fixed) / tier.bwl.bytes;
+                    const int bfixed = ml.blink_bytes + stats_bytes;      // model prefix + statistic partials
+                    tier.blink_warp0 = bfixed;
+                    const int fit = (h->max_smem - bfixed) / tier.bwl.bytes;
                     int bw = (d->max_warps > 0) ? std::min(d->max_warps, NXB_BLINK_THREADS / 32)
                                                 : NXB_BLINK_THREADS / 32;
                     if (const char* ev = getenv("NXB_BLINK_WARPS")) bw = std::max(1, std::min(atoi(ev), NXB_BLINK_THREADS / 32));
@@ -1195,7 +1201,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
                     if (bu >= 1) {
                         tier.blink_units = bu;
                         tier.blink_warps = std::min(bw, (bu * K + 31) / 32);
-                        tier.blink_smem = (size_t)fixed + (size_t)bu * tier.bwl.bytes;
+                        tier.blink_smem = (size_t)bfixed + (size_t)bu * tier.bwl.bytes;
                     }
                 }
                 (pass == 0 ? h->tiers : h->init_tiers).push_back(tier);
@@ -1311,6 +1317,10 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
     memset(&p, 0, sizeof(p));
     p.ml = h->ml; p.wl = (kind == KIND_BLINK) ? tier.bwl : tier.wl; p.sl = h->sl;
     p.smem_warp0 = tier.smem_warp0;
+    if (kind == KIND_BLINK) {       // only the tolerance tables of the model are staged
+        p.ml.bytes = h->ml.blink_bytes; p.ml.off_stats = h->ml.blink_bytes;
+        p.smem_warp0 = tier.blink_warp0;
+    }
     p.blob = h->d_blob; p.rmax_tab = h->d_rmax;
     p.pri_ok = h->d_pri_ok; p.tol_true_ok = h->d_tt; p.tol_false_ok = h->d_tf;
     p.state = h->d_state; p.state_stride = h->stride;

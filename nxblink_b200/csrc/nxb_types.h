@@ -65,6 +65,7 @@ struct NxbModelLayout {
     int off_ell_q;      // f32 or f64 (message type) [ell_w*64] rates, 0 in the padding
     int off_qdt;        // message type [64*64] dense transposed rates: qdt[b*64 + a] = q[a -> b]
     int bytes;
+    int blink_bytes;    // prefix of the blob that the tolerance update reads (edge records, slots, classes, Q_meta)
     double rate_on, rate_off;
     double inv_omega_pri;   // 1 / (2 * Rmax(all classes on))
     double acc_blk[4];      // thinning acceptance [own][fg state]
