@@ -225,9 +225,14 @@ def run_gpu_arm(args, rank, local_rank, world):
     barrier()
     t0 = time.perf_counter()
     dev_ms = 0.0
+    kind_ms = {}
     for _ in range(args.steps):
         sampler.sweep(1, accumulate=True)
         dev_ms += sampler.last_kernel_ms()[0]
+        for k, (ms, n) in sampler.last_kernel_ms_by_kind().items():
+            a = kind_ms.setdefault(k, [0.0, 0])
+            a[0] += ms
+            a[1] += n
     barrier()
     wall = time.perf_counter() - t0
     clock_info = clocks.stop()
@@ -284,9 +289,25 @@ def run_gpu_arm(args, rank, local_rank, world):
         state_bytes = st1['state_bytes_used'] / st1['n_units']
         data_bytes_per_site = pm.n_nodes * 16
         bytes_per_unit = 2.0 * state_bytes + data_bytes_per_site / chains
-        kernel_s = (dev_ms * 1e-3) / max(launches, 1)
-        bytes_per_launch = bytes_per_unit * n_units * args.steps / max(launches, 1)
-        achieved = bytes_per_launch / kernel_s / 1e9
+        # One sweep of the batch is two launches (primary-only sweep_kernel, then blink_kernel),
+        # each over all units.  The roofline is quoted for the dominant one (blink_kernel) on
+        # the bytes IT has to move per unit: the whole trajectory and the tolerance data in,
+        # node tolerance states and the new blink events out.  `step` below is the same
+        # ratio for the whole sweep on SURVEY 8(d)'s per-sweep figure.
+        kernels = dict((k, {'ms_per_step': v[0] / args.steps, 'launches': v[1]})
+                for k, v in kind_ms.items() if v[1])
+        dom = max(kernels, key=lambda k: kernels[k]['ms_per_step'])
+        N_nodes = pm.n_nodes
+        blk_bytes = 12.0 * st1['n_blk_events'] / st1['n_units']
+        if dom == 'blink_kernel':
+            dom_bytes = state_bytes + (8 + 4 * N_nodes + blk_bytes) + 8.0 * N_nodes / chains
+        elif dom == 'sweep_kernel (primary only)':
+            dom_bytes = state_bytes + (state_bytes - 4 * N_nodes - blk_bytes) + 16.0 * N_nodes / chains
+        else:
+            dom_bytes = bytes_per_unit
+        dom_s = kernels[dom]['ms_per_step'] * 1e-3 / max(kernels[dom]['launches'] / args.steps, 1)
+        achieved = dom_bytes * n_units / dom_s / 1e9
+        step_achieved = bytes_per_unit * n_units * args.steps / (dev_ms * 1e-3) / 1e9
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
         try:
             with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -299,7 +320,8 @@ def run_gpu_arm(args, rank, local_rank, world):
             with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
                 # ncu capture (one launch at a smaller batch) -> bytes per unit-sweep,
                 # scaled to the units one timed launch processes
-                traffic = json.load(f)['dram_bytes_per_unit_sweep'] * n_units * args.steps / max(launches, 1)
+                tj = json.load(f)
+                traffic = tj.get('dram_bytes_per_unit', {}).get(dom, tj['dram_bytes_per_unit_sweep']) * n_units
         except Exception:
             pass
         cores = os.cpu_count() or 1
@@ -332,12 +354,16 @@ def run_gpu_arm(args, rank, local_rank, world):
             'clocks': clock_info,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'kernel': dom, 'kernel_bytes_per_unit': dom_bytes,
+                'kernel_share_of_step': kernels[dom]['ms_per_step'] / (dev_ms / args.steps),
                 'bytes_per_site_sweep': bytes_per_unit,
+                'step': {'achieved': step_achieved, 'frac': step_achieved / peak},
                 'note': 'the sweep is instruction/latency bound, not HBM bound: see DESIGN.md'},
             'cpu_baseline': {'value': cpu_val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                 'sample': '%d host processes x 1 p53-shaped site x 1 chain x %d sweeps (after 1 '
                     'burn-in), %.1f s wall' % (cores, args.cpu_sweeps, cpu_wall)},
             'allreduce_ms': allreduce_ms,
+            'kernels': kernels,
             'per_rank_ms_and_sm_mhz': per_rank,
         }
         print(json.dumps(out))

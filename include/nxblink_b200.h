@@ -135,6 +135,9 @@ int nxb_read_node_states(nxb_handle* h, int32_t* node_pri, uint32_t* node_tol);
 int nxb_get_stats(nxb_handle* h, nxb_stats* out);
 /* Last sweep-kernel launch times (ms, CUDA events on the launching stream). */
 int nxb_last_kernel_ms(nxb_handle* h, float* total_ms, int32_t* n_launches);
+/* The same, per kernel: [0] fused sweep_kernel (deferral tiers / split_phases < 0),
+ * [1] primary-only sweep_kernel, [2] blink_kernel, [3] validation-only pass. */
+int nxb_last_kernel_ms_by_kind(nxb_handle* h, float ms[4], int32_t n_launches[4]);
 
 /* Per-phase cycle counters of the sweep kernel (lane 0 of every warp, summed):
  * load, P0..P5 (primary update), B0..B2 + write-back (tolerance updates), store.

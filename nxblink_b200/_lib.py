@@ -63,7 +63,7 @@ EXPORTS = (
     'nxb_set_data', 'nxb_init_chains', 'nxb_sweep', 'nxb_summary_layout_get',
     'nxb_summary_reset', 'nxb_summary_read', 'nxb_summary_device_ptrs',
     'nxb_summarize_current', 'nxb_export_unit', 'nxb_get_stats',
-    'nxb_last_kernel_ms', 'nxb_profile', 'nxb_philox4x32_10',
+    'nxb_last_kernel_ms', 'nxb_last_kernel_ms_by_kind', 'nxb_profile', 'nxb_philox4x32_10',
     'nxb_expm_batched', 'nxb_expm_frechet_batched', 'nxb_pruning_loglik', 'nxb_dense_last_error',
     'nxb_forward_sample', 'nxb_forward_sample_rooted', 'nxb_read_node_states',
 )
@@ -99,6 +99,7 @@ def load():
     lib.nxb_export_unit.argtypes = [H, C.c_int64] + [C.c_void_p] * 2 + [C.c_int32] + [C.c_void_p] * 10
     lib.nxb_get_stats.argtypes = [H, C.POINTER(Stats)]
     lib.nxb_last_kernel_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    lib.nxb_last_kernel_ms_by_kind.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.nxb_profile.argtypes = [H, C.c_int32, C.c_void_p]
     lib.nxb_expm_batched.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nxb_expm_frechet_batched.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

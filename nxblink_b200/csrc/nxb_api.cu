@@ -739,6 +739,8 @@ struct nxb_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
     int last_launches = 0;
+    float kind_ms[4] = {0.f, 0.f, 0.f, 0.f};   // of the last call: fused, primary-only, blink, check
+    int kind_launches[4] = {0, 0, 0, 0};
     long long deferred_total = 0, launches_total = 0;
     std::string err;
 };
@@ -1373,6 +1375,7 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->last_ms += ms; h->last_launches++; h->launches_total++;
+    h->kind_ms[kind] += ms; h->kind_launches[kind]++;
     if (hs[0] != 0) {
         char buf[256];
         snprintf(buf, sizeof(buf), "%s (code %d, unit %d, detail %d, sweep %d)", status_text(hs[0]),
@@ -1453,6 +1456,7 @@ extern "C" int nxb_init_chains(nxb_handle* h, int32_t chains, uint64_t seed, int
     h->n_units = n_units; h->chains = chains; h->seed = seed; h->unit_offset = unit_offset;
     h->sweeps = 0;
     h->last_ms = 0.f; h->last_launches = 0;
+    for (int i = 0; i < 4; ++i) { h->kind_ms[i] = 0.f; h->kind_launches[i] = 0; }
     return run_tiers(h, 0u, 0xffffffffu, 1);
 }
 
@@ -1463,6 +1467,7 @@ extern "C" int nxb_sweep(nxb_handle* h, int32_t n_sweeps, int32_t accumulate) {
     const unsigned target = h->sweeps + (unsigned)n_sweeps;
     const unsigned accum_from = accumulate ? h->sweeps : 0xffffffffu;
     h->last_ms = 0.f; h->last_launches = 0;
+    for (int i = 0; i < 4; ++i) { h->kind_ms[i] = 0.f; h->kind_launches[i] = 0; }
     if (h->split && h->tiers[0].blink_units > 0) return run_split(h, target, accum_from);
     int rc = run_tiers(h, target, accum_from, 0);
     if (rc == NXB_OK) h->sweeps = target;
@@ -1663,6 +1668,15 @@ extern "C" int nxb_get_stats(nxb_handle* h, nxb_stats* o) {
     o->n_tiers = (int32_t)h->tiers.size();
     o->capP = t0.wl.capP; o->capB = t0.wl.capB; o->capF = t0.wl.capF; o->capC = t0.wl.capC;
     o->deferred_units = h->deferred_total; o->kernel_launches = h->launches_total;
+    return NXB_OK;
+}
+
+extern "C" int nxb_last_kernel_ms_by_kind(nxb_handle* h, float ms[4], int32_t n[4]) {
+    if (!h) return NXB_ERR_BAD_ARG;
+    for (int i = 0; i < 4; ++i) {
+        if (ms) ms[i] = h->kind_ms[i];
+        if (n) n[i] = h->kind_launches[i];
+    }
     return NXB_OK;
 }
 

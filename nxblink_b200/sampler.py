@@ -145,6 +145,14 @@ class BlinkSampler(object):
         self._check(self.lib.nxb_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    KERNELS = ('sweep_kernel (fused)', 'sweep_kernel (primary only)', 'blink_kernel', 'check')
+
+    def last_kernel_ms_by_kind(self):
+        """{kernel: (ms, launches)} of the last ``sweep`` / ``init_chains`` call."""
+        ms, n = (C.c_float * 4)(), (C.c_int32 * 4)()
+        self._check(self.lib.nxb_last_kernel_ms_by_kind(self._h, ms, n))
+        return dict((k, (ms[i], n[i])) for i, k in enumerate(self.KERNELS))
+
     PHASES = ('load', 'P0 edge-major view', 'P1 candidates', 'P2 chunks', 'P3 upward',
             'P4 downward', 'P5 writeback+stats', 'B0 pool', 'B1 upward', 'B2 downward+stats',
             'BW writeback', 'store')
