@@ -808,6 +808,7 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     wl->off_toff = take(4 * (K + 1), 4);
     wl->off_acc = take(4 * 3 * K * ml.nslots, 4);
     wl->off_newtol = take(4 * N, 4);
+    wl->off_nrec = take(16 * E, 16);
     // validate_unit needs bord while the persistent state is live; it is only called
     // between phases, when either scratch is dead.
     const int end_blk = o;
@@ -850,6 +851,7 @@ static void build_blink_layout(const NxbModelLayout& ml, int capP, int capB, Nxb
     wl->off_toff = take(4 * (K + 1), 4);
     wl->off_acc = take(4 * 3 * K * ml.nslots, 4);
     wl->off_newtol = take(4 * N, 4);
+    wl->off_nrec = take(16 * E, 16);
     wl->bytes = align_up(o, 16);
 }
 

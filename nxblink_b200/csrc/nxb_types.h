@@ -99,6 +99,7 @@ struct NxbWarpLayout {
         off_finv, off_fu;
     // blink-phase scratch
     int off_ctm, off_cell, off_cedge, off_toff, off_acc, off_newtol;
+    int off_nrec;           // uint4[E]: per-edge record of the tolerance update's upward walk
     int off_uhdr;           // int[8 + 32]: unit header read by the lane jobs of other warps (persistent region)
     int bytes;
 };

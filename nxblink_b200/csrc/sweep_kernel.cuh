@@ -724,6 +724,14 @@ __device__ __forceinline__ void blink_setup(Ctx& c, bool accumulate, bool active
         if (lane < K) toff_own[lane] = ex;
         if (lane == 0) toff_own[K] = total;
     }
+    if (active) {
+        // one 16-byte record per edge for the upward walk: data masks, old tolerance states and
+        // primary state of the lower node, and the index of the edge's first primary event
+        const SPtr<uint4> nrec_own = {c.wbase + wl.off_nrec};
+        for (int e = lane; e < c.E; e += 32)
+            nrec_own[e] = make_uint4(c.tt_ok[e + 1], c.tf_ok[e + 1], c.node_tol[e + 1],
+                                     (unsigned)c.node_pri[e + 1] | ((unsigned)c.poff[e] << 8));
+    }
     if (lane == 0) {
         uhdr_own[0] = active ? 1 : 0; uhdr_own[2] = c.nB; uhdr_own[3] = (int)c.unit32; uhdr_own[4] = 0;
         uhdr_own[5] = (int)c.sweep; uhdr_own[6] = accumulate ? 1 : 0;
@@ -757,6 +765,7 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
     const SPtr<unsigned> newtol = {ub + wl.off_newtol};
     const SPtr<int> poff = {ub + wl.off_poff};
     const SPtr<const int> toff = {ub + wl.off_toff};
+    const SPtr<const uint4> nrec = {ub + wl.off_nrec};
     const SPtr<unsigned> u_node_tol = {ub + wl.off_node_tol};
     const SPtr<unsigned char> u_node_pri = {ub + wl.off_node_pri};
     const SPtr<double> u_ptm = {ub + wl.off_ptm};
@@ -800,14 +809,13 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
         double tma = 0.0, rate = 0.0, tcur = 0.0, u0 = 1.0, u1 = 1.0, pen = 0.0;
         double tcand = -NXB_INF;
         float gsc = 0.f;
-        int s = 0, ip = 0, ip0 = 0, sa_slot = 0, sb_slot = -1;
+        int s = 0, ip = trk ? poff[E] - 1 : 0, ip0 = 0, sa_slot = 0, sb_slot = -1;
         unsigned xold = 0u;
         while (__any_sync(FULL, e >= 0)) {
             if (e >= 0) {
                 bool draw_gap = false;
                 if (fresh) {
                     const NxbEdgeRec er = erec[e];
-                    const int vb = e + 1;
                     sb_slot = er.sb_slot; sa_slot = er.sa_slot;
                     tma = er.tma; rate = er.rate; tcur = er.tmb;
                     u0 = 1.0; u1 = 1.0; pen = 0.0;
@@ -815,11 +823,14 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                         const int ai = (sb_slot * K + k) * 3;
                         u0 = (double)acc[ai]; u1 = (double)acc[ai + 1]; pen = (double)acc[ai + 2];
                     }
-                    if (!((u_tt_ok[vb] >> k) & 1u)) u1 = 0.0;
-                    if (!((u_tf_ok[vb] >> k) & 1u)) u0 = 0.0;
-                    s = u_node_pri[vb];
-                    xold = (u_node_tol[vb] >> k) & 1u;
-                    ip = poff[e + 1] - 1; ip0 = poff[e];
+                    const uint4 nr = nrec[e];
+                    if (!((nr.x >> k) & 1u)) u1 = 0.0;
+                    if (!((nr.y >> k) & 1u)) u0 = 0.0;
+                    s = (int)(nr.w & 0xffu);
+                    xold = (nr.z >> k) & 1u;
+                    // the cursor into the primary events carries over from the edge before
+                    // (events are sorted by edge): only the lower bound is new
+                    ip0 = (int)(nr.w >> 8);
                     // dominating rate of the edge: 2 * max(on, off) * rate_e per unit time
                     gsc = er.gsc;
                     draw_gap = gsc > 0.f;
