@@ -1225,14 +1225,14 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             // live events per track and sweep: retained + accepted candidates
             {
                 const double per_track = (mean_blk + cand_blk) / K;
-                h->gcapC = align_up((int)(4.0 * per_track + 10.0 * sqrt(per_track + 1.0) + 64.0), 8);
+                h->gcapC = std::min(32760, align_up((int)(4.0 * per_track + 10.0 * sqrt(per_track + 1.0) + 64.0), 8));
             }
             int o = 0;
             h->g_off_msg = o; o += (h->msg_f64 ? 8 : 4) * (h->gcapF + 1) * NXB_PPAD;
             o = align_up(o, 16);
             h->g_off_ctm = o; o += 16 * h->gcapC * 32;     // one region per lane (track), 16 B records
             h->g_off_cell = o;
-            h->g_off_cedge = o; o += 2 * h->gcapC * 32;
+            h->g_off_cedge = o;                           // (the edge is part of the 16 B record)
             h->gscratch_stride = align_up(o, 256);
             cudaError_t e1 = cudaMalloc(&h->d_gscratch, (size_t)h->gscratch_stride * max_w * h->num_sms);
             if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }

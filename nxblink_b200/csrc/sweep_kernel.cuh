@@ -696,8 +696,11 @@ __device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a :
 #define CE_EDGE 0x3fffu
 #define CE_NEW1 0x4000u     // (survivors only) new state of the surviving event
 
-// one 16-byte record per live event: time, (OFF, ON) message below the event
-struct __align__(16) LiveEv { double t; float l0, l1; };
+// One 16-byte record per live event: time, q = l1 / (l0 + l1) of the (OFF, ON) message below the
+// event (the backward draw only needs the ratio), edge.  The downward pass reuses the records it
+// has consumed for the survivors (e then also carries CE_NEW1), so a track touches only
+// ceil(16 * live / 128) lines of the L2-resident pool per sweep.
+struct __align__(16) LiveEv { double t; float q; unsigned short e, pad; };
 
 // ---- S0 (the warp that owns the unit): index of the primary events, offsets of the retained
 // events per track, and the unit header that the lane jobs of other warps read
@@ -759,7 +762,6 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
     // live foreground events of this sweep: global (L2-resident) scratch, one fixed region per
     // (unit, track), filled by the upward pass and consumed backwards by the downward pass
     LiveEv* cev = (LiveEv*)(ugb + p.g_off_ctm) + (size_t)k * TCAP;
-    unsigned short* cedge = (unsigned short*)(ugb + p.g_off_cedge) + (size_t)k * TCAP;
     const SPtr<int> uhdr = {ub + wl.off_uhdr};
     const SPtr<float> acc = {ub + wl.off_acc};                  // [slot][K][3]: u0, u1, penalty
     const SPtr<unsigned> newtol = {ub + wl.off_newtol};
@@ -882,9 +884,9 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                         const double r = pow2_rescale(mx);
                         const double l1 = u1 * r, l0 = u0 * r;       // scale-free message below the event
                         if (cnt < TCAP) {
-                            LiveEv ev; ev.t = tnext; ev.l0 = (float)l0; ev.l1 = (float)l1;
+                            LiveEv ev; ev.t = tnext; ev.q = __fdividef((float)l1, (float)(l0 + l1));      // operands in [0, 2): fast division is safe
+                            ev.e = (unsigned short)e; ev.pad = 0;
                             cev[cnt] = ev;
-                            cedge[cnt] = (unsigned short)e;
                         } else bad = 2;
                         ++cnt;
                         // uniformized 2x2 matrix of this context (poisson.py:92-96)
@@ -923,7 +925,7 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
     // reverse; survivors (real transitions) are written from the top of the region downwards.
     // The OFF-time and transition statistics are fused in (summary.py:123-131,234-243).
     const NxbSummaryLayout& sl = p.sl;
-    int wtop = TCAP - 1;
+    int wtop = cnt - 1;            // survivors overwrite consumed records, from the last one down
     {
         const float a_on_f = (float)ml.a_on, a_off1_f = (float)(1.0 - ml.a_off);
         int e = trk ? 0 : E;
@@ -931,9 +933,8 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
         bool fresh = true;
         int s = 0, ip = 0, ipe = 0, vb = 0, n_on = 0, n_off = 0;
         double tmb = 0.0, tcur = 0.0, offtime = 0.0;
-        LiveEv pf; pf.t = NXB_INF; pf.l0 = 0.f; pf.l1 = 0.f;
-        unsigned pf_e = 0xffffu;
-        if (ir >= 0) { pf = cev[ir]; pf_e = cedge[ir]; }
+        LiveEv pf; pf.t = NXB_INF; pf.q = 0.f; pf.e = 0xffffu; pf.pad = 0;
+        if (ir >= 0) pf = cev[ir];
         while (__any_sync(FULL, e < E)) {
             if (e < E) {
                 if (fresh) {
@@ -948,15 +949,16 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                     fresh = false;
                 }
                 const double tp = (ip < ipe) ? u_ptm[ip] : NXB_INF;
-                const double tc = (pf_e == (unsigned)e) ? pf.t : NXB_INF;
+                const double tc = ((unsigned)pf.e == (unsigned)e) ? pf.t : NXB_INF;
                 const double tnext = dmin2(dmin2(tp, tc), tmb);
                 if (!x) offtime += tnext - tcur;
                 tcur = tnext;
                 if (tc < tp) {
-                    const float l0 = pf.l0, l1 = pf.l1;
+                    const float l1 = pf.q, l0 = 1.f - pf.q;
                     --ir;
-                    if (ir >= 0) { pf = cev[ir]; pf_e = cedge[ir]; }
-                    else { pf.t = NXB_INF; pf_e = 0xffffu; }
+                    // (the record at ir is in registers before a survivor may overwrite it: wtop >= ir)
+                    if (ir >= 0) pf = cev[ir];
+                    else { pf.t = NXB_INF; pf.e = 0xffffu; }
                     const bool own = (c.cls[s] == k);
                     const float p1 = own ? (x ? 1.f : 0.5f) : (x ? a_off1_f : a_on_f);
                     const float w1 = p1 * l1, w0 = (1.f - p1) * l0;
@@ -964,8 +966,8 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                     const float u = (float)(nxb_xo_next(xo) >> 8) * (1.0f / 16777216.0f);
                     const unsigned xn = (u * (w0 + w1) < w1) ? 1u : 0u;
                     if (xn != x) {
-                        cev[wtop].t = tc;
-                        cedge[wtop] = (unsigned short)(e | (xn ? CE_NEW1 : 0u));
+                        LiveEv sv; sv.t = tc; sv.q = 0.f; sv.e = (unsigned short)(e | (xn ? CE_NEW1 : 0u)); sv.pad = 0;
+                        cev[wtop] = sv;
                         --wtop;
                         if (xn) ++n_on; else ++n_off;
                         x = xn;
@@ -992,7 +994,7 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
         }
     }
     if (trk) {
-        uhdr[8 + k] = TCAP - 1 - wtop;                  // survivors of this track
+        uhdr[8 + k] = (cnt - 1 - wtop) | (cnt << 16);   // survivors of this track | live events
         if (bad) atomicOr(&uhdr[4], bad);
     }
     tick(c, T_B2);
@@ -1013,8 +1015,9 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         if (flags & 1) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
     }
     LiveEv* cev_own = (LiveEv*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
-    unsigned short* cedge_own = (unsigned short*)(c.gbase + p.g_off_cedge) + (size_t)lane * TCAP;
-    int n_mine = (lane < K) ? uhdr_own[8 + lane] : 0, total;
+    const int packed = (lane < K) ? uhdr_own[8 + lane] : 0;
+    const int n_mine = packed & 0xffff, n_live = packed >> 16;
+    int total;
     int dst = warp_excl_scan(n_mine, lane, total);
     for (int v = lane; v < N; v += 32) c.node_tol[v] = newtol_own[v];
     if (accumulate && lane == 0) {
@@ -1036,9 +1039,9 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         obcode = (unsigned*)(slab + p.so_bcode);
     }
     for (int q = 0; q < n_mine; ++q) {
-        const int src = TCAP - 1 - q;          // first survivor (rootmost, earliest) sits at the top
-        const unsigned ce = cedge_own[src];
-        obtm[dst + q] = cev_own[src].t;
+        const LiveEv sv = cev_own[n_live - 1 - q];      // first survivor (rootmost, earliest) on top
+        const unsigned ce = sv.e;
+        obtm[dst + q] = sv.t;
         obcode[dst + q] = (unsigned)(ce & CE_EDGE) | ((unsigned)lane << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);
     }
     __syncwarp();
