@@ -248,12 +248,13 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
                 if (hdr.phase != NXB_PHASE_INIT) {
                     unsigned* g_tol = (unsigned*)(slab + p.so_tol);
                     unsigned* g_npri = (unsigned*)(slab + p.so_pri);
-                    for (int v = lane; v < N; v += 32) __stcs(g_tol + v, c.node_tol[v]);
+                    // (the primary update leaves the tolerance states and blink events as they are)
+                    if (!PRIMARY_ONLY) for (int v = lane; v < N; v += 32) __stcs(g_tol + v, c.node_tol[v]);
                     for (int v = lane; v < (N + 3) / 4; v += 32) __stcs(g_npri + v, sm_ptr<unsigned>(c.node_pri.off)[v]);
                     double* g_ptm = (double*)(slab + p.so_ptm);
                     unsigned* g_pcode = (unsigned*)(slab + p.so_pcode);
                     for (int i = lane; i < c.nP; i += 32) { __stcs(g_ptm + i, c.ptm[i]); __stcs(g_pcode + i, c.pcode[i]); }
-                    if (!spilled) {
+                    if (!spilled && !PRIMARY_ONLY) {
                         double* g_btm = (double*)(slab + p.so_btm);
                         unsigned* g_bcode = (unsigned*)(slab + p.so_bcode);
                         for (int i = lane; i < c.nB; i += 32) { __stcs(g_btm + i, c.btm[i]); __stcs(g_bcode + i, c.bcode[i]); }
