@@ -709,7 +709,7 @@ struct nxb_handle {
     unsigned long long* d_perf = nullptr;
     unsigned char* d_gscratch = nullptr;
     long long gscratch_stride = 0;
-    int g_off_msg = 0, g_off_ctm = 0, g_off_cell = 0, g_off_cedge = 0, gcapF = 0, gcapC = 0;
+    int g_off_msg = 0, g_off_ctm = 0, gcapF = 0, gcapC = 0;
     int profile = 0;
     int lockstep = 0;              // warps per lockstep group in tier 0 (0: independent warps)
     bool split = true;             // tier 0: primary and tolerance updates as alternating kernels
@@ -805,7 +805,6 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     const int end_pri = o;
     // blink-phase scratch (aliases the primary-phase scratch)
     o = scratch0;
-    wl->off_ctm = wl->off_cell = wl->off_cedge = 0;            // candidate pool is global
     wl->off_toff = take(4 * (K + 1), 4);
     wl->off_acc = take(4 * 3 * K * ml.nslots, 4);
     wl->off_newtol = take(4 * N, 4);
@@ -1231,9 +1230,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             int o = 0;
             h->g_off_msg = o; o += (h->msg_f64 ? 8 : 4) * (h->gcapF + 1) * NXB_PPAD;
             o = align_up(o, 16);
-            h->g_off_ctm = o; o += 16 * h->gcapC * 32;     // one region per lane (track), 16 B records
-            h->g_off_cell = o;
-            h->g_off_cedge = o;                           // (the edge is part of the 16 B record)
+            h->g_off_ctm = o; o += 16 * h->gcapC * K;      // one region per track, 16 B records
             h->gscratch_stride = align_up(o, 256);
             cudaError_t e1 = cudaMalloc(&h->d_gscratch, (size_t)h->gscratch_stride * max_w * h->num_sms);
             if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }
@@ -1347,8 +1344,7 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
     p.work_counter = h->d_work;
     p.perf = h->profile ? h->d_perf : nullptr;
     p.gscratch = h->d_gscratch; p.gscratch_stride = h->gscratch_stride;
-    p.g_off_msg = h->g_off_msg; p.g_off_ctm = h->g_off_ctm; p.g_off_cell = h->g_off_cell;
-    p.g_off_cedge = h->g_off_cedge; p.gcapF = h->gcapF; p.gcapC = h->gcapC;
+    p.g_off_msg = h->g_off_msg; p.g_off_ctm = h->g_off_ctm; p.gcapF = h->gcapF; p.gcapC = h->gcapC;
     CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
     if (!append) CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
     const long long n_work = list ? n_list : h->n_units;

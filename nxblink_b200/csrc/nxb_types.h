@@ -98,7 +98,7 @@ struct NxbWarpLayout {
         off_nchunk, off_jump, off_par, off_toland, off_callow, off_cstate, off_msg,
         off_finv, off_fu;
     // blink-phase scratch
-    int off_ctm, off_cell, off_cedge, off_toff, off_acc, off_newtol;
+    int off_toff, off_acc, off_newtol;
     int off_nrec;           // uint4[E]: per-edge record of the tolerance update's upward walk
     int off_uhdr;           // int[8 + 32]: unit header read by the lane jobs of other warps (persistent region)
     int bytes;
@@ -149,7 +149,7 @@ struct NxbSweepParams {
     unsigned accum_from;                // accumulate statistics for sweeps >= this
     int init;                           // 1: initialise trajectories (raoteh.py:337-361)
     int group_warps;                    // >1: warps run in phase lockstep in groups of this size
-    unsigned sync_mask;                 // lockstep: bits 0-5 primary sync points, 6-9 blink sync points
+    unsigned sync_mask;                 // lockstep: which of the 6 primary sync points wait (the tolerance update's always do)
     unsigned begin_sweeps;              // lockstep: every unit starts the launch at this sweep count
     int validate;                       // 1: check trajectory invariants after every phase
     int validate_only;                  // primary-only kernel: load, check, do nothing else
@@ -163,6 +163,6 @@ struct NxbSweepParams {
     // FFBS and the candidate pool of the tolerance update
     unsigned char* gscratch;
     long long gscratch_stride;
-    int g_off_msg, g_off_ctm, g_off_cell, g_off_cedge;
+    int g_off_msg, g_off_ctm;          // global scratch: chunk messages, event pool
     int gcapF, gcapC;
 };
