@@ -31,6 +31,7 @@ __device__ __forceinline__ void cta_prologue(Ctx& c, const NxbSweepParams& p, in
     c.p = &p;
     c.N = ml.N; c.E = ml.E; c.P = ml.P; c.K = ml.K; c.lane = lane;
     c.parent.off = ml.off_parent;
+    c.eperm.off = ml.off_eperm;
     c.slot.off = ml.off_slot;
     c.tma.off = ml.off_tma;
     c.len.off = ml.off_len;
@@ -1031,6 +1032,23 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         ml.blink_bytes = (int)blob.size();
         // ---- the rest: primary update ----
         ml.off_parent = put(parent.data(), 4 * E, 4);
+        {
+            // longest-processing-time assignment of the edges to 32 lane slots per round: round r
+            // serves the r-th block of 32 edges by decreasing rate x length, odd rounds reversed,
+            // so that the longest edges share a lane with the shortest ones
+            const int Epad = (E + 31) / 32 * 32;
+            std::vector<int> order(E);
+            for (int e = 0; e < E; ++e) order[e] = e;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                return rate[a] * len[a] > rate[b] * len[b]; });
+            std::vector<unsigned short> eperm(Epad, 0xffffu);
+            for (int i = 0; i < Epad; ++i) {
+                const int r = i / 32, l = i % 32;
+                const int src = r * 32 + ((r & 1) ? 31 - l : l);
+                if (src < E) eperm[i] = (unsigned short)order[src];
+            }
+            ml.off_eperm = put(eperm.data(), 2 * Epad, 2);
+        }
         ml.off_tma = put(tma.data(), 8 * E, 8);
         ml.off_len = put(len.data(), 8 * E, 8);
         ml.off_rate = put(rate.data(), 8 * E, 8);

@@ -42,6 +42,7 @@ struct NxbModelLayout {
     int N, E, P, K, nnz, nslots, diameter, table_bits;
     int off_stats;      // CTA-level statistic partials (u64), zeroed per launch
     int stats_words;
+    int off_eperm;      // u16    [ceil32(E)] balanced lane assignment of the edges (0xffff: none)
     int off_parent;     // int32  [E]   parent node of node e+1
     int off_slot;       // int32  [N]   accumulator slot of internal nodes, -1 for leaves
     int off_tma;        // f64    [E]   time at the rootward end of edge e

@@ -56,6 +56,7 @@ struct Ctx {
     int N, E, P, K, lane;
     // model tables (shared memory)
     SPtr<const int> parent, slot;
+    SPtr<const unsigned short> eperm;   // edge served by lane slot i of the edge-parallel loops (0xffff: none)
     SPtr<const double> tma, len, rate, lam_pri, p0_pri, lam_blk, p0_blk, qval, pi, qm;
     SPtr<const float> gsc_blk;
     SPtr<const unsigned short> qinfo, qptr;
@@ -269,6 +270,9 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     const SPtr<MSG> srow = {c.wbase + wl.off_msg};           // staging row of the chunk being pushed up
     const SPtr<int> boff = c.boff, poff = c.poff;
     const SPtr<int> mE = c.tmpa, rbase = c.tmpb, foff = c.tmpc;
+    // Edge-parallel loops serve edges in a balanced order (longest edges alone on a lane, short
+    // ones paired): the work of an edge is proportional to rate x length, which spans 2 decades.
+    const int Epad = (E + 31) & ~31;
 
     phase_sync(c);
     // ---- P0: edge-major, time-sorted view of the retained blink events ----------
@@ -294,7 +298,9 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         bord[boff[e] + pos] = (unsigned short)i;
     }
     __syncwarp();
-    for (int e = lane; e < E; e += 32) {
+    for (int q = lane; q < Epad; q += 32) {
+        const int e = c.eperm[q];
+        if (e >= E) continue;
         int a = boff[e], b = boff[e + 1];
         for (int i = a + 1; i < b; ++i) {
             unsigned short id = bord[i];
@@ -311,8 +317,8 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 
     // ---- P1: candidates by thinning, merged walk, foreground event regions ------
     int run = 0;
-    for (int b = 0; b < E; b += 32) {
-        const int e = b + lane;
+    for (int b = 0; b < Epad; b += 32) {
+        const int e = c.eperm[b + lane];
         const bool valid = e < E;
         int n_ret = 0, n_cand = 0;
         bool active = false;
@@ -403,7 +409,9 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     __syncwarp();
     tick(c, T_P1);
     phase_sync(c);
-    for (int e = lane; e < E; e += 32) {
+    for (int q = lane; q < Epad; q += 32) {
+        const int e = c.eperm[q];
+        if (e >= E) continue;
         int src = rbase[e], dst = foff[e], m = mE[e];
         for (int i = 0; i < m; ++i) {
             ftm[dst + i] = rtm[src + i];
@@ -440,7 +448,9 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         par[j + 1] = (unsigned short)((j == foff[e]) ? nchunk[c.parent[e]] : j);
     }
     __syncwarp();
-    for (int e = lane; e < E; e += 32) {
+    for (int q = lane; q < Epad; q += 32) {
+        const int e = c.eperm[q];
+        if (e >= E) continue;
         const int va = c.parent[e];
         int cur = nchunk[va];
         unsigned mask = c.node_tol[va];
@@ -649,7 +659,9 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     if (accumulate) {
         build_poff(c);
         const NxbSummaryLayout& sl = p.sl;
-        for (int e = lane; e < E; e += 32) {
+        for (int q = lane; q < Epad; q += 32) {
+            const int e = c.eperm[q];
+            if (e >= E) continue;
             double t = c.tma[e];
             int s = c.node_pri[c.parent[e]];
             for (int i = poff[e]; i < poff[e + 1]; ++i) {
