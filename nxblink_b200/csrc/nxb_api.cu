@@ -807,7 +807,7 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     // blink-phase scratch (aliases the primary-phase scratch)
     o = scratch0;
     wl->off_toff = take(4 * (K + 1), 4);
-    wl->off_acc = take(4 * 3 * K * ml.nslots, 4);
+    wl->off_acc = take(16 * K * ml.nslots, 16);
     wl->off_newtol = take(4 * N, 4);
     wl->off_nrec = take(16 * E, 16);
     // validate_unit needs bord while the persistent state is live; it is only called
@@ -850,7 +850,7 @@ static void build_blink_layout(const NxbModelLayout& ml, int capP, int capB, Nxb
     wl->off_tmpa = take(4 * (E + 1), 4);
     wl->off_uhdr = take(4 * (8 + 32), 4);
     wl->off_toff = take(4 * (K + 1), 4);
-    wl->off_acc = take(4 * 3 * K * ml.nslots, 4);
+    wl->off_acc = take(16 * K * ml.nslots, 16);
     wl->off_newtol = take(4 * N, 4);
     wl->off_nrec = take(16 * E, 16);
     wl->bytes = align_up(o, 16);

@@ -685,23 +685,17 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 // TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, lane k = track k
 // ---------------------------------------------------------------------------
 // Exponential gap of the dominating Poisson process, mean gsc / ln 2 (time units).  The
-// logarithm is taken in f32 (23-bit uniform); a second word spreads the result over the f64 grid so that event times never tie.
+// logarithm is taken in f32 (23-bit uniform); a second word spreads the result over the f64 grid
+// (uniformly within the f32 ulp) so that event times never tie.
 __device__ __forceinline__ double exp_gap(NxbXo& xo, float gsc) {
     const float f = ((float)(nxb_xo_next(xo) >> 9) + 0.5f) * (1.0f / 8388608.0f);   // in (0,1), exact
     // MUFU.LG2 has ~2^-22 absolute error, which only matters for f within 1e-6 of 1: clamp so
     // that the gap stays strictly positive (affects one draw in a million by < 1e-7 of a mean gap)
     const double g = (double)(fmaxf(-__log2f(f), 5.9604645e-8f) * gsc);
-    return g * (1.0 + ((double)nxb_xo_next(xo) + 0.5) * (1.0 / 72057594037927936.0));   // * (1 + u * 2^-24)
+    // the f32 value has 29 zero low mantissa bits as an f64: fill them with random bits
+    return __longlong_as_double(__double_as_longlong(g) | (long long)(nxb_xo_next(xo) >> 3));
 }
 
-// 2^-floor(log2 m) for a positive finite m: exact power-of-two rescaling that keeps message
-// magnitudes in [1, 2) without a division and preserves exact zeros of the other component.
-__device__ __forceinline__ double pow2_rescale(double m) {
-    const long long bits = __double_as_longlong(m);
-    return __longlong_as_double((0x7fdLL << 52) - (bits & (0x7ffLL << 52)));
-}
-
-// max / min without the NaN handling of fmax / fmin (event times and messages are never NaN)
 __device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a : b; }
 
@@ -713,6 +707,15 @@ __device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a :
 // has consumed for the survivors (e then also carries CE_NEW1), so a track touches only
 // ceil(16 * live / 128) lines of the L2-resident pool per sweep.
 struct __align__(16) LiveEv { double t; float q; unsigned short e, pad; };
+// Accumulator of a node for one track: product of the (OFF, ON) messages of the children folded
+// so far (f32, rescaled by powers of two) and the penalty exponent still to be applied to ON.
+struct __align__(16) AccRec { double pen; float u0, u1; };
+
+// 2^-(floor(log2 m) + 1) for a positive finite m: exact power-of-two rescaling into [0.5, 1)
+// without a division; preserves exact zeros of the other component.
+__device__ __forceinline__ float pow2_rescale_f(float m) {
+    return __int_as_float((0xfd << 23) - (__float_as_int(m) & (0xff << 23)));
+}
 
 // ---- S0 (the warp that owns the unit): index of the primary events, offsets of the retained
 // events per track, and the unit header that the lane jobs of other warps read
@@ -775,7 +778,7 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
     // (unit, track), filled by the upward pass and consumed backwards by the downward pass
     LiveEv* cev = (LiveEv*)(ugb + p.g_off_ctm) + (size_t)k * TCAP;
     const SPtr<int> uhdr = {ub + wl.off_uhdr};
-    const SPtr<float> acc = {ub + wl.off_acc};                  // [slot][K][3]: u0, u1, penalty
+    const SPtr<AccRec> acc = {ub + wl.off_acc};                 // [slot][K]
     const SPtr<unsigned> newtol = {ub + wl.off_newtol};
     const SPtr<int> poff = {ub + wl.off_poff};
     const SPtr<const int> toff = {ub + wl.off_toff};
@@ -815,12 +818,13 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
         const unsigned thr_o1 = (unsigned)fmin(ml.acc_blk[1] * 4294967296.0, 4294967295.0);
         const unsigned thr_w0 = (unsigned)fmin(ml.acc_blk[2] * 4294967296.0, 4294967295.0);
         const unsigned thr_w1 = (unsigned)fmin(ml.acc_blk[3] * 4294967296.0, 4294967295.0);
-        const double a_on = ml.a_on, a_off = ml.a_off;
+        const float a_on = (float)ml.a_on, a_off = (float)ml.a_off;
         int e = trk ? E - 1 : -1;
         int io = ohi - 1;              // cursor into the retained events (descending)
         unsigned inited = 0u;          // live accumulator slots of this lane
         bool fresh = true;
-        double tma = 0.0, rate = 0.0, tcur = 0.0, u0 = 1.0, u1 = 1.0, pen = 0.0;
+        double tma = 0.0, rate = 0.0, tcur = 0.0, pen = 0.0;
+        float u0 = 1.f, u1 = 1.f;      // (OFF, ON) message at the current point of the walk
         double tcand = -NXB_INF;
         float gsc = 0.f;
         int s = 0, ip = trk ? poff[E] - 1 : 0, ip0 = 0, sa_slot = 0, sb_slot = -1;
@@ -832,14 +836,14 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                     const NxbEdgeRec er = erec[e];
                     sb_slot = er.sb_slot; sa_slot = er.sa_slot;
                     tma = er.tma; rate = er.rate; tcur = er.tmb;
-                    u0 = 1.0; u1 = 1.0; pen = 0.0;
+                    u0 = 1.f; u1 = 1.f; pen = 0.0;
                     if (sb_slot >= 0 && ((inited >> sb_slot) & 1u)) {
-                        const int ai = (sb_slot * K + k) * 3;
-                        u0 = (double)acc[ai]; u1 = (double)acc[ai + 1]; pen = (double)acc[ai + 2];
+                        const AccRec a = acc[sb_slot * K + k];
+                        u0 = a.u0; u1 = a.u1; pen = a.pen;
                     }
                     const uint4 nr = nrec[e];
-                    if (!((nr.x >> k) & 1u)) u1 = 0.0;
-                    if (!((nr.y >> k) & 1u)) u0 = 0.0;
+                    if (!((nr.x >> k) & 1u)) u1 = 0.f;
+                    if (!((nr.y >> k) & 1u)) u0 = 0.f;
                     s = (int)(nr.w & 0xffu);
                     xold = (nr.z >> k) & 1u;
                     // the cursor into the primary events carries over from the edge before
@@ -863,17 +867,18 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                 const bool own = (c.cls[s] == k);
                 // chunking.py:67-79: own class forces ON; ON pays the rate into class k
                 pen += c.qm[s * K + k] * rate * (tcur - tnext);
-                if (own) u0 = 0.0;
+                if (own) u0 = 0.f;
                 tcur = tnext;
                 if (tp == -NXB_INF && tf == -NXB_INF) {
                     // top of the edge: fold into the parent's accumulator (one normalisation)
-                    const int ai = (sa_slot * K + k) * 3;
-                    double n0 = u0, n1 = u1, np = pen;
-                    if ((inited >> sa_slot) & 1u) { n0 *= (double)acc[ai]; n1 *= (double)acc[ai + 1]; np += (double)acc[ai + 2]; }
-                    double m2 = dmax2(n0, n1);
-                    if (!(m2 > 0.0)) { bad = 1; m2 = 1.0; }
-                    const double r2 = pow2_rescale(m2);
-                    acc[ai] = (float)(n0 * r2); acc[ai + 1] = (float)(n1 * r2); acc[ai + 2] = (float)np;
+                    const int ai = sa_slot * K + k;
+                    AccRec n; n.u0 = u0; n.u1 = u1; n.pen = pen;
+                    if ((inited >> sa_slot) & 1u) { const AccRec a = acc[ai]; n.u0 *= a.u0; n.u1 *= a.u1; n.pen += a.pen; }
+                    float m2 = fmaxf(n.u0, n.u1);
+                    if (!(m2 > 0.f)) { bad = 1; m2 = 1.f; }
+                    const float r2 = pow2_rescale_f(m2);
+                    n.u0 *= r2; n.u1 *= r2;
+                    acc[ai] = n;
                     inited |= 1u << sa_slot;
                     if (sb_slot >= 0) inited &= ~(1u << sb_slot);
                     --e;
@@ -890,19 +895,19 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                         if (!(tcand > tma)) tcand = -NXB_INF;
                     }
                     if (live) {
-                        if (pen != 0.0) { u1 *= (double)expf((float)(-pen)); pen = 0.0; }
-                        double mx = dmax2(u0, u1);
-                        if (!(mx > 0.0)) { bad = 1; mx = 1.0; }
-                        const double r = pow2_rescale(mx);
-                        const double l1 = u1 * r, l0 = u0 * r;       // scale-free message below the event
+                        if (pen != 0.0) { u1 *= expf((float)(-pen)); pen = 0.0; }
+                        float mx = fmaxf(u0, u1);
+                        if (!(mx > 0.f)) { bad = 1; mx = 1.f; }
+                        const float r = pow2_rescale_f(mx);
+                        const float l1 = u1 * r, l0 = u0 * r;        // scale-free message below the event
                         if (cnt < TCAP) {
-                            LiveEv ev; ev.t = tnext; ev.q = __fdividef((float)l1, (float)(l0 + l1));      // operands in [0, 2): fast division is safe
+                            LiveEv ev; ev.t = tnext; ev.q = __fdividef(l1, l0 + l1);      // operands in [0, 2): fast division is safe
                             ev.e = (unsigned short)e; ev.pad = 0;
                             cev[cnt] = ev;
                         } else bad = 2;
                         ++cnt;
                         // uniformized 2x2 matrix of this context (poisson.py:92-96)
-                        if (own) { u0 = 0.5 * l0 + 0.5 * l1; u1 = l1; }
+                        if (own) { u0 = 0.5f * l0 + 0.5f * l1; u1 = l1; }
                         else {
                             u0 = l0 + a_on * (l1 - l0);
                             u1 = l1 + a_off * (l0 - l1);
@@ -921,9 +926,9 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
     // ---- root draw (prior: toymodel.py:17-27 get_blink_distn) ----------------------------------------
     unsigned x = 0u;
     if (trk) {
-        const int ai = (c.slot[0] * K + k) * 3;
-        double w1 = (double)acc[ai + 1] * exp(-(double)acc[ai + 2]) * ml.p_on;
-        double w0 = (double)acc[ai] * ml.p_off;
+        const AccRec a = acc[c.slot[0] * K + k];
+        double w1 = (double)a.u1 * exp(-a.pen) * ml.p_on;
+        double w0 = (double)a.u0 * ml.p_off;
         if (!((u_tt_ok[0] >> k) & 1u)) w1 = 0.0;
         if (!((u_tf_ok[0] >> k) & 1u)) w0 = 0.0;
         if (c.cls[u_node_pri[0]] == k) w0 = 0.0;
