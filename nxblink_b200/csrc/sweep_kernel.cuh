@@ -696,6 +696,7 @@ __device__ __forceinline__ double exp_gap(NxbXo& xo, float gsc) {
     return __longlong_as_double(__double_as_longlong(g) | (long long)(nxb_xo_next(xo) >> 3));
 }
 
+// max / min without the NaN handling of fmax / fmin (event times are never NaN)
 __device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a : b; }
 
