@@ -79,6 +79,13 @@ int nxb_device_count(void);
 /* Build device tables for one model on `device`. */
 int nxb_create(const nxb_model_desc* desc, int device, nxb_handle** out);
 int nxb_destroy(nxb_handle* h);
+/* Replace the VALUES of the model (rates, branch lengths, prior, blink rates) by those of a
+ * model of the same shape (tree, sparsity pattern of Q, classes): what an EM iteration changes
+ * (examples/p53/run-stochastic.py:154-208 builds a new model object per iteration).  Device
+ * buffers, capacity tiers, data and unit states are kept; chains may be continued (warm start)
+ * or initialised again with nxb_init_chains.  If an edge switched between zero and positive
+ * rate x length the unit states are dropped and nxb_init_chains must be called. */
+int nxb_update_model(nxb_handle* h, const nxb_model_desc* desc);
 const char* nxb_last_error(const nxb_handle* h);   /* h may be NULL: last create error */
 
 /* Per-site data constraints; replaces the `data` duck type of raoteh.py:45-52,61

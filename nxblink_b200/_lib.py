@@ -59,7 +59,7 @@ class Stats(C.Structure):
 
 # every symbol include/nxblink_b200.h declares
 EXPORTS = (
-    'nxb_device_count', 'nxb_create', 'nxb_destroy', 'nxb_last_error',
+    'nxb_device_count', 'nxb_create', 'nxb_destroy', 'nxb_update_model', 'nxb_last_error',
     'nxb_set_data', 'nxb_init_chains', 'nxb_sweep', 'nxb_summary_layout_get',
     'nxb_summary_reset', 'nxb_summary_read', 'nxb_summary_device_ptrs',
     'nxb_summarize_current', 'nxb_export_unit', 'nxb_get_stats',
@@ -101,6 +101,7 @@ def load():
     lib.nxb_last_kernel_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.nxb_last_kernel_ms_by_kind.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.nxb_profile.argtypes = [H, C.c_int32, C.c_void_p]
+    lib.nxb_update_model.argtypes = [H, C.POINTER(ModelDesc)]
     lib.nxb_expm_batched.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nxb_expm_frechet_batched.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_void_p, C.c_void_p]

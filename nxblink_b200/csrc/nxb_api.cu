@@ -714,6 +714,9 @@ struct nxb_handle {
     int profile = 0;
     int lockstep = 0;              // warps per lockstep group in tier 0 (0: independent warps)
     bool split = true;             // tier 0: primary and tolerance updates as alternating kernels
+    // shape of the model the handle was created for (nxb_update_model accepts only the same)
+    std::vector<int> shape_parent, shape_qptr, shape_qcol, shape_cls;
+    std::vector<char> shape_active;     // edge has rate > 0 and length > 0
     unsigned sync_mask = 0x3ffu;
     int gcapP = 0, gcapB = 0;
     int so_tol = 0, so_pri = 0, so_ptm = 0, so_pcode = 0, so_btm = 0, so_bcode = 0;
@@ -747,6 +750,7 @@ struct nxb_handle {
     std::string err;
 };
 
+extern "C" int nxb_destroy(nxb_handle* h);
 static std::string g_create_err;
 
 static int set_err(nxb_handle* h, int code, const std::string& msg) {
@@ -871,64 +875,20 @@ extern "C" void nxb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], 
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
-extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out) {
-    if (!d || !out) return set_err(nullptr, NXB_ERR_BAD_ARG, "null argument");
-    *out = nullptr;
-    const int N = d->n_nodes, P = d->n_states, K = d->n_classes, nnz = d->nnz, E = N - 1;
-    if (N < 2 || N > 16384) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 2 <= n_nodes <= 16384");
-    if (P < 1 || P > NXB_MAX_STATES) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 1 <= n_states <= 64");
-    if (K < 1 || K > NXB_MAX_CLASSES) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 1 <= n_classes <= 32");
-    if (!(d->rate_on > 0.0) || !(d->rate_off > 0.0))
-        return set_err(nullptr, NXB_ERR_BAD_ARG, "blink rates must be positive");
-    if (d->parent[0] != -1) return set_err(nullptr, NXB_ERR_BAD_ARG, "parent[0] must be -1 (root)");
-    for (int v = 1; v < N; ++v)
-        if (d->parent[v] < 0 || d->parent[v] >= v)
-            return set_err(nullptr, NXB_ERR_BAD_ARG, "nodes must be numbered so that parent[v] < v");
-    for (int v = 1; v < N; ++v)
-        if (!(d->blen[v] >= 0.0) || !(d->rate[v] >= 0.0))
-            return set_err(nullptr, NXB_ERR_BAD_ARG, "branch lengths and rates must be >= 0");
-    if (d->q_ptr[0] != 0 || d->q_ptr[P] != nnz) return set_err(nullptr, NXB_ERR_BAD_ARG, "bad q_ptr");
-    for (int s = 0; s < P; ++s) {
-        if (d->state_class[s] < 0 || d->state_class[s] >= K)
-            return set_err(nullptr, NXB_ERR_BAD_ARG, "state_class out of range");
-        if (d->q_ptr[s + 1] - d->q_ptr[s] > 31)
-            return set_err(nullptr, NXB_ERR_BAD_ARG, "at most 31 transitions per primary state");
-        for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i) {
-            if (d->q_col[i] < 0 || d->q_col[i] >= P || d->q_col[i] == s || !(d->q_val[i] > 0.0))
-                return set_err(nullptr, NXB_ERR_BAD_ARG, "bad primary rate matrix entry");
-        }
-    }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
-        return set_err(nullptr, NXB_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
-    if (device < 0 || device >= ndev) return set_err(nullptr, NXB_ERR_BAD_ARG, "bad device index");
-
-    nxb_handle* h = new nxb_handle();
-    h->device = device;
-    h->msg_f64 = d->msg_f64 != 0;
-    h->validate = d->validate;
-    if (getenv("NXB_SYNC_MASK")) h->sync_mask = (unsigned)strtoul(getenv("NXB_SYNC_MASK"), nullptr, 0);
-    // default: one group of up to 20 warps (measured best at the p53 shape); negative switches it off
-    h->lockstep = d->lockstep_warps == 0 ? -1 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);   // -1: automatic
-    h->split = d->split_phases >= 0;
-#define CUDA_TRY_C(call)                                                                  \
+// Everything that depends on the VALUES of the model (rates, branch lengths, prior): the model
+// blob, the scalar constants in h->ml and the table of uniformization rates.  Called by
+// nxb_create and, for a model of the same shape, by nxb_update_model (device buffers are reused).
+// sums: [0] sum of rate x length, [1] / [2] dominating Poisson means of the primary / tolerance tracks.
+#define CUDA_TRY_M(call)                                                                  \
     do {                                                                                  \
         cudaError_t e_ = (call);                                                          \
         if (e_ != cudaSuccess) {                                                          \
             set_err(nullptr, NXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
-            delete h;                                                                     \
             return NXB_ERR_CUDA;                                                          \
         }                                                                                 \
     } while (0)
-    CUDA_TRY_C(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_TRY_C(cudaGetDeviceProperties(&prop, device));
-    h->num_sms = prop.multiProcessorCount;
-    h->max_smem = (int)prop.sharedMemPerBlockOptin;
-    CUDA_TRY_C(cudaStreamCreate(&h->stream));
-    CUDA_TRY_C(cudaEventCreate(&h->ev0));
-    CUDA_TRY_C(cudaEventCreate(&h->ev1));
-
+static int build_model_tables(nxb_handle* h, const nxb_model_desc* d, double sums[3]) {
+    const int N = d->n_nodes, P = d->n_states, K = d->n_classes, nnz = d->nnz, E = N - 1;
     // ---- derived model quantities ----
     NxbModelLayout& ml = h->ml;
     memset(&ml, 0, sizeof(ml));
@@ -954,7 +914,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         ml.nslots = std::max(next, 1);
         if (ml.nslots > 32) {
             set_err(nullptr, NXB_ERR_BAD_ARG, "tree needs more than 32 live accumulators; renumber nodes depth-first");
-            delete h; return NXB_ERR_BAD_ARG;
+            return NXB_ERR_BAD_ARG;
         }
     }
     // rates: total out-rate per state with every class on, and its maximum
@@ -964,7 +924,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i) acc += d->q_val[i];
         rmax_all = std::max(rmax_all, acc);
     }
-    if (!(rmax_all > 0.0)) { set_err(nullptr, NXB_ERR_BAD_ARG, "empty rate matrix"); delete h; return NXB_ERR_BAD_ARG; }
+    if (!(rmax_all > 0.0)) { set_err(nullptr, NXB_ERR_BAD_ARG, "empty rate matrix"); return NXB_ERR_BAD_ARG; }
     ml.inv_omega_pri = 1.0 / (2.0 * rmax_all);
     const double M = std::max(d->rate_on, d->rate_off);
     ml.a_on = d->rate_on / (2.0 * M);
@@ -984,7 +944,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         memcpy(blob.data() + o, src, bytes);
         return o;
     };
-    double sum_rt = 0.0, lam_pri_sum = 0.0, lam_blk_sum = 0.0;
+    double& sum_rt = sums[0]; double& lam_pri_sum = sums[1]; double& lam_blk_sum = sums[2];
+    sum_rt = 0.0; lam_pri_sum = 0.0; lam_blk_sum = 0.0;
     {
         std::vector<int> parent(E);
         std::vector<double> tma(E), len(E), rate(E), lam_pri(E), p0_pri(E), lam_blk(E), p0_blk(E);
@@ -1002,7 +963,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             lam_blk_sum += lam_blk[e];
             if (lam_pri[e] > 600.0 || lam_blk[e] > 600.0) {
                 set_err(nullptr, NXB_ERR_BAD_ARG, "edge rate * length too large for the tabulated Poisson inversion");
-                delete h; return NXB_ERR_BAD_ARG;
+                return NXB_ERR_BAD_ARG;
             }
         }
         // ---- tables of the tolerance update first: blink_kernel stages only this prefix ----
@@ -1106,13 +1067,13 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         ml.off_stats = ml.bytes;
         ml.stats_words = 2 * E + P + 4 + K;
     }
-    CUDA_TRY_C(cudaMalloc(&h->d_blob, blob.size()));
-    CUDA_TRY_C(cudaMemcpy(h->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    if (!h->d_blob) CUDA_TRY_M(cudaMalloc(&h->d_blob, blob.size()));
+    CUDA_TRY_M(cudaMemcpy(h->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     {
         double inv_n[64];
         inv_n[0] = 0.0;
         for (int i = 1; i < 64; ++i) inv_n[i] = 1.0 / (double)i;
-        CUDA_TRY_C(cudaMemcpyToSymbol(c_inv_n, inv_n, sizeof(inv_n)));
+        CUDA_TRY_M(cudaMemcpyToSymbol(c_inv_n, inv_n, sizeof(inv_n)));
     }
     // ---- L2-resident table of uniformization rates, one entry per tolerance mask ----
     ml.table_bits = 0;
@@ -1122,18 +1083,93 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         int *dq_ptr, *dq_cls; double* dq_val;
         std::vector<int> qcls(nnz);
         for (int i = 0; i < nnz; ++i) qcls[i] = d->state_class[d->q_col[i]];
-        CUDA_TRY_C(cudaMalloc(&h->d_rmax, sizeof(double) * n_masks));
-        CUDA_TRY_C(cudaMalloc(&dq_ptr, 4 * (P + 1)));
-        CUDA_TRY_C(cudaMalloc(&dq_cls, 4 * std::max(nnz, 1)));
-        CUDA_TRY_C(cudaMalloc(&dq_val, 8 * std::max(nnz, 1)));
-        CUDA_TRY_C(cudaMemcpy(dq_ptr, d->q_ptr, 4 * (P + 1), cudaMemcpyHostToDevice));
-        CUDA_TRY_C(cudaMemcpy(dq_cls, qcls.data(), 4 * nnz, cudaMemcpyHostToDevice));
-        CUDA_TRY_C(cudaMemcpy(dq_val, d->q_val, 8 * nnz, cudaMemcpyHostToDevice));
+        if (!h->d_rmax) CUDA_TRY_M(cudaMalloc(&h->d_rmax, sizeof(double) * n_masks));
+        CUDA_TRY_M(cudaMalloc(&dq_ptr, 4 * (P + 1)));
+        CUDA_TRY_M(cudaMalloc(&dq_cls, 4 * std::max(nnz, 1)));
+        CUDA_TRY_M(cudaMalloc(&dq_val, 8 * std::max(nnz, 1)));
+        CUDA_TRY_M(cudaMemcpy(dq_ptr, d->q_ptr, 4 * (P + 1), cudaMemcpyHostToDevice));
+        CUDA_TRY_M(cudaMemcpy(dq_cls, qcls.data(), 4 * nnz, cudaMemcpyHostToDevice));
+        CUDA_TRY_M(cudaMemcpy(dq_val, d->q_val, 8 * nnz, cudaMemcpyHostToDevice));
         rmax_table_kernel<<<(n_masks + 255) / 256, 256, 0, h->stream>>>(h->d_rmax, n_masks, P, dq_ptr, dq_cls, dq_val);
-        CUDA_TRY_C(cudaGetLastError());
-        CUDA_TRY_C(cudaStreamSynchronize(h->stream));
+        CUDA_TRY_M(cudaGetLastError());
+        CUDA_TRY_M(cudaStreamSynchronize(h->stream));
         cudaFree(dq_ptr); cudaFree(dq_cls); cudaFree(dq_val);
     }
+    return NXB_OK;
+}
+
+static int check_desc(const nxb_model_desc* d) {
+    const int N = d->n_nodes, P = d->n_states, K = d->n_classes, nnz = d->nnz;
+    if (N < 2 || N > 16384) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 2 <= n_nodes <= 16384");
+    if (P < 1 || P > NXB_MAX_STATES) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 1 <= n_states <= 64");
+    if (K < 1 || K > NXB_MAX_CLASSES) return set_err(nullptr, NXB_ERR_BAD_ARG, "need 1 <= n_classes <= 32");
+    if (!(d->rate_on > 0.0) || !(d->rate_off > 0.0))
+        return set_err(nullptr, NXB_ERR_BAD_ARG, "blink rates must be positive");
+    if (d->parent[0] != -1) return set_err(nullptr, NXB_ERR_BAD_ARG, "parent[0] must be -1 (root)");
+    for (int v = 1; v < N; ++v)
+        if (d->parent[v] < 0 || d->parent[v] >= v)
+            return set_err(nullptr, NXB_ERR_BAD_ARG, "nodes must be numbered so that parent[v] < v");
+    for (int v = 1; v < N; ++v)
+        if (!(d->blen[v] >= 0.0) || !(d->rate[v] >= 0.0))
+            return set_err(nullptr, NXB_ERR_BAD_ARG, "branch lengths and rates must be >= 0");
+    if (d->q_ptr[0] != 0 || d->q_ptr[P] != nnz) return set_err(nullptr, NXB_ERR_BAD_ARG, "bad q_ptr");
+    for (int s = 0; s < P; ++s) {
+        if (d->state_class[s] < 0 || d->state_class[s] >= K)
+            return set_err(nullptr, NXB_ERR_BAD_ARG, "state_class out of range");
+        if (d->q_ptr[s + 1] - d->q_ptr[s] > 31)
+            return set_err(nullptr, NXB_ERR_BAD_ARG, "at most 31 transitions per primary state");
+        for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i) {
+            if (d->q_col[i] < 0 || d->q_col[i] >= P || d->q_col[i] == s || !(d->q_val[i] > 0.0))
+                return set_err(nullptr, NXB_ERR_BAD_ARG, "bad primary rate matrix entry");
+        }
+    }
+    return NXB_OK;
+}
+
+extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out) {
+    if (!d || !out) return set_err(nullptr, NXB_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    const int N = d->n_nodes, P = d->n_states, K = d->n_classes, nnz = d->nnz, E = N - 1;
+    { int rc = check_desc(d); if (rc) return rc; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return set_err(nullptr, NXB_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err(nullptr, NXB_ERR_BAD_ARG, "bad device index");
+
+    nxb_handle* h = new nxb_handle();
+    h->device = device;
+    h->msg_f64 = d->msg_f64 != 0;
+    h->validate = d->validate;
+    if (getenv("NXB_SYNC_MASK")) h->sync_mask = (unsigned)strtoul(getenv("NXB_SYNC_MASK"), nullptr, 0);
+    // default: one group of up to 20 warps (measured best at the p53 shape); negative switches it off
+    h->lockstep = d->lockstep_warps == 0 ? -1 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);   // -1: automatic
+    h->split = d->split_phases >= 0;
+#define CUDA_TRY_C(call)                                                                  \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            set_err(nullptr, NXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+            delete h;                                                                     \
+            return NXB_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+    CUDA_TRY_C(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY_C(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    CUDA_TRY_C(cudaStreamCreate(&h->stream));
+    CUDA_TRY_C(cudaEventCreate(&h->ev0));
+    CUDA_TRY_C(cudaEventCreate(&h->ev1));
+
+    // ---- model tables ----
+    double sums[3];
+    {
+        int rc = build_model_tables(h, d, sums);
+        if (rc) { nxb_destroy(h); return rc; }
+    }
+    NxbModelLayout& ml = h->ml;
+    const double sum_rt = sums[0], lam_pri_sum = sums[1], lam_blk_sum = sums[2];
     // ---- statistics ----
     {
         NxbSummaryLayout& sl = h->sl;
@@ -1277,7 +1313,43 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }
     }
     cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+    h->shape_parent.assign(d->parent, d->parent + N);
+    h->shape_qptr.assign(d->q_ptr, d->q_ptr + P + 1);
+    h->shape_qcol.assign(d->q_col, d->q_col + nnz);
+    h->shape_cls.assign(d->state_class, d->state_class + P);
+    h->shape_active.resize(E);
+    for (int e = 0; e < E; ++e) h->shape_active[e] = (d->blen[e + 1] > 0.0 && d->rate[e + 1] > 0.0);
     *out = h;
+    return NXB_OK;
+}
+
+extern "C" int nxb_update_model(nxb_handle* h, const nxb_model_desc* d) {
+    if (!h || !d) return set_err(h, NXB_ERR_BAD_ARG, "null argument");
+    { int rc = check_desc(d); if (rc) { h->err = g_create_err; return rc; } }
+    const int N = d->n_nodes, P = d->n_states, nnz = d->nnz, E = N - 1;
+    const NxbModelLayout& ml = h->ml;
+    if (N != ml.N || P != ml.P || d->n_classes != ml.K || nnz != ml.nnz || (d->msg_f64 != 0) != h->msg_f64 ||
+        !std::equal(d->parent, d->parent + N, h->shape_parent.begin()) ||
+        !std::equal(d->q_ptr, d->q_ptr + P + 1, h->shape_qptr.begin()) ||
+        !std::equal(d->q_col, d->q_col + nnz, h->shape_qcol.begin()) ||
+        !std::equal(d->state_class, d->state_class + P, h->shape_cls.begin()))
+        return set_err(h, NXB_ERR_BAD_ARG, "nxb_update_model: the model must have the shape the handle was created for "
+                                           "(tree, sparsity pattern of Q, classes, message type)");
+    if (d->diameter != ml.diameter) return set_err(h, NXB_ERR_BAD_ARG, "nxb_update_model: diameter changed");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    double sums[3];
+    int rc = build_model_tables(h, d, sums);
+    if (rc) { h->err = g_create_err; return rc; }
+    // Trajectories stay valid under new rates unless an edge switched between active and
+    // inactive (events on a zero-rate edge); then the chains have to be initialised again.
+    bool same_active = true;
+    for (int e = 0; e < E; ++e) {
+        const char act = (d->blen[e + 1] > 0.0 && d->rate[e + 1] > 0.0);
+        if (act != h->shape_active[e]) same_active = false;
+        h->shape_active[e] = act;
+    }
+    if (!same_active && h->d_state) { cudaFree(h->d_state); h->d_state = nullptr; h->n_units = 0; }
     return NXB_OK;
 }
 

@@ -168,19 +168,27 @@ def maximization_step(mstep, kappa, omega, A, C, G, T, blink_on, blink_off, edge
 
 
 def em_iteration(model, packed_data, params, chains=8, nburnin=10, nsamples=10, seed=0,
-        device=0, reduce_fn=None):
+        device=0, reduce_fn=None, sampler=None):
     """One EM iteration (run-stochastic.py:154-208): build the model from ``params``, run
     the E-step on the device, maximise.  ``reduce_fn(counts, dwell)`` may all-reduce the
-    statistics across ranks (nxblink_b200.distributed)."""
+    statistics across ranks (nxblink_b200.distributed).  Pass the ``sampler`` of the previous
+    iteration (returned as ``new['sampler']`` when one was given) to reuse its device buffers:
+    only the model values are replaced (``BlinkSampler.update_model``)."""
     pm0 = PackedModel(model)
     edge_to_rate = dict(zip(pm0.edges, params['edge_rates']))
     m = Model(params['kappa'], params['omega'], params['A'], params['C'], params['G'], params['T'],
             params['rate_on'], params['rate_off'], model._tree, model._root,
             model.get_edge_to_blen(), edge_to_rate, model.genetic_code)
     pm = PackedModel(m)
-    sampler = BlinkSampler(pm, device=device)
+    keep = sampler is not None
+    if keep:
+        sampler.update_model(pm)
+        sampler.reset_summary()
+    else:
+        sampler = BlinkSampler(pm, device=device)
     try:
-        sampler.set_data(packed_data)
+        if not keep or sampler.data is not packed_data:
+            sampler.set_data(packed_data)
         sampler.init_chains(chains=chains, seed=seed)
         sampler.sweep(nburnin, accumulate=False)
         sampler.sweep(nsamples, accumulate=True)
@@ -189,10 +197,13 @@ def em_iteration(model, packed_data, params, chains=8, nburnin=10, nsamples=10, 
             counts, dwell = reduce_fn(counts, dwell)
         summary = sampler.summary(counts, dwell)
     finally:
-        sampler.close()
+        if not keep:
+            sampler.close()
     mstep = MStep(pm, summary, m.genetic_code)
     new = maximization_step(mstep, params['kappa'], params['omega'], params['A'], params['C'],
             params['G'], params['T'], params['rate_on'], params['rate_off'], params['edge_rates'])
     new['summary'] = summary
     new['mstep'] = mstep
+    if keep:
+        new['sampler'] = sampler
     return new

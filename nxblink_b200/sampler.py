@@ -44,9 +44,10 @@ class BlinkSampler(object):
         self.lib = _lib.load()
         self.pm = model if isinstance(model, PackedModel) else PackedModel(model)
         self._h = C.c_void_p()
-        desc = self.pm.desc(msg_f64=msg_f64, cap_scale=cap_scale,
+        self._desc_kwargs = dict(msg_f64=msg_f64, cap_scale=cap_scale,
                 validate=validate, max_warps=max_warps, lockstep_warps=lockstep_warps,
                 split_phases=split_phases)
+        desc = self.pm.desc(**self._desc_kwargs)
         rc = self.lib.nxb_create(C.byref(desc), int(device), C.byref(self._h))
         if rc:
             msg = self.lib.nxb_last_error(None).decode()
@@ -57,6 +58,17 @@ class BlinkSampler(object):
         self.data = None
         self.chains = 0
         self.n_units = 0
+
+    def update_model(self, model):
+        """Swap in a model of the same shape with new rates / branch lengths / prior (what an EM
+        iteration changes) without rebuilding the handle; data and chains are kept (re-initialise
+        them with ``init_chains`` for the reference's behaviour, or continue them as a warm start)."""
+        pm = model if isinstance(model, PackedModel) else PackedModel(model)
+        if pm.nodes != self.pm.nodes or pm.states != self.pm.states or pm.tols != self.pm.tols:
+            raise NxbError(5, 'update_model: the model must have the same tree, states and classes')
+        desc = pm.desc(**self._desc_kwargs)
+        self._check(self.lib.nxb_update_model(self._h, C.byref(desc)))
+        self.pm = pm
 
     def _check(self, rc):
         if rc:

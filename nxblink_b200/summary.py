@@ -65,13 +65,43 @@ class Summary(object):
         # unambiguous primitives behind root_xon_count
         self.root_on_total = 0
         self.root_xon_intended = 0
-        self.edge_to_pri_trans = {}
+        self._pri_trans = {}
         self.edge_to_off_xon_trans = defaultdict(int)
         self.edge_to_xon_off_trans = defaultdict(int)
-        self.edge_to_pri_dwell = {}
+        self._pri_dwell = {}
+        self._lazy = None
         self.edge_to_off_xon_dwell = defaultdict(float)
         self.edge_to_xon_off_dwell = defaultdict(float)
         self.flat = None
+
+    def _unfold(self):
+        pm, pri_trans, pri_dwell = self._lazy
+        self._lazy = None
+        rows, cols = np.nonzero((pri_trans != 0) | (pri_dwell > 0))
+        for edge in pm.edges:
+            self._pri_trans[edge] = WeightGraph()
+            self._pri_dwell[edge] = WeightGraph()
+        for e, i in zip(rows.tolist(), cols.tolist()):
+            edge = pm.edges[e]
+            sa, sb = pm.states[pm.q_row[i]], pm.states[pm.q_col[i]]
+            if pri_trans[e, i]:
+                self._pri_trans[edge].add_edge(sa, sb, int(pri_trans[e, i]))
+            if pri_dwell[e, i] > 0:
+                self._pri_dwell[edge].add_edge(sa, sb, float(pri_dwell[e, i]))
+
+    @property
+    def edge_to_pri_trans(self):
+        """{edge: graph of primary transition counts} (summary.py:102)."""
+        if self._lazy is not None:
+            self._unfold()
+        return self._pri_trans
+
+    @property
+    def edge_to_pri_dwell(self):
+        """{edge: graph of primary dwell times by allowed transition} (summary.py:107)."""
+        if self._lazy is not None:
+            self._unfold()
+        return self._pri_dwell
 
     @classmethod
     def from_device(cls, pm, layout, counts, dwell, Q_primary=None):
@@ -113,16 +143,9 @@ class Summary(object):
         self.flat = dict(pri_trans=pri_trans, pri_dwell=pri_dwell, off_on=off_on,
                 on_off=on_off, off_xon_dwell=off_xon_dwell, xon_off_dwell=xon_off_dwell,
                 root_pri=root_pri, T=T, Doff=Doff)
+        # the per-edge tables of the reference (nx.DiGraph-like) are unfolded on first access
+        self._lazy = (pm, pri_trans, pri_dwell)
         for e, edge in enumerate(pm.edges):
-            gt, gd = WeightGraph(), WeightGraph()
-            for i in range(nnz):
-                sa, sb = pm.states[pm.q_row[i]], pm.states[pm.q_col[i]]
-                if pri_trans[e, i]:
-                    gt.add_edge(sa, sb, int(pri_trans[e, i]))
-                if pri_dwell[e, i] > 0:
-                    gd.add_edge(sa, sb, float(pri_dwell[e, i]))
-            self.edge_to_pri_trans[edge] = gt
-            self.edge_to_pri_dwell[edge] = gd
             self.edge_to_off_xon_trans[edge] = int(off_on[e])
             self.edge_to_xon_off_trans[edge] = int(on_off[e])
             self.edge_to_off_xon_dwell[edge] = float(off_xon_dwell[e])

@@ -45,3 +45,69 @@ def test_em_iteration_p53_shape(nb):
     x_cf[8:] = np.log(np.maximum(cf, 1e-12))
     assert abs(mstep.neg_ll(x_cf) - new['neg_ll']) < 1e-4 * abs(new['neg_ll'])
     assert 0.2 < new['rate_on'] < 10 and 0.05 < new['rate_off'] < 5
+
+
+def test_update_model_equals_a_fresh_handle(nb):
+    """nxb_update_model swaps the model values in place: after re-initialising the chains the
+    sweep gives exactly what a handle created for the new model gives (same seed), and the kept
+    chains can also be continued under the new rates (warm start) with every invariant holding."""
+    m = p53.p53_model()
+    pm = packing.PackedModel(m)
+    leaf = pm.node_index[m.name_to_leaf['Has']]
+    ls, tt, tf = p53.synthetic_alignment(pm, 16, seed=2, reference_leaf=leaf)
+    data = packing.pack_alignment(pm, ls, tt, tf)
+    prm = p53.jeff_params()
+    edge_to_rate = dict((e, 0.7 * r + 0.01) for e, r in m.get_edge_to_rate().items()
+            if True)
+    edge_to_rate = dict((e, (r if m.get_edge_to_rate()[e] > 0 else 0.0)) for e, r in edge_to_rate.items())
+    m2 = p53.Model(1.3 * prm['kappa'], 0.8 * prm['omega'], prm['A'], prm['C'], prm['G'], prm['T'],
+            1.1, 0.7, m._tree, m._root, m.get_edge_to_blen(), edge_to_rate, m.genetic_code)
+    pm2 = packing.PackedModel(m2)
+
+    def run(s):
+        s.set_data(data)
+        s.init_chains(chains=8, seed=11)
+        s.sweep(3, accumulate=False)
+        s.reset_summary()
+        s.sweep(4, accumulate=True)
+        return s.read_summary()
+
+    fresh = nb.BlinkSampler(pm2, validate=True)
+    c_fresh, d_fresh = run(fresh)
+    fresh.close()
+    s = nb.BlinkSampler(pm, validate=True)
+    run(s)
+    s.update_model(pm2)
+    c_upd, d_upd = run(s)
+    assert (c_fresh == c_upd).all()
+    assert_allclose(d_fresh, d_upd, rtol=1e-11, atol=1e-9)
+    # warm start: continue the chains under the first model's rates again
+    s.update_model(pm)
+    s.sweep(3, accumulate=True)                 # validate=True checks every invariant
+    assert s.read_summary()[0][s.layout.c_nsamples] == 16 * 8 * 7
+    # a model of another shape is refused
+    with pytest.raises(Exception):
+        s.update_model(packing.PackedModel(__import__('nxblink_b200').toymodel.BlinkModelA))
+    s.close()
+
+
+def test_em_iterations_reuse_the_sampler(nb):
+    m = p53.p53_model()
+    pm = packing.PackedModel(m)
+    leaf = pm.node_index[m.name_to_leaf['Has']]
+    ls, tt, tf = p53.synthetic_alignment(pm, 32, seed=4, reference_leaf=leaf)
+    data = packing.pack_alignment(pm, ls, tt, tf)
+    prm = p53.jeff_params()
+    params = dict(kappa=prm['kappa'], omega=prm['omega'], A=prm['A'], C=prm['C'], G=prm['G'],
+            T=prm['T'], rate_on=1.5, rate_off=0.5, edge_rates=np.maximum(pm.rate[1:], 1e-6))
+    fresh = p53em.em_iteration(m, data, params, chains=4, nburnin=4, nsamples=4, seed=9)
+    sampler = nb.BlinkSampler(pm)
+    first = p53em.em_iteration(m, data, params, chains=4, nburnin=4, nsamples=4, seed=9, sampler=sampler)
+    assert first['sampler'] is sampler
+    # (dwell sums are floating-point atomics: equal to ~1e-12, the optimiser amplifies that)
+    assert_allclose(first['neg_ll'], fresh['neg_ll'], rtol=1e-5)
+    keys = ('kappa', 'omega', 'A', 'C', 'G', 'T', 'rate_on', 'rate_off', 'edge_rates')
+    second = p53em.em_iteration(m, data, dict((k, first[k]) for k in keys), chains=4, nburnin=4,
+            nsamples=4, seed=10, sampler=sampler)
+    assert second['summary'].nsamples == 32 * 4 * 4 and np.isfinite(second['neg_ll'])
+    sampler.close()
