@@ -17,7 +17,7 @@
 namespace nxb {
 
 // ---------------------------------------------------------------------------
-// persistent sweep kernel: one CTA per SM, one warp per unit
+// persistent sweep kernel: one CTA per SM, one warp per unit (primary update; fused form: both updates)
 // ---------------------------------------------------------------------------
 // model blob -> shared memory, statistic partials zeroed, model-level fields of the context
 __device__ __forceinline__ void cta_prologue(Ctx& c, const NxbSweepParams& p, int tid, int lane) {
@@ -822,7 +822,7 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
 
 // Warps per lockstep group.  Several small groups per CTA drift out of phase, so the walks of
 // one group's tolerance update (few, fully populated warps) overlap another group's primary
-// update; measured on the p53 shape with 20 warps: 5 -> 11.8, 10 -> 11.6, 4 -> 11.3, 20 -> 11.1
+// update; measured for the FUSED kernel on the p53 shape with 20 warps: 5 -> 11.8, 10 -> 11.6, 4 -> 11.3, 20 -> 11.1
 // M unit-sweeps/s.  Automatic choice: 5, 4 or 6, whichever leaves the fewest warps unused.
 static int group_warps_for(const nxb_handle* h, int warps) {
     if (h->lockstep == 0 || warps < 2) return 1;
@@ -1141,7 +1141,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     h->msg_f64 = d->msg_f64 != 0;
     h->validate = d->validate;
     if (getenv("NXB_SYNC_MASK")) h->sync_mask = (unsigned)strtoul(getenv("NXB_SYNC_MASK"), nullptr, 0);
-    // default: one group of up to 20 warps (measured best at the p53 shape); negative switches it off
+    // 0: automatic group size (group_warps_for / run_split); negative switches lockstep off
     h->lockstep = d->lockstep_warps == 0 ? -1 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);   // -1: automatic
     h->split = d->split_phases >= 0;
 #define CUDA_TRY_C(call)                                                                  \

@@ -1,4 +1,5 @@
-// The Rao-Teh uniformization Gibbs sweep of the blink model, one warp per unit.
+// The Rao-Teh uniformization Gibbs sweep of the blink model: device functions of the primary
+// update (one warp per unit) and of the tolerance updates (one lane per (unit, track)).
 //
 // Replaces, for a batch of independent (site, chain) units, the body of
 // nxblink/raoteh.py:392-435 (_gen_samples) and everything it calls:
@@ -9,18 +10,19 @@
 //   nxblink/summary.py:190-243       Summary.on_sample
 // and nxblink/raoteh.py:187-361 (init_tracks) in `init` mode.
 //
-// B200 mapping:
-//   * persistent grid, one CTA per SM, W warps per CTA, one warp per unit; the
-//     unit's whole trajectory lives in shared memory for the duration of its sweeps;
+// B200 mapping (the kernels themselves are in nxb_api.cu):
+//   * persistent grids, one CTA per SM; a unit's trajectory is staged in shared memory for the
+//     phase (split form: primary-only sweep_kernel, then blink_kernel) or for all requested
+//     sweeps (fused sweep_kernel: capacity tiers, split_phases < 0);
 //   * primary update: lanes over edges for candidate generation/thinning, lanes over
 //     the (<=64) primary states for the chunk-tree FFBS mat-vecs;
 //   * tolerance updates: the K tracks are conditionally independent given the primary
 //     track (chunking.py:39-107 reads only the primary track), so all K are updated
-//     concurrently, one lane per track, edge-synchronously;
+//     concurrently, every lane walking one track of one unit at its own pace;
 //   * candidate events are drawn by thinning one dominating Poisson process per
-//     (track, edge) whose exp(-lambda) is tabulated per edge -- no transcendental in the
-//     candidate path; the uniformization rate 2*max_s(rate) of poisson.py:88-90 is a
-//     table lookup in an L2-resident 2^K-entry table;
+//     (track, edge): tabulated exp(-lambda) and uniform times for the primary track,
+//     exponential gaps inside the walk for the tolerance tracks; the uniformization rate
+//     2*max_s(rate) of poisson.py:88-90 is a lookup in an L2-resident 2^K-entry table;
 //   * sufficient statistics are reduced on device (shared-memory partials per CTA,
 //     fp64/u64 atomics to L2 for the big tables).
 #pragma once
@@ -682,7 +684,7 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 }
 
 // ---------------------------------------------------------------------------
-// TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, lane k = track k
+// TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, one lane per (unit, track)
 // ---------------------------------------------------------------------------
 // Exponential gap of the dominating Poisson process, mean gsc / ln 2 (time units).  The
 // logarithm is taken in f32 (23-bit uniform); a second word spreads the result over the f64 grid
