@@ -135,6 +135,8 @@ def run_reference_arm(args, rank):
 # ---------------------------------------------------------------------------
 
 class ClockSampler(object):
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 10 ms from a thread
+    (the `nvidia-smi` query line of B200_PROFILING.md as a fallback when pynvml is missing)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
@@ -143,12 +145,34 @@ class ClockSampler(object):
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []         # (sm MHz, reasons bit mask)
+        self.stop_flag = False
+        self.max_mhz = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.gpu
+            if vis:
+                ids = [x for x in vis.split(',') if x.strip() != '']
+                if self.gpu < len(ids) and ids[self.gpu].strip().isdigit():
+                    idx = int(ids[self.gpu])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll)
+            self.thread.daemon = True
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                     ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                        '--format=csv,noheader,nounits', '-lms', '200'],
+                        '--format=csv,noheader,nounits', '-lms', '50'],
                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
             self.thread = threading.Thread(target=self._pump)
             self.thread.daemon = True
@@ -156,11 +180,39 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        get_reasons = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                getattr(n, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+        while not self.stop_flag:
+            try:
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)),
+                    int(get_reasons(self.handle))))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            n = self.nvml
+            names = (('hw_slowdown', 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+                    ('hw_thermal_slowdown', 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                    ('sw_thermal_slowdown', 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+                    ('sw_power_cap', 'nvmlClocksThrottleReasonSwPowerCap', 0x4))
+            reasons = set()
+            for _, mask in self.samples:
+                for name, attr, default in names:
+                    if mask & int(getattr(n, attr, default)):
+                        reasons.add(name)
+            sm = [x for x, _ in self.samples]
+            return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.max_mhz,
+                    'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvml, 10 ms period'}
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -184,7 +236,7 @@ class ClockSampler(object):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': float(np.max(mx)) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi -lms 50'}
 
 
 # ---------------------------------------------------------------------------
