@@ -501,7 +501,11 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         }
         if (__any_sync(FULL, bad)) { fail(c, NXB_ERR_ZERO_RATE, 0); return RC_ERROR; }
     }
-    for (int i = lane; i < (F + 1) * NXB_PPAD; i += 32) msg[i] = (MSG)1.0;
+    // A chunk message is the product of what its child chunks push up; cstate[] (free until the
+    // downward pass) flags the chunks that have received a factor, so that the first child
+    // assigns instead of multiplying and an untouched chunk reads as all ones -- no
+    // initialisation pass over the L2 scratch and no read of never-written messages.
+    for (int j = lane; j <= F; j += 32) cstate[j] = 0;
     __syncwarp();
     const SPtr<const unsigned short> ell_info = {c.ell_info};
     const SPtr<const MSG> ell_q = {c.ell_q};
@@ -515,11 +519,12 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         const MSG inv = finv[j];
         MSG* mc = msg + ci * NXB_PPAD;
         MSG* mp = msg + pi_ * NXB_PPAD;
+        const bool cinit = cstate[ci] != 0, pinit = cstate[pi_] != 0;
         if (__popcll(allow) == 1) {
             // One feasible state o in the child chunk (it holds an observed leaf): the message is
             // one-hot, so P . L is column o of the uniformized matrix -- a lookup, not a mat-vec.
             const int o = __ffsll((long long)allow) - 1;
-            if (!((MSG)mc[o] > (MSG)0)) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
+            if (cinit && !((MSG)mc[o] > (MSG)0)) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
             MSG qo = 0;
             if (lane < W) {
                 const unsigned info = ell_info[lane * NXB_PPAD + o];
@@ -528,17 +533,18 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) qo += __shfl_xor_sync(FULL, qo, d);     // R_o(mask)
             const MSG c0 = (lane == o) ? (MSG)1 - inv * qo : inv * qdt[o * NXB_PPAD + lane];
-            mp[lane] *= c0;
+            mp[lane] = pinit ? mp[lane] * c0 : c0;
             if (two) {
                 const MSG c1 = (lane + 32 == o) ? (MSG)1 - inv * qo : inv * qdt[o * NXB_PPAD + lane + 32];
-                mp[lane + 32] *= c1;
+                mp[lane + 32] = pinit ? mp[lane + 32] * c1 : c1;
             }
+            if (lane == 0) cstate[pi_] = 1;
             __syncwarp();
             continue;
         }
         // each lane reads back exactly the two entries it wrote itself (program order)
-        MSG v0 = ((allow >> lane) & 1ull) ? mc[lane] : (MSG)0;
-        MSG v1 = (two && ((allow >> (lane + 32)) & 1ull)) ? mc[lane + 32] : (MSG)0;
+        MSG v0 = ((allow >> lane) & 1ull) ? (cinit ? mc[lane] : (MSG)1) : (MSG)0;
+        MSG v1 = (two && ((allow >> (lane + 32)) & 1ull)) ? (cinit ? mc[lane + 32] : (MSG)1) : (MSG)0;
         MSG mx = v0 > v1 ? v0 : v1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { MSG y = __shfl_xor_sync(FULL, mx, o); mx = y > mx ? y : mx; }
@@ -566,8 +572,15 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
                 am1 += q1 * srow[i1 & 0xffu];
             }
         }
-        mp[lane] *= v0 + inv * (am0 - aq0 * v0);
-        if (two) mp[lane + 32] *= v1 + inv * (am1 - aq1 * v1);
+        {
+            const MSG f0 = v0 + inv * (am0 - aq0 * v0);
+            mp[lane] = pinit ? mp[lane] * f0 : f0;
+            if (two) {
+                const MSG f1 = v1 + inv * (am1 - aq1 * v1);
+                mp[lane + 32] = pinit ? mp[lane + 32] * f1 : f1;
+            }
+        }
+        if (lane == 0) cstate[pi_] = 1;
         __syncwarp();
     }
     tick(c, T_P3);
@@ -575,9 +588,11 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     // ---- P4: root draw and downward sampling ----------------------------------------------
     {
         const unsigned long long allow = callow[0];
-        double w0 = (lane < P && ((allow >> lane) & 1ull)) ? (double)msg[lane] * c.pi[lane] : 0.0;
+        const bool rinit = cstate[0] != 0;        // false only when there is no event at all
+        double w0 = (lane < P && ((allow >> lane) & 1ull)) ? (rinit ? (double)msg[lane] : 1.0) * c.pi[lane] : 0.0;
         double w1 = (lane + 32 < P && ((allow >> (lane + 32)) & 1ull))
-                    ? (double)msg[lane + 32] * c.pi[lane + 32] : 0.0;
+                    ? (rinit ? (double)msg[lane + 32] : 1.0) * c.pi[lane + 32] : 0.0;
+        __syncwarp();
         int s0 = warp_sample64(w0, w1, fu[0], lane);
         if (s0 < 0) { fail(c, NXB_ERR_INFEASIBLE, -1); return RC_ERROR; }
         if (lane == 0) cstate[0] = (unsigned char)s0;
