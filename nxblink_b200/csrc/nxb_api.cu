@@ -12,7 +12,7 @@
 #include "sweep_kernel.cuh"
 
 #define NXB_MAX_THREADS 640
-#define NXB_BLINK_THREADS 736      /* register cap 88; 25 warps at 72 registers measured slower (spills) */
+#define NXB_BLINK_THREADS 800      /* 25 warps at 72 registers: 40 units x 20 tracks per CTA at the p53 shape */
 
 namespace nxb {
 
@@ -304,7 +304,6 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
         c.bcode.off = c.wbase + wl.off_bcode;
         c.poff.off = c.wbase + wl.off_poff;
         c.tmpa.off = c.wbase + wl.off_tmpa;
-        c.tt_ok.off = c.wbase + wl.off_dtt; c.tf_ok.off = c.wbase + wl.off_dtf;
     };
     while (true) {
         if (tid == 0) s_batch[0] = atomicAdd(p.work_counter, 1ull);
@@ -318,6 +317,7 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
             const long long widx = w0 + ui;
             bool active = false, accum = false;
             SPtr<int> uhdr = {c.wbase + wl.off_uhdr};
+            const unsigned *g_tt = nullptr, *g_tf = nullptr, *g_bcode = nullptr;
             c.nP = 0; c.nB = 0; c.unit = 0; c.unit32 = 0u; c.sweep = 0u;
             if (widx < n_work) {
                 const long long u = p.unit_list ? (long long)p.unit_list[widx] : widx;
@@ -332,35 +332,30 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
                         c.nP = hdr.n_pri; c.nB = hdr.n_blk; c.sweep = hdr.sweeps_done;
                         accum = hdr.sweeps_done >= p.accum_from;
                         const long long site = u / p.chains;
-                        const unsigned* g_tt = p.tol_true_ok + site * N;
-                        const unsigned* g_tf = p.tol_false_ok + site * N;
-                        unsigned* d_tt = sm_ptr<unsigned>(c.wbase + wl.off_dtt);
-                        unsigned* d_tf = sm_ptr<unsigned>(c.wbase + wl.off_dtf);
+                        g_tt = p.tol_true_ok + site * N;
+                        g_tf = p.tol_false_ok + site * N;
+                        g_bcode = (const unsigned*)(slab + p.so_bcode);
                         const unsigned* g_tol = (const unsigned*)(slab + p.so_tol);
                         const unsigned* g_npri = (const unsigned*)(slab + p.so_pri);
-                        for (int v = lane; v < N; v += 32) {
-                            d_tt[v] = g_tt[v]; d_tf[v] = g_tf[v];
-                            c.node_tol[v] = __ldcs(g_tol + v);
-                        }
+                        for (int v = lane; v < N; v += 32) c.node_tol[v] = __ldcs(g_tol + v);
                         for (int v = lane; v < (N + 3) / 4; v += 32) sm_ptr<unsigned>(c.node_pri.off)[v] = __ldcs(g_npri + v);
                         const double* g_ptm = (const double*)(slab + p.so_ptm);
                         const unsigned* g_pcode = (const unsigned*)(slab + p.so_pcode);
                         for (int i = lane; i < c.nP; i += 32) { c.ptm[i] = __ldcs(g_ptm + i); c.pcode[i] = __ldcs(g_pcode + i); }
                         const double* g_btm = (const double*)(slab + p.so_btm);
-                        const unsigned* g_bcode = (const unsigned*)(slab + p.so_bcode);
-                        for (int i = lane; i < c.nB; i += 32) { c.btm[i] = __ldcs(g_btm + i); c.bcode[i] = __ldcs(g_bcode + i); }
+                        for (int i = lane; i < c.nB; i += 32) c.btm[i] = __ldcs(g_btm + i);
                         __syncwarp();
                     }
                 }
             }
             tick(c, T_LOAD);
-            blink_setup(c, accum, active);
+            blink_setup<true>(c, accum, active, g_tt, g_tf, g_bcode);
             if (lane == 0) uhdr[7] = (int)c.unit;
             tick(c, T_B0);
         }
         __syncthreads();
         // ---- one (unit, track) job per lane ----
-        blink_job(c, tid, U * K, (unsigned)p.smem_warp0, gb0);
+        blink_job<true>(c, tid, U * K, (unsigned)p.smem_warp0, gb0);
         __syncthreads();
         tick(c, T_BW);          // (waiting for the slowest lane of the CTA is booked here)
         // ---- write the units back ----
@@ -372,23 +367,16 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
             c.unit = (long long)uhdr[7];
             const bool accum = uhdr[6] != 0;
             unsigned char* slab = p.state + c.unit * p.state_stride;
-            int rc = blink_finish(c, accum);
+            int rc = blink_finish<true>(c, accum);          // new blink list written to the slab
             tick(c, T_BW);
             if (rc == RC_ERROR) continue;
-            const bool spilled = (rc == RC_DEFER);
-            if (!spilled && c.nB > p.gcapB) { fail(c, NXB_ERR_STATE_CAP, c.nB); continue; }
             NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;
             hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
-            hdr.n_blk = (uint16_t)(spilled ? -c.nB : c.nB);
+            hdr.n_blk = (uint16_t)c.nB;
             __syncwarp();
             if (lane == 0) *(NxbUnitHeader*)slab = hdr;
             unsigned* g_tol = (unsigned*)(slab + p.so_tol);
             for (int v = lane; v < N; v += 32) __stcs(g_tol + v, c.node_tol[v]);
-            if (!spilled) {
-                double* g_btm = (double*)(slab + p.so_btm);
-                unsigned* g_bcode = (unsigned*)(slab + p.so_bcode);
-                for (int i = lane; i < c.nB; i += 32) { __stcs(g_btm + i, c.btm[i]); __stcs(g_bcode + i, c.bcode[i]); }
-            }
             __syncwarp();
             tick(c, T_STORE);
         }
@@ -788,7 +776,7 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     wl->off_tmpa = take(4 * (E + 1), 4);
     wl->off_tmpb = take(4 * (E + 1), 4);
     wl->off_tmpc = take(4 * (E + 1), 4);
-    wl->off_uhdr = take(4 * (8 + 32), 4);
+    wl->off_uhdr = take(4 * (10 + 32), 4);
     const int scratch0 = align_up(o, 16);
     // primary-phase scratch
     o = scratch0;
@@ -847,15 +835,13 @@ static void build_blink_layout(const NxbModelLayout& ml, int capP, int capB, Nxb
     wl->off_node_tol = take(4 * N, 4);
     wl->off_node_pri = take(align_up(N, 4), 4);
     wl->off_pcode = take(4 * capP, 4);
-    wl->off_bcode = take(4 * capB, 4);
-    wl->off_dtt = take(4 * N, 4);
-    wl->off_dtf = take(4 * N, 4);
+    wl->off_bcode = take(2 * capB, 2);               // edges only (u16)
     wl->off_poff = take(4 * (E + 1), 4);
-    wl->off_tmpa = take(4 * (E + 1), 4);
-    wl->off_uhdr = take(4 * (8 + 32), 4);
+    wl->off_uhdr = take(4 * (10 + 32), 4);
     wl->off_toff = take(4 * (K + 1), 4);
     wl->off_acc = take(16 * K * ml.nslots, 16);
     wl->off_newtol = take(4 * N, 4);
+    wl->off_tmpa = wl->off_newtol;                   // scratch of build_poff, dead before newtol is zeroed
     wl->off_nrec = take(16 * E, 16);
     wl->bytes = align_up(o, 16);
 }

@@ -28,6 +28,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "nxb_types.h"
 #include "philox.cuh"
 
@@ -737,8 +738,13 @@ __device__ __forceinline__ float pow2_rescale_f(float m) {
 
 // ---- S0 (the warp that owns the unit): index of the primary events, offsets of the retained
 // events per track, and the unit header that the lane jobs of other warps read
-//   uhdr: [0] active [2] nB [3] unit32 [4] bad [5] sweep [6] accumulate, [8 + k] survivors of track k
-__device__ __forceinline__ void blink_setup(Ctx& c, bool accumulate, bool active) {
+//   uhdr: [0] active [2] nB [3] unit32 [4] bad [5] sweep [6] accumulate [8] / [9] data masks of the
+//   root (tolerance may be ON / OFF), [10 + k] survivors | live events << 16 of track k
+// SPLIT (blink_kernel): the data masks and the codes of the retained events are read straight from
+// global memory (tt, tf, g_bcode); shared memory keeps only the edge (u16) of every retained event.
+template <bool SPLIT>
+__device__ __forceinline__ void blink_setup(Ctx& c, bool accumulate, bool active,
+        const unsigned* tt, const unsigned* tf, const unsigned* g_bcode) {
     const NxbWarpLayout& wl = c.p->wl;
     const int N = c.N, K = c.K, lane = c.lane;
     const SPtr<int> uhdr_own = {c.wbase + wl.off_uhdr};
@@ -751,7 +757,16 @@ __device__ __forceinline__ void blink_setup(Ctx& c, bool accumulate, bool active
         if (lane <= K) toff_own[lane] = 0;
         if (K == 32 && lane == 0) toff_own[32] = 0;
         __syncwarp();
-        for (int i = lane; i < c.nB; i += 32) atomicAdd(&toff_own[(c.bcode[i] >> 16) & 0xffu], 1);
+        if (SPLIT) {
+            unsigned short* bedge = sm_ptr<unsigned short>(c.bcode.off);
+            for (int i = lane; i < c.nB; i += 32) {
+                const unsigned code = __ldcs(g_bcode + i);
+                bedge[i] = (unsigned short)(code & 0xffffu);
+                atomicAdd(&toff_own[(code >> 16) & 0xffu], 1);
+            }
+        } else {
+            for (int i = lane; i < c.nB; i += 32) atomicAdd(&toff_own[(c.bcode[i] >> 16) & 0xffu], 1);
+        }
         __syncwarp();
         int total;
         const int cnt = lane < K ? toff_own[lane] : 0;
@@ -765,12 +780,13 @@ __device__ __forceinline__ void blink_setup(Ctx& c, bool accumulate, bool active
         // primary state of the lower node, and the index of the edge's first primary event
         const SPtr<uint4> nrec_own = {c.wbase + wl.off_nrec};
         for (int e = lane; e < c.E; e += 32)
-            nrec_own[e] = make_uint4(c.tt_ok[e + 1], c.tf_ok[e + 1], c.node_tol[e + 1],
+            nrec_own[e] = make_uint4(tt[e + 1], tf[e + 1], c.node_tol[e + 1],
                                      (unsigned)c.node_pri[e + 1] | ((unsigned)c.poff[e] << 8));
     }
     if (lane == 0) {
         uhdr_own[0] = active ? 1 : 0; uhdr_own[2] = c.nB; uhdr_own[3] = (int)c.unit32; uhdr_own[4] = 0;
         uhdr_own[5] = (int)c.sweep; uhdr_own[6] = accumulate ? 1 : 0;
+        if (active) { uhdr_own[8] = (int)tt[0]; uhdr_own[9] = (int)tf[0]; }
     }
     __syncwarp();
 }
@@ -780,6 +796,7 @@ __device__ __forceinline__ void blink_setup(Ctx& c, bool accumulate, bool active
 // CTA's shared memory (regions ub0 + u * wl.bytes, global scratch gb0 + u * gscratch_stride), so
 // that every lane of the busy warps walks a track; with lane = track only K of 32 lanes would
 // (20 of 32 at the p53 shape).
+template <bool SPLIT>
 __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned ub0, unsigned char* gb0) {
     const NxbSweepParams& p = *c.p;
     const NxbWarpLayout& wl = p.wl;
@@ -806,8 +823,8 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
     const SPtr<double> u_ptm = {ub + wl.off_ptm};
     const SPtr<unsigned> u_pcode = {ub + wl.off_pcode};
     const SPtr<double> u_btm = {ub + wl.off_btm};
-    const SPtr<unsigned> u_bcode = {ub + wl.off_bcode};
-    const SPtr<const unsigned> u_tt_ok = {ub + wl.off_dtt}, u_tf_ok = {ub + wl.off_dtf};
+    typedef typename std::conditional<SPLIT, unsigned short, unsigned>::type BCode;   // edge in the low 16 bits
+    const SPtr<BCode> u_bcode = {ub + wl.off_bcode};
 
     const bool trk = has_job && uhdr[0] != 0;
     const bool accum_u = trk && uhdr[6] != 0;
@@ -947,8 +964,8 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
         const AccRec a = acc[c.slot[0] * K + k];
         double w1 = (double)a.u1 * exp(-a.pen) * ml.p_on;
         double w0 = (double)a.u0 * ml.p_off;
-        if (!((u_tt_ok[0] >> k) & 1u)) w1 = 0.0;
-        if (!((u_tf_ok[0] >> k) & 1u)) w0 = 0.0;
+        if (!(((unsigned)uhdr[8] >> k) & 1u)) w1 = 0.0;
+        if (!(((unsigned)uhdr[9] >> k) & 1u)) w0 = 0.0;
         if (c.cls[u_node_pri[0]] == k) w0 = 0.0;
         if (!(w0 + w1 > 0.0)) bad = 1;
         x = (nxb_u32(nxb_xo_next(xo)) * (w0 + w1) < w1) ? 1u : 0u;
@@ -1029,13 +1046,15 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
         }
     }
     if (trk) {
-        uhdr[8 + k] = (cnt - 1 - wtop) | (cnt << 16);   // survivors of this track | live events
+        uhdr[10 + k] = (cnt - 1 - wtop) | (cnt << 16);   // survivors of this track | live events
         if (bad) atomicOr(&uhdr[4], bad);
     }
     tick(c, T_B2);
 }
 
 // ---- S3 (the warp that owns the unit): write back the new retained blink events
+// SPLIT: the new list goes straight to the unit's slab (the shared-memory copy is not needed again).
+template <bool SPLIT>
 __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
     const NxbSweepParams& p = *c.p;
     const NxbWarpLayout& wl = p.wl;
@@ -1050,7 +1069,7 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         if (flags & 1) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
     }
     LiveEv* cev_own = (LiveEv*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
-    const int packed = (lane < K) ? uhdr_own[8 + lane] : 0;
+    const int packed = (lane < K) ? uhdr_own[10 + lane] : 0;
     const int n_mine = packed & 0xffff, n_live = packed >> 16;
     int total;
     int dst = warp_excl_scan(n_mine, lane, total);
@@ -1063,7 +1082,7 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         atomicAdd(&c.s_root_misc[2], 1ull);
     }
     double* obtm = c.btm.ptr(); unsigned* obcode = c.bcode.ptr();
-    const bool spill = total > wl.capB;
+    const bool spill = SPLIT || total > wl.capB;
     if (spill) {
         // The sweep is complete and its statistics are booked; only the shared-memory
         // arrays are too small.  Spill the new blink list straight to the HBM slab and
@@ -1081,7 +1100,7 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
     }
     __syncwarp();
     tick(c, T_BW);
-    if (spill) { c.nB = -total; return RC_DEFER; }
+    if (spill && !SPLIT) { c.nB = -total; return RC_DEFER; }
     c.nB = total;
     return RC_OK;
 }
@@ -1091,14 +1110,14 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
 // then carry the group's (unit, track) jobs, then write their own units back.
 __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active) {
     phase_sync(c);
-    blink_setup(c, accumulate, active);
+    blink_setup<false>(c, accumulate, active, sm_ptr<const unsigned>(c.tt_ok.off), sm_ptr<const unsigned>(c.tf_ok.off), nullptr);
     tick(c, T_B0);
     phase_sync(c);            // (a named barrier orders shared memory across the group)
     const int GW = c.bar_threads >> 5;                 // 1 when the warps run independently
-    blink_job(c, c.wing * 32 + c.lane, GW * c.K, c.gwbase, c.ggbase);
+    blink_job<false>(c, c.wing * 32 + c.lane, GW * c.K, c.gwbase, c.ggbase);
     phase_sync(c);
     if (!active) return RC_OK;
-    return blink_finish(c, accumulate);
+    return blink_finish<false>(c, accumulate);
 }
 
 // ---------------------------------------------------------------------------

@@ -31,6 +31,7 @@ s.profile(True)
 for r in range(a.reps):
     t0 = time.time(); s.sweep(a.sweeps, accumulate=True); dt = time.time() - t0
     ms, nl = s.last_kernel_ms()
+    print('   by kernel:', dict((k, round(v[0], 3)) for k, v in s.last_kernel_ms_by_kind().items() if v[1]))
     n = a.sites * a.chains * a.sweeps
     print('sweep x%d: wall %.3fs kernel %.2f ms (%d launches) -> %.3e unit-sweeps/s (kernel)' % (a.sweeps, dt, ms, nl, n / (ms * 1e-3)))
 prof = s.profile(False); tot = sum(prof.values()) or 1
