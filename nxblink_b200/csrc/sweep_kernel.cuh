@@ -702,16 +702,17 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 // ---------------------------------------------------------------------------
 // TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, one lane per (unit, track)
 // ---------------------------------------------------------------------------
-// Exponential gap of the dominating Poisson process, mean gsc / ln 2 (time units).  The
-// logarithm is taken in f32 (23-bit uniform); a second word spreads the result over the f64 grid
-// (uniformly within the f32 ulp) so that event times never tie.
-__device__ __forceinline__ double exp_gap(NxbXo& xo, float gsc) {
+// Exponential gap of the dominating Poisson process, mean gsc / ln 2 (time units).  The logarithm
+// is taken in f32 (23-bit uniform).  As an f64 the value has 29 zero low mantissa bits: the track
+// id goes there, so that events of DIFFERENT tracks never share a time; a candidate that ties with
+// a retained event of its own track (both sit on the f32 grid below the same edge end, ~1e-6 per
+// unit-sweep) is dropped by the walk.
+__device__ __forceinline__ double exp_gap(NxbXo& xo, float gsc, int tag) {
     const float f = ((float)(nxb_xo_next(xo) >> 9) + 0.5f) * (1.0f / 8388608.0f);   // in (0,1), exact
     // MUFU.LG2 has ~2^-22 absolute error, which only matters for f within 1e-6 of 1: clamp so
     // that the gap stays strictly positive (affects one draw in a million by < 1e-7 of a mean gap)
     const double g = (double)(fmaxf(-__log2f(f), 5.9604645e-8f) * gsc);
-    // the f32 value has 29 zero low mantissa bits as an f64: fill them with random bits
-    return __longlong_as_double(__double_as_longlong(g) | (long long)(nxb_xo_next(xo) >> 3));
+    return __longlong_as_double(__double_as_longlong(g) | (long long)tag);
 }
 
 // max / min without the NaN handling of fmax / fmin (event times are never NaN)
@@ -891,7 +892,7 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                     fresh = false;
                 }
                 if (draw_gap) {
-                    tcand -= exp_gap(xo, gsc);
+                    tcand -= exp_gap(xo, gsc, k + 1);
                     if (!(tcand > tma)) tcand = -NXB_INF;
                 }
                 const double tp = (ip >= ip0) ? u_ptm[ip] : -NXB_INF;
@@ -926,7 +927,7 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                         // (a candidate that ties with a retained event is dropped: probability ~2^-50)
                         live = (nxb_xo_next(xo) < thr) && (tcand != to);
                         // next arrival of the dominating process (rootward)
-                        tcand -= exp_gap(xo, gsc);
+                        tcand -= exp_gap(xo, gsc, k + 1);
                         if (!(tcand > tma)) tcand = -NXB_INF;
                     }
                     if (live) {
@@ -936,7 +937,12 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                         const float r = pow2_rescale_f(mx);
                         const float l1 = u1 * r, l0 = u0 * r;        // scale-free message below the event
                         if (cnt < TCAP) {
-                            LiveEv ev; ev.t = tnext; ev.q = __fdividef(l1, l0 + l1);      // operands in [0, 2): fast division is safe
+                            // Ratio by fast division (operands in [0, 2)) -- but a hard constraint must stay
+                            // exact: x / x is not guaranteed to be 1 there, and a q of 1 - 2^-24 in an own-class
+                            // segment (l0 == 0) let the downward pass switch the class off once in ~10^8
+                            // unit-sweeps.  l1 == 0 gives an exact 0.
+                            LiveEv ev; ev.t = tnext;
+                            ev.q = (l0 == 0.f) ? 1.f : fminf(__fdividef(l1, l0 + l1), 1.f);
                             ev.e = (unsigned short)e; ev.pad = 0;
                             cev[cnt] = ev;
                         } else bad = 2;

@@ -35,8 +35,7 @@ def flat(sm, pm):
             out['pri_dwell', e, sa, sb] = sm.flat['pri_dwell'][pm.edge_index[e], i] / n
     return out
 
-def main():
-  nseeds, chains, sweeps = 16, 65536, 100
+def main(nseeds=16, chains=65536, sweeps=100, grids=None):
   for M, D in ((toymodel.BlinkModelB, toydata.DataC), (toymodel.BlinkModelA, toydata.DataA),
           (toymodel.BlinkModelC, toydata.DataB)):
       cp = dense.CompoundProcess(M)
@@ -60,4 +59,7 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1:      # e.g. 64: more seeds
+        main(nseeds=int(sys.argv[1]))
+    else:
+        main()

@@ -114,3 +114,16 @@ def test_invariants_hold_over_a_million_unit_sweeps(nb):
     s.sweep(20, accumulate=True)
     assert s.summary().nsamples == 4096 * 16 * 20
     s.close()
+
+
+def test_hard_constraints_survive_a_long_soak(nb):
+    """1.6e8 validated unit-sweeps on the toy grid with tolerance data.  Regression: the message
+    ratio kept per live tolerance event once came from an approximate division, so that l1 / l1
+    could be 1 - 2^-24 and the downward pass switched the own class of the primary state off once
+    in ~3e8 unit-sweeps (found by scripts/gpu_exact_long.py).  Hard constraints must be exact."""
+    for seed in range(16):
+        s = nb.BlinkSampler(toymodel.BlinkModelB, validate=True)
+        s.set_data([toydata.DataC])
+        s.init_chains(chains=65536, seed=7000 + seed)
+        s.sweep(150, accumulate=False)          # raises on the first violated invariant
+        s.close()
