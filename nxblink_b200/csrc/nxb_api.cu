@@ -431,15 +431,18 @@ __global__ void summarize_kernel(const __grid_constant__ NxbSweepParams p) {
             unsigned mask = g_tol[parent[e]];
             double t = tma[e];
             const double tend = tma[e] + len[e];
+            int last_blk = -1;      // blink events already processed at time t (events of DIFFERENT
+                                    // tracks may share a time: gap times sit on the f32 grid)
             while (true) {
-                // next event on this edge strictly after t
+                // next event on this edge after t, ties between blink events in index order
                 double best = NXB_INF; int which = -1; bool is_pri = false;
                 for (int i = 0; i < hdr.n_pri; ++i)
                     if ((int)(g_pcode[i] & 0xffffu) == e && g_ptm[i] > t && g_ptm[i] < best) {
                         best = g_ptm[i]; which = i; is_pri = true;
                     }
                 for (int i = 0; i < hdr.n_blk; ++i)
-                    if ((int)(g_bcode[i] & 0xffffu) == e && g_btm[i] > t && g_btm[i] < best) {
+                    if ((int)(g_bcode[i] & 0xffffu) == e &&
+                        (g_btm[i] > t || (g_btm[i] == t && i > last_blk && last_blk >= 0)) && g_btm[i] < best) {
                         best = g_btm[i]; which = i; is_pri = false;
                     }
                 double tn = (which < 0) ? tend : best;
@@ -461,6 +464,7 @@ __global__ void summarize_kernel(const __grid_constant__ NxbSweepParams p) {
                     else atomicAdd(p.counts + sl.c_on_off + e, 1ull);
                     mask ^= 1u << ((code >> 16) & 0xffu);
                 }
+                last_blk = is_pri ? -1 : which;
                 t = tn;
             }
         }
