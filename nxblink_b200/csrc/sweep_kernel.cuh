@@ -703,16 +703,18 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 // TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, one lane per (unit, track)
 // ---------------------------------------------------------------------------
 // Exponential gap of the dominating Poisson process, mean gsc / ln 2 (time units).  The logarithm
-// is taken in f32 (23-bit uniform).  As an f64 the value has 29 zero low mantissa bits: the track
-// id goes there, so that events of DIFFERENT tracks never share a time; a candidate that ties with
-// a retained event of its own track (both sit on the f32 grid below the same edge end, ~1e-6 per
-// unit-sweep) is dropped by the walk.
+// is taken in f32 (23-bit uniform).  As an f64 the value has 29 zero low mantissa bits: the unused
+// 9 bits of the random word and the track id go there, which makes equal event times rare (they
+// are harmless between tracks; a candidate that ties with a retained event of its own track is
+// dropped by the walk).
 __device__ __forceinline__ double exp_gap(NxbXo& xo, float gsc, int tag) {
-    const float f = ((float)(nxb_xo_next(xo) >> 9) + 0.5f) * (1.0f / 8388608.0f);   // in (0,1), exact
+    const unsigned w = nxb_xo_next(xo);
+    const float f = ((float)(w >> 9) + 0.5f) * (1.0f / 8388608.0f);   // in (0,1), exact
     // MUFU.LG2 has ~2^-22 absolute error, which only matters for f within 1e-6 of 1: clamp so
     // that the gap stays strictly positive (affects one draw in a million by < 1e-7 of a mean gap)
     const double g = (double)(fmaxf(-__log2f(f), 5.9604645e-8f) * gsc);
-    return __longlong_as_double(__double_as_longlong(g) | (long long)tag);
+    // low mantissa bits: the 9 bits of the word that the uniform did not use, then the track id
+    return __longlong_as_double(__double_as_longlong(g) | (long long)(((w & 0x1ffu) << 6) | (unsigned)tag));
 }
 
 // max / min without the NaN handling of fmax / fmin (event times are never NaN)
