@@ -867,9 +867,13 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
         float gsc = 0.f;
         int s = 0, ip = trk ? poff[E] - 1 : 0, ip0 = 0, sa_slot = 0, sb_slot = -1;
         unsigned xold = 0u;
+        bool gap_due = false;
         while (__any_sync(FULL, e >= 0)) {
             if (e >= 0) {
-                bool draw_gap = false;
+                // one gap is due: at the bottom of a fresh edge, or after the candidate consumed by the
+                // previous step (drawn here so that the walk has a single copy of the gap code)
+                bool draw_gap = gap_due;
+                gap_due = false;
                 if (fresh) {
                     const NxbEdgeRec er = erec[e];
                     sb_slot = er.sb_slot; sa_slot = er.sa_slot;
@@ -928,9 +932,9 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                         const unsigned thr = own ? (xold ? thr_w1 : thr_w0) : (xold ? thr_o1 : thr_o0);
                         // (a candidate that ties with a retained event is dropped: probability ~2^-50)
                         live = (nxb_xo_next(xo) < thr) && (tcand != to);
-                        // next arrival of the dominating process (rootward)
-                        tcand -= exp_gap(xo, gsc, k + 1);
-                        if (!(tcand > tma)) tcand = -NXB_INF;
+                        // next arrival of the dominating process (rootward): drawn by the next step;
+                        // until then the candidate slot is empty
+                        gap_due = true;
                     }
                     if (live) {
                         if (pen != 0.0) { u1 *= expf((float)(-pen)); pen = 0.0; }
