@@ -84,7 +84,10 @@ int nxb_destroy(nxb_handle* h);
  * (examples/p53/run-stochastic.py:154-208 builds a new model object per iteration).  Device
  * buffers, capacity tiers, data and unit states are kept; chains may be continued (warm start)
  * or initialised again with nxb_init_chains.  If an edge switched between zero and positive
- * rate x length the unit states are dropped and nxb_init_chains must be called. */
+ * rate x length the unit states are dropped and nxb_init_chains must be called.  Capacities
+ * (shared-memory tiers, slab sizes: 4x the expected event counts) remain those of the model the
+ * handle was created for: a model with several times higher rates may exhaust them
+ * (NXB_ERR_STATE_CAP / NXB_ERR_SCRATCH_CAP); create a new handle in that case. */
 int nxb_update_model(nxb_handle* h, const nxb_model_desc* desc);
 const char* nxb_last_error(const nxb_handle* h);   /* h may be NULL: last create error */
 
