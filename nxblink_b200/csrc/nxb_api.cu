@@ -734,6 +734,8 @@ struct nxb_handle {
     unsigned long long* d_scratch = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;     // a launch whose result is collected by the next one
+    int pending_kind = -1;
     float last_ms = 0.f;
     int last_launches = 0;
     float kind_ms[4] = {0.f, 0.f, 0.f, 0.f};   // of the last call: fused, primary-only, blink, check
@@ -1151,6 +1153,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     CUDA_TRY_C(cudaStreamCreate(&h->stream));
     CUDA_TRY_C(cudaEventCreate(&h->ev0));
     CUDA_TRY_C(cudaEventCreate(&h->ev1));
+    CUDA_TRY_C(cudaEventCreate(&h->ev2));
+    CUDA_TRY_C(cudaEventCreate(&h->ev3));
 
     // ---- model tables ----
     double sums[3];
@@ -1352,6 +1356,8 @@ extern "C" int nxb_destroy(nxb_handle* h) {
     cudaFree(h->d_scratch); cudaFree(h->d_perf); cudaFree(h->d_gscratch);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->ev3) cudaEventDestroy(h->ev3);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return NXB_OK;
@@ -1392,9 +1398,11 @@ enum { KIND_FUSED = 0, KIND_PRIMARY = 1, KIND_BLINK = 2, KIND_CHECK = 3 };
 
 // One kernel launch over `list` (or every unit): fills the defer list `out` (appending when
 // `append`), adds the kernel time, returns the number of listed units through *n_deferred.
+// `no_wait`: do not wait for the kernel; its time, status and listed units are collected by the
+// next (waiting) launch on the same stream.
 static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps, const int* list, int n_list,
                       int* out, bool append, unsigned begin, unsigned target, unsigned accum_from, int init,
-                      int* n_deferred) {
+                      int* n_deferred, bool no_wait = false) {
     NxbSweepParams p;
     memset(&p, 0, sizeof(p));
     p.ml = h->ml; p.wl = (kind == KIND_BLINK) ? tier.bwl : tier.wl; p.sl = h->sl;
@@ -1428,7 +1436,7 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
     CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
     if (!append) CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
     const long long n_work = list ? n_list : h->n_units;
-    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    CUDA_TRY(h, cudaEventRecord(no_wait ? h->ev2 : h->ev0, h->stream));
     if (kind == KIND_BLINK) {
         int grid = (int)std::min<long long>(h->num_sms, (n_work + tier.blink_units - 1) / tier.blink_units);
         blink_kernel<<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
@@ -1446,7 +1454,8 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
         }
     }
     CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(h, cudaEventRecord(no_wait ? h->ev3 : h->ev1, h->stream));
+    if (no_wait) { h->pending_kind = kind; *n_deferred = 0; return NXB_OK; }
     int hs[5];
     CUDA_TRY(h, cudaMemcpyAsync(hs, h->d_status, 16, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(hs + 4, h->d_defer_count, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1455,6 +1464,13 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->last_ms += ms; h->last_launches++; h->launches_total++;
     h->kind_ms[kind] += ms; h->kind_launches[kind]++;
+    if (h->pending_kind >= 0) {
+        float ms2 = 0.f;
+        cudaEventElapsedTime(&ms2, h->ev2, h->ev3);
+        h->last_ms += ms2; h->last_launches++; h->launches_total++;
+        h->kind_ms[h->pending_kind] += ms2; h->kind_launches[h->pending_kind]++;
+        h->pending_kind = -1;
+    }
     if (hs[0] != 0) {
         char buf[256];
         snprintf(buf, sizeof(buf), "%s (code %d, unit %d, detail %d, sweep %d)", status_text(hs[0]),
@@ -1497,8 +1513,9 @@ static int run_split(nxb_handle* h, unsigned target, unsigned accum_from) {
     const int gw = (h->lockstep < 0 && t0.warps >= 8) ? (t0.warps % 10 == 0 ? 10 : t0.warps / 2) : group_warps_for(h, t0.warps);
     while (h->sweeps < target) {
         int nd = 0;
+        // (the tolerance launch below waits and collects the status and the listed units of both)
         int rc = launch_one(h, KIND_PRIMARY, t0, gw, nullptr, 0, h->d_defer[0], false, h->sweeps, h->sweeps + 1,
-                            accum_from, 0, &nd);
+                            accum_from, 0, &nd, true);
         if (rc) return rc;
         rc = launch_one(h, KIND_BLINK, t0, 1, nullptr, 0, h->d_defer[0], true, h->sweeps, h->sweeps + 1,
                         accum_from, 0, &nd);
