@@ -32,17 +32,19 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 // C = A * B for ND x ND matrices in shared memory (row-major, leading dimension ND).
-// 8 warps: warp w owns the 8-row strip w; C must not alias A or B.
+// 8 warps: warp w owns the 8-row strip w; C must not alias A or B.  The A fragments of the
+// strip (16 k-steps) stay in registers across the 8 column tiles: one shared-memory load per
+// DMMA instead of two.
 __device__ void matmul64(const double* A, const double* B, double* C, int warp, int lane) {
     const int r = lane >> 2, q = lane & 3;
+    double a[ND / 4];
+#pragma unroll
+    for (int ks = 0; ks < ND / 4; ++ks) a[ks] = A[(warp * 8 + r) * ND + ks * 4 + q];
     for (int jt = 0; jt < ND / 8; ++jt) {
         double c0 = 0.0, c1 = 0.0;
-#pragma unroll 4
-        for (int k0 = 0; k0 < ND; k0 += 4) {
-            const double a = A[(warp * 8 + r) * ND + k0 + q];
-            const double b = B[(k0 + q) * ND + jt * 8 + r];
-            dmma(c0, c1, a, b);
-        }
+#pragma unroll
+        for (int ks = 0; ks < ND / 4; ++ks)
+            dmma(c0, c1, a[ks], B[(ks * 4 + q) * ND + jt * 8 + r]);
         C[(warp * 8 + r) * ND + jt * 8 + 2 * q] = c0;
         C[(warp * 8 + r) * ND + jt * 8 + 2 * q + 1] = c1;
     }
@@ -106,15 +108,15 @@ __global__ void __launch_bounds__(256) expm_kernel(int n, const double* __restri
 template <bool ACC>
 __device__ void matmul64x(const double* A, const double* B, double* C, int warp, int lane) {
     const int r = lane >> 2, q = lane & 3;
+    double a[ND / 4];
+#pragma unroll
+    for (int ks = 0; ks < ND / 4; ++ks) a[ks] = A[(warp * 8 + r) * ND + ks * 4 + q];
     for (int jt = 0; jt < ND / 8; ++jt) {
         double* cp = C + (warp * 8 + r) * ND + jt * 8 + 2 * q;
         double c0 = ACC ? cp[0] : 0.0, c1 = ACC ? cp[1] : 0.0;
-#pragma unroll 4
-        for (int k0 = 0; k0 < ND; k0 += 4) {
-            const double a = A[(warp * 8 + r) * ND + k0 + q];
-            const double b = B[(k0 + q) * ND + jt * 8 + r];
-            dmma(c0, c1, a, b);
-        }
+#pragma unroll
+        for (int ks = 0; ks < ND / 4; ++ks)
+            dmma(c0, c1, a[ks], B[(ks * 4 + q) * ND + jt * 8 + r]);
         cp[0] = c0; cp[1] = c1;
     }
 }
@@ -251,14 +253,14 @@ __global__ void __launch_bounds__(256) pruning_kernel(
         __syncthreads();
         {
             const int r = lane >> 2, q = lane & 3;
+            double a[ND / 4];           // this warp's strip of P_e, reused across the site tiles
+#pragma unroll
+            for (int ks = 0; ks < ND / 4; ++ks) a[ks] = Pe[(warp * 8 + r) * ND + ks * 4 + q];
             for (int jt = 0; jt < ST / 8; ++jt) {
                 double c0 = 0.0, c1 = 0.0;
-#pragma unroll 4
-                for (int k0 = 0; k0 < ND; k0 += 4) {
-                    const double a = Pe[(warp * 8 + r) * ND + k0 + q];
-                    const double b = Lv[(k0 + q) * ST + jt * 8 + r];
-                    dmma(c0, c1, a, b);
-                }
+#pragma unroll
+                for (int ks = 0; ks < ND / 4; ++ks)
+                    dmma(c0, c1, a[ks], Lv[(ks * 4 + q) * ST + jt * 8 + r]);
                 M[(warp * 8 + r) * ST + jt * 8 + 2 * q] = c0;
                 M[(warp * 8 + r) * ST + jt * 8 + 2 * q + 1] = c1;
             }
