@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(256) pruning_kernel(
     double* slots = M + ND * ST;                // nslots x ND x ST
     __shared__ double s_logscale[ST];
     __shared__ double s_colmax[ST];
+    double* s_part = M;                         // M is free until the contraction below
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long site0 = (long long)blockIdx.x * ST;
     const int E = n_nodes - 1;
@@ -231,9 +232,18 @@ __global__ void __launch_bounds__(256) pruning_kernel(
             Lv[i] = ok ? val : 0.0;
         }
         __syncthreads();
+        {
+            // per-site maximum over the states: 8 groups of 8 states in parallel, then 8 partials
+            const int si = tid % ST, g = tid / ST;          // blockDim.x == 8 * ST
+            double mx = 0.0;
+            for (int st = g * 8; st < g * 8 + 8; ++st) mx = fmax(mx, Lv[st * ST + si]);   // rows >= n are 0
+            s_part[g * ST + si] = mx;
+        }
+        __syncthreads();
         if (tid < ST) {
             double mx = 0.0;
-            for (int st = 0; st < n; ++st) mx = fmax(mx, Lv[st * ST + tid]);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) mx = fmax(mx, s_part[g * ST + tid]);
             s_colmax[tid] = mx;
             if (mx > 0.0) s_logscale[tid] += log(mx);
             else if (site0 + tid < n_sites) s_logscale[tid] = -INFINITY;
