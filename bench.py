@@ -81,6 +81,15 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def host_cores():
+    """Host threads this process may use (affinity / cgroup aware), at most 128 workers."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 128))
+
+
 def cpu_site_sweeps_per_sec(cores, burn, sweeps, pool=None):
     """All `cores` workers sweep one p53-shaped site each; aggregate site-sweeps/s."""
     own = pool is None
@@ -102,7 +111,7 @@ def cpu_site_sweeps_per_sec(cores, burn, sweeps, pool=None):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     burn, sweeps = 1, 4
     pool = multiprocessing.get_context('spawn').Pool(cores)
     try:
@@ -376,7 +385,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                 traffic = tj.get('dram_bytes_per_unit', {}).get(dom, tj['dram_bytes_per_unit_sweep']) * n_units
         except Exception:
             pass
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         if args.cpu_sweeps > 0:
             cpu_val, cpu_wall = cpu_site_sweeps_per_sec(cores, 1, args.cpu_sweeps)
         else:
