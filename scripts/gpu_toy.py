@@ -16,7 +16,7 @@ tt = np.full(ls.shape, allk, np.uint32); tf = np.full(ls.shape, allk, np.uint32)
 ref = pm.node_index['N0']            # full tolerance observation at the reference leaf (DataC style)
 tt[:, ref] = node_tol[:, ref]; tf[:, ref] = (~node_tol[:, ref]) & allk
 data = packing.pack_alignment(pm, ls, tt, tf)
-s = nb.BlinkSampler(pm)
+s = nb.BlinkSampler(pm, lockstep_warps=int(os.environ.get('TOY_LOCKSTEP', '0')), split_phases=int(os.environ.get('TOY_SPLIT', '0')))
 s.set_data(data); s.init_chains(chains=64, seed=1)
 s.sweep(10, accumulate=False)
 s.profile(True)
