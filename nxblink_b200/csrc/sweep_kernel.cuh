@@ -937,7 +937,9 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
                         gap_due = true;
                     }
                     if (live) {
-                        if (pen != 0.0) { u1 *= expf((float)(-pen)); pen = 0.0; }
+                        // (messages are scale-free: with OFF impossible the factor is a pure rescaling
+                        // and is dropped, so that a long own-class segment cannot underflow ON to 0)
+                        if (pen != 0.0) { if (u0 != 0.f) u1 *= expf((float)(-pen)); pen = 0.0; }
                         float mx = fmaxf(u0, u1);
                         if (!(mx > 0.f)) { bad = 1; mx = 1.f; }
                         const float r = pow2_rescale_f(mx);
@@ -974,7 +976,7 @@ __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned 
     unsigned x = 0u;
     if (trk) {
         const AccRec a = acc[c.slot[0] * K + k];
-        double w1 = (double)a.u1 * exp(-a.pen) * ml.p_on;
+        double w1 = (double)a.u1 * (a.u0 != 0.f ? exp(-a.pen) : 1.0) * ml.p_on;
         double w0 = (double)a.u0 * ml.p_off;
         if (!(((unsigned)uhdr[8] >> k) & 1u)) w1 = 0.0;
         if (!(((unsigned)uhdr[9] >> k) & 1u)) w0 = 0.0;
