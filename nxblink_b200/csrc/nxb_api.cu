@@ -10,6 +10,7 @@
 
 #include "../../include/nxblink_b200.h"
 #include "sweep_kernel.cuh"
+#include "tol_tables.h"
 
 #define NXB_MAX_THREADS 640
 #define NXB_BLINK_THREADS 800      /* 25 warps at 72 registers: 40 units x 20 tracks per CTA at the p53 shape */
@@ -224,7 +225,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             } else if (!PRIMARY_ONLY) {
                 // every warp of a lockstep group takes part: its lanes carry tracks of other units
                 if (active || lockstep) {
-                    const int brc = blink_phase(c, accum, active);
+                    const int brc = blink_phase<MSG>(c, accum, active);
                     if (active) {
                         rc = brc;
                         if (rc == RC_DEFER && c.nB < 0) {     // sweep complete, blink list spilled to HBM
@@ -279,6 +280,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
 // Units that are elsewhere are skipped (the primary launch listed them for the next tier);
 // units whose events do not fit the shared-memory capacities are listed here.
 // ---------------------------------------------------------------------------
+template <typename MSG>
 __global__ void __launch_bounds__(NXB_BLINK_THREADS, 1)
 blink_kernel(const __grid_constant__ NxbSweepParams p) {
     const NxbModelLayout& ml = p.ml;
@@ -355,7 +357,7 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
         }
         __syncthreads();
         // ---- one (unit, track) job per lane ----
-        blink_job<true>(c, tid, U * K, (unsigned)p.smem_warp0, gb0);
+        blink_job<MSG, true>(c, tid, U * K, (unsigned)p.smem_warp0, gb0);
         __syncthreads();
         tick(c, T_BW);          // (waiting for the slowest lane of the CTA is booked here)
         // ---- write the units back ----
@@ -367,7 +369,7 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
             c.unit = (long long)uhdr[7];
             const bool accum = uhdr[6] != 0;
             unsigned char* slab = p.state + c.unit * p.state_stride;
-            int rc = blink_finish<true>(c, accum);          // new blink list written to the slab
+            int rc = blink_finish<MSG, true>(c, accum);          // new blink list written to the slab
             tick(c, T_BW);
             if (rc == RC_ERROR) continue;
             NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;
@@ -805,7 +807,7 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     // blink-phase scratch (aliases the primary-phase scratch)
     o = scratch0;
     wl->off_toff = take(4 * (K + 1), 4);
-    wl->off_acc = take(16 * K * ml.nslots, 16);
+    wl->off_acc = take((msg_f64 ? 32 : 16) * K * ml.nslots, 16);
     wl->off_newtol = take(4 * N, 4);
     wl->off_nrec = take(16 * E, 16);
     // validate_unit needs bord while the persistent state is live; it is only called
@@ -830,7 +832,7 @@ static int group_warps_for(const nxb_handle* h, int warps) {
 
 // One unit of blink_kernel: the trajectory, the tolerance data, the index arrays of the
 // tolerance update and its accumulators -- none of the primary update's scratch.
-static void build_blink_layout(const NxbModelLayout& ml, int capP, int capB, NxbWarpLayout* wl) {
+static void build_blink_layout(const NxbModelLayout& ml, bool msg_f64, int capP, int capB, NxbWarpLayout* wl) {
     const int N = ml.N, E = ml.E, K = ml.K;
     memset(wl, 0, sizeof(*wl));
     int o = 0;
@@ -845,7 +847,7 @@ static void build_blink_layout(const NxbModelLayout& ml, int capP, int capB, Nxb
     wl->off_poff = take(4 * (E + 1), 4);
     wl->off_uhdr = take(4 * (10 + 32), 4);
     wl->off_toff = take(4 * (K + 1), 4);
-    wl->off_acc = take(16 * K * ml.nslots, 16);
+    wl->off_acc = take((msg_f64 ? 32 : 16) * K * ml.nslots, 16);
     wl->off_newtol = take(4 * N, 4);
     wl->off_tmpa = wl->off_newtol;                   // scratch of build_poff, dead before newtol is zeroed
     wl->off_nrec = take(16 * E, 16);
@@ -888,27 +890,6 @@ static int build_model_tables(nxb_handle* h, const nxb_model_desc* d, double sum
     ml.rate_on = d->rate_on; ml.rate_off = d->rate_off;
     std::vector<double> tm(N, 0.0);
     for (int v = 1; v < N; ++v) tm[v] = tm[d->parent[v]] + d->blen[v];
-    // accumulator slots for the upward blink pass (edges in descending index)
-    std::vector<int> slot(N, -1);
-    {
-        std::vector<int> free_slots;
-        int next = 0;
-        for (int e = E - 1; e >= 0; --e) {
-            int vb = e + 1, va = d->parent[vb];
-            if (slot[va] < 0) {
-                if (!free_slots.empty()) {
-                    auto it = std::min_element(free_slots.begin(), free_slots.end());
-                    slot[va] = *it; free_slots.erase(it);
-                } else slot[va] = next++;
-            }
-            if (slot[vb] >= 0) free_slots.push_back(slot[vb]);
-        }
-        ml.nslots = std::max(next, 1);
-        if (ml.nslots > 32) {
-            set_err(nullptr, NXB_ERR_BAD_ARG, "tree needs more than 32 live accumulators; renumber nodes depth-first");
-            return NXB_ERR_BAD_ARG;
-        }
-    }
     // rates: total out-rate per state with every class on, and its maximum
     double rmax_all = 0.0;
     for (int s = 0; s < P; ++s) {
@@ -919,17 +900,13 @@ static int build_model_tables(nxb_handle* h, const nxb_model_desc* d, double sum
     if (!(rmax_all > 0.0)) { set_err(nullptr, NXB_ERR_BAD_ARG, "empty rate matrix"); return NXB_ERR_BAD_ARG; }
     ml.inv_omega_pri = 1.0 / (2.0 * rmax_all);
     const double M = std::max(d->rate_on, d->rate_off);
-    ml.a_on = d->rate_on / (2.0 * M);
-    ml.a_off = d->rate_off / (2.0 * M);
-    ml.acc_blk[0] = (2.0 * M - d->rate_on) / (2.0 * M);   // other class, track OFF
-    ml.acc_blk[1] = (2.0 * M - d->rate_off) / (2.0 * M);  // other class, track ON
-    ml.acc_blk[2] = d->rate_on / (2.0 * M);               // own class, OFF (infeasible state)
-    ml.acc_blk[3] = d->rate_on / M;                       // own class, ON
-    ml.p_on = d->rate_on / (d->rate_on + d->rate_off);
-    ml.p_off = d->rate_off / (d->rate_on + d->rate_off);
 
     // ---- model blob ----
     std::vector<unsigned char> blob;
+    {
+        std::string err;
+        if (nxb_build_tol_tables(d, ml, blob, err)) { set_err(nullptr, NXB_ERR_BAD_ARG, err); return NXB_ERR_BAD_ARG; }
+    }
     auto put = [&](const void* src, int bytes, int al) {
         int o = align_up((int)blob.size(), al);
         blob.resize(o + bytes);
@@ -958,32 +935,11 @@ static int build_model_tables(nxb_handle* h, const nxb_model_desc* d, double sum
                 return NXB_ERR_BAD_ARG;
             }
         }
-        // ---- tables of the tolerance update first: blink_kernel stages only this prefix ----
+        // ---- the rest: primary update (the tolerance tables, built by nxb_build_tol_tables above,
+        // are the prefix of the blob: blink_kernel stages only that prefix) ----
         std::vector<float> gsc(E, 0.f);
         for (int e = 0; e < E; ++e)
             if (rate[e] > 0.0 && len[e] > 0.0) gsc[e] = (float)(0.6931471805599453 / (2.0 * M * rate[e]));
-        {
-            std::vector<NxbEdgeRec> recs(E);
-            for (int e = 0; e < E; ++e) {
-                recs[e].tma = tma[e]; recs[e].tmb = tma[e] + len[e]; recs[e].rate = rate[e];
-                recs[e].gsc = gsc[e]; recs[e].va = (unsigned short)parent[e];
-                recs[e].sa_slot = (signed char)slot[parent[e]];
-                recs[e].sb_slot = (signed char)slot[e + 1];
-            }
-            ml.off_edgerec = put(recs.data(), (int)(sizeof(NxbEdgeRec) * E), 16);
-        }
-        ml.off_slot = put(slot.data(), 4 * N, 4);
-        std::vector<unsigned char> cls(P);
-        for (int s = 0; s < P; ++s) cls[s] = (unsigned char)d->state_class[s];
-        ml.off_cls = put(cls.data(), P, 1);
-        std::vector<double> qm((size_t)P * K, 0.0);
-        for (int s = 0; s < P; ++s)
-            for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i)
-                qm[(size_t)s * K + d->state_class[d->q_col[i]]] += d->q_val[i];
-        ml.off_qm = put(qm.data(), 8 * P * K, 8);
-        blob.resize(align_up((int)blob.size(), 16));
-        ml.blink_bytes = (int)blob.size();
-        // ---- the rest: primary update ----
         ml.off_parent = put(parent.data(), 4 * E, 4);
         {
             // longest-processing-time assignment of the edges to 32 lane slots per round: round r
@@ -1237,7 +1193,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
                 tier.warps = std::min(w, max_warps);
                 tier.smem = (size_t)fixed + (size_t)tier.warps * tier.wl.bytes;
                 if (pass == 0 && t == 0) {
-                    build_blink_layout(ml, tier.wl.capP, tier.wl.capB, &tier.bwl);
+                    build_blink_layout(ml, h->msg_f64, tier.wl.capP, tier.wl.capB, &tier.bwl);
                     const int bfixed = ml.blink_bytes + stats_bytes;      // model prefix + statistic partials
                     tier.blink_warp0 = bfixed;
                     const int fit = (h->max_smem - bfixed) / tier.bwl.bytes;
@@ -1278,7 +1234,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             int o = 0;
             h->g_off_msg = o; o += (h->msg_f64 ? 8 : 4) * (h->gcapF + 1) * NXB_PPAD;
             o = align_up(o, 16);
-            h->g_off_ctm = o; o += 16 * h->gcapC * K;      // one region per track, 16 B records
+            h->g_off_ctm = o; o += (h->msg_f64 ? 32 : 16) * h->gcapC * K;      // one region per track, 16 B (f32) / 32 B (f64) records
             h->gscratch_stride = align_up(o, 256);
             cudaError_t e1 = cudaMalloc(&h->d_gscratch, (size_t)h->gscratch_stride * max_w * h->num_sms);
             if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }
@@ -1302,8 +1258,9 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
         if (e1 == cudaSuccess) e1 = h->msg_f64
             ? cudaFuncSetAttribute(sweep_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
             : cudaFuncSetAttribute(sweep_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
-        if (e1 == cudaSuccess)
-            e1 = cudaFuncSetAttribute(blink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+        if (e1 == cudaSuccess) e1 = h->msg_f64
+            ? cudaFuncSetAttribute(blink_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
+            : cudaFuncSetAttribute(blink_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
         if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }
     }
     cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
@@ -1439,7 +1396,8 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
     CUDA_TRY(h, cudaEventRecord(no_wait ? h->ev2 : h->ev0, h->stream));
     if (kind == KIND_BLINK) {
         int grid = (int)std::min<long long>(h->num_sms, (n_work + tier.blink_units - 1) / tier.blink_units);
-        blink_kernel<<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
+        if (h->msg_f64) blink_kernel<double><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
+        else blink_kernel<float><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
     } else {
         const int gw = std::max(group_warps, 1);
         const int launch_warps = tier.warps / gw * gw;       // whole groups only

@@ -31,28 +31,16 @@
 #include <type_traits>
 #include "nxb_types.h"
 #include "philox.cuh"
+#include "nxb_portable.h"
+#include "tol_update.cuh"
 
 #define FULL 0xffffffffu
-#define NXB_INF (__longlong_as_double(0x7ff0000000000000LL))
 
 namespace nxb {
 
 enum { RC_OK = 0, RC_DEFER = 1, RC_ERROR = 2 };
 
 __constant__ double c_inv_n[64];
-
-// Everything a warp touches in shared memory is addressed as a 32-bit offset from the one dynamic
-// shared array, so that the compiler keeps shared-space (LDS/STS) addressing with 32-bit
-// arithmetic instead of rebuilding 64-bit generic pointers inside the hot loops.
-extern __shared__ __align__(16) unsigned char nxb_smem[];
-template <typename T> struct SPtr {
-    unsigned off;
-    __device__ __forceinline__ T& operator[](int i) const { return reinterpret_cast<T*>(nxb_smem + off)[i]; }
-    __device__ __forceinline__ T* ptr() const { return reinterpret_cast<T*>(nxb_smem + off); }
-};
-template <typename T> __device__ __forceinline__ T* sm_ptr(unsigned off) {
-    return reinterpret_cast<T*>(nxb_smem + off);
-}
 
 struct Ctx {
     const NxbSweepParams* p;
@@ -115,14 +103,8 @@ __device__ __forceinline__ void tick(Ctx& c, int which) {
     }
 }
 
-// One out-of-line copy: the sweep kernel is far larger than the instruction cache, so
-// code size (not call overhead) is what matters for the helpers below.
-__device__ __noinline__ NxbU4 philox_call(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
-                                          unsigned k0, unsigned k1) {
-    return nxb_philox4x32_10(c0, c1, c2, c3, k0, k1);
-}
 __device__ __forceinline__ NxbU4 rng(const Ctx& c, unsigned stream, unsigned block) {
-    return philox_call(c.unit32, c.sweep, stream, block, c.k0, c.k1);
+    return nxb_philox_call(c.unit32, c.sweep, stream, block, c.k0, c.k1);
 }
 
 __device__ __noinline__ int warp_excl_scan(int v, int lane, int& total) {
@@ -700,44 +682,9 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
 }
 
 // ---------------------------------------------------------------------------
-// TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, one lane per (unit, track)
+// TOLERANCE TRACK UPDATES  (raoteh.py:413-432), all K tracks at once, one lane per (unit, track):
+// the per-lane code is in tol_update.cuh; here the warp-level set-up and write-back of a unit.
 // ---------------------------------------------------------------------------
-// Exponential gap of the dominating Poisson process, mean gsc / ln 2 (time units).  The logarithm
-// is taken in f32 (23-bit uniform).  As an f64 the value has 29 zero low mantissa bits: the unused
-// 9 bits of the random word and the track id go there, which makes equal event times rare (they
-// are harmless between tracks; a candidate that ties with a retained event of its own track is
-// dropped by the walk).
-__device__ __forceinline__ double exp_gap(NxbXo& xo, float gsc, int tag) {
-    const unsigned w = nxb_xo_next(xo);
-    const float f = ((float)(w >> 9) + 0.5f) * (1.0f / 8388608.0f);   // in (0,1), exact
-    // MUFU.LG2 has ~2^-22 absolute error, which only matters for f within 1e-6 of 1: clamp so
-    // that the gap stays strictly positive (affects one draw in a million by < 1e-7 of a mean gap)
-    const double g = (double)(fmaxf(-__log2f(f), 5.9604645e-8f) * gsc);
-    // low mantissa bits: the 9 bits of the word that the uniform did not use, then the track id
-    return __longlong_as_double(__double_as_longlong(g) | (long long)(((w & 0x1ffu) << 6) | (unsigned)tag));
-}
-
-// max / min without the NaN handling of fmax / fmin (event times are never NaN)
-__device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }
-__device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a : b; }
-
-#define CE_EDGE 0x3fffu
-#define CE_NEW1 0x4000u     // (survivors only) new state of the surviving event
-
-// One 16-byte record per live event: time, q = l1 / (l0 + l1) of the (OFF, ON) message below the
-// event (the backward draw only needs the ratio), edge.  The downward pass reuses the records it
-// has consumed for the survivors (e then also carries CE_NEW1), so a track touches only
-// ceil(16 * live / 128) lines of the L2-resident pool per sweep.
-struct __align__(16) LiveEv { double t; float q; unsigned short e, pad; };
-// Accumulator of a node for one track: product of the (OFF, ON) messages of the children folded
-// so far (f32, rescaled by powers of two) and the penalty exponent still to be applied to ON.
-struct __align__(16) AccRec { double pen; float u0, u1; };
-
-// 2^-(floor(log2 m) + 1) for a positive finite m: exact power-of-two rescaling into [0.5, 1)
-// without a division; preserves exact zeros of the other component.
-__device__ __forceinline__ float pow2_rescale_f(float m) {
-    return __int_as_float((0xfd << 23) - (__float_as_int(m) & (0xff << 23)));
-}
 
 // ---- S0 (the warp that owns the unit): index of the primary events, offsets of the retained
 // events per track, and the unit header that the lane jobs of other warps read
@@ -779,12 +726,14 @@ __device__ __forceinline__ void blink_setup(Ctx& c, bool accumulate, bool active
         if (lane == 0) toff_own[K] = total;
     }
     if (active) {
-        // one 16-byte record per edge for the upward walk: data masks, old tolerance states and
-        // primary state of the lower node, and the index of the edge's first primary event
+        // one 16-byte record per edge: data masks, old tolerance states and primary state of the
+        // lower node, whether the edge holds primary events, and the index of its first one
         const SPtr<uint4> nrec_own = {c.wbase + wl.off_nrec};
-        for (int e = lane; e < c.E; e += 32)
+        for (int e = lane; e < c.E; e += 32) {
+            const unsigned lo = (unsigned)c.poff[e], hi = (unsigned)c.poff[e + 1];
             nrec_own[e] = make_uint4(tt[e + 1], tf[e + 1], c.node_tol[e + 1],
-                                     (unsigned)c.node_pri[e + 1] | ((unsigned)c.poff[e] << 8));
+                                     (unsigned)c.node_pri[e + 1] | (hi != lo ? 0x100u : 0u) | (lo << 9));
+        }
     }
     if (lane == 0) {
         uhdr_own[0] = active ? 1 : 0; uhdr_own[2] = c.nB; uhdr_own[3] = (int)c.unit32; uhdr_own[4] = 0;
@@ -794,281 +743,32 @@ __device__ __forceinline__ void blink_setup(Ctx& c, bool accumulate, bool active
     __syncwarp();
 }
 
-// ---- lane job: the whole update of ONE tolerance track of ONE unit (upward pass, root draw,
-// downward pass).  Job j works on track j % K of unit j / K of a pool of units resident in this
-// CTA's shared memory (regions ub0 + u * wl.bytes, global scratch gb0 + u * gscratch_stride), so
-// that every lane of the busy warps walks a track; with lane = track only K of 32 lanes would
-// (20 of 32 at the p53 shape).
-template <bool SPLIT>
+// ---- lane job: the whole update of ONE tolerance track of ONE unit.  Job j works on track j % K
+// of unit j / K of a pool of units resident in this CTA's shared memory (regions ub0 + u * wl.bytes,
+// global scratch gb0 + u * gscratch_stride), so that every lane of the busy warps carries a track;
+// with lane = track only K of 32 lanes would (20 of 32 at the p53 shape).
+template <typename MSG, bool SPLIT>
 __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned ub0, unsigned char* gb0) {
-    const NxbSweepParams& p = *c.p;
-    const NxbWarpLayout& wl = p.wl;
-    const NxbModelLayout& ml = p.ml;
-    const int E = c.E, P = c.P, K = c.K;
-    const int TCAP = p.gcapC;
-    const SPtr<const NxbEdgeRec> erec = {(unsigned)ml.off_edgerec};
-    const bool has_job = job < n_jobs;
-    const int ju = has_job ? job / K : 0;
-    const int k = has_job ? job - ju * K : 0;
-    const unsigned ub = ub0 + (unsigned)(ju * wl.bytes);             // unit ju's shared-memory region
-    unsigned char* const ugb = gb0 + (long long)ju * p.gscratch_stride;
-    // live foreground events of this sweep: global (L2-resident) scratch, one fixed region per
-    // (unit, track), filled by the upward pass and consumed backwards by the downward pass
-    LiveEv* cev = (LiveEv*)(ugb + p.g_off_ctm) + (size_t)k * TCAP;
-    const SPtr<int> uhdr = {ub + wl.off_uhdr};
-    const SPtr<AccRec> acc = {ub + wl.off_acc};                 // [slot][K]
-    const SPtr<unsigned> newtol = {ub + wl.off_newtol};
-    const SPtr<int> poff = {ub + wl.off_poff};
-    const SPtr<const int> toff = {ub + wl.off_toff};
-    const SPtr<const uint4> nrec = {ub + wl.off_nrec};
-    const SPtr<unsigned> u_node_tol = {ub + wl.off_node_tol};
-    const SPtr<unsigned char> u_node_pri = {ub + wl.off_node_pri};
-    const SPtr<double> u_ptm = {ub + wl.off_ptm};
-    const SPtr<unsigned> u_pcode = {ub + wl.off_pcode};
-    const SPtr<double> u_btm = {ub + wl.off_btm};
-    typedef typename std::conditional<SPLIT, unsigned short, unsigned>::type BCode;   // edge in the low 16 bits
-    const SPtr<BCode> u_bcode = {ub + wl.off_bcode};
-
-    const bool trk = has_job && uhdr[0] != 0;
-    const bool accum_u = trk && uhdr[6] != 0;
-    // retained events of track k are the contiguous run [olo, ohi) of the (track, edge, time)
-    // sorted list (offsets per track: blink_setup)
-    const int olo = trk ? toff[k] : 0, ohi = trk ? toff[k + 1] : 0;
-    int bad = 0;
-    // per-track sequential stream: candidate gaps, thinning and backward-sampling decisions
-    NxbXo xo;
-    {
-        NxbU4 r = philox_call((unsigned)uhdr[3], (unsigned)uhdr[5], NXB_STREAM_BLK_FFBS | ((unsigned)k << 16), 0u, c.k0, c.k1);
-        xo.s0 = r.x; xo.s1 = r.y; xo.s2 = r.z; xo.s3 = r.w | 1u;
-    }
-
-    // ---- B1: upward pass.  Every lane walks its own track through the edges in descending
-    // index (children before parents), one boundary per iteration: a retained event of the old
-    // trajectory, a candidate, a primary event, or the top of the edge.  Candidates are the
-    // arrivals of the dominating Poisson process of the edge, generated backwards in time by
-    // exponential gaps (poisson.py:22-50 draws count + uniform times; same process), then thinned
-    // to the local rate (poisson.py:111-116).  Only accepted ("live") events are stored.
-    int cnt = 0;                       // live events pushed by this lane
-    {
-        // thinning acceptance as integer thresholds: accept iff u32 <= thr (an acceptance
-        // probability of exactly 1 becomes 1 - 2^-32)
-        const unsigned thr_o0 = (unsigned)fmin(ml.acc_blk[0] * 4294967296.0, 4294967295.0);
-        const unsigned thr_o1 = (unsigned)fmin(ml.acc_blk[1] * 4294967296.0, 4294967295.0);
-        const unsigned thr_w0 = (unsigned)fmin(ml.acc_blk[2] * 4294967296.0, 4294967295.0);
-        const unsigned thr_w1 = (unsigned)fmin(ml.acc_blk[3] * 4294967296.0, 4294967295.0);
-        const float a_on = (float)ml.a_on, a_off = (float)ml.a_off;
-        int e = trk ? E - 1 : -1;
-        int io = ohi - 1;              // cursor into the retained events (descending)
-        unsigned inited = 0u;          // live accumulator slots of this lane
-        bool fresh = true;
-        double tma = 0.0, rate = 0.0, tcur = 0.0, pen = 0.0;
-        float u0 = 1.f, u1 = 1.f;      // (OFF, ON) message at the current point of the walk
-        double tcand = -NXB_INF;
-        float gsc = 0.f;
-        int s = 0, ip = trk ? poff[E] - 1 : 0, ip0 = 0, sa_slot = 0, sb_slot = -1;
-        unsigned xold = 0u;
-        bool gap_due = false;
-        while (__any_sync(FULL, e >= 0)) {
-            if (e >= 0) {
-                // one gap is due: at the bottom of a fresh edge, or after the candidate consumed by the
-                // previous step (drawn here so that the walk has a single copy of the gap code)
-                bool draw_gap = gap_due;
-                gap_due = false;
-                if (fresh) {
-                    const NxbEdgeRec er = erec[e];
-                    sb_slot = er.sb_slot; sa_slot = er.sa_slot;
-                    tma = er.tma; rate = er.rate; tcur = er.tmb;
-                    u0 = 1.f; u1 = 1.f; pen = 0.0;
-                    if (sb_slot >= 0 && ((inited >> sb_slot) & 1u)) {
-                        const AccRec a = acc[sb_slot * K + k];
-                        u0 = a.u0; u1 = a.u1; pen = a.pen;
-                    }
-                    const uint4 nr = nrec[e];
-                    if (!((nr.x >> k) & 1u)) u1 = 0.f;
-                    if (!((nr.y >> k) & 1u)) u0 = 0.f;
-                    s = (int)(nr.w & 0xffu);
-                    xold = (nr.z >> k) & 1u;
-                    // the cursor into the primary events carries over from the edge before
-                    // (events are sorted by edge): only the lower bound is new
-                    ip0 = (int)(nr.w >> 8);
-                    // dominating rate of the edge: 2 * max(on, off) * rate_e per unit time
-                    gsc = er.gsc;
-                    draw_gap = gsc > 0.f;
-                    tcand = draw_gap ? tcur : -NXB_INF;
-                    fresh = false;
-                }
-                if (draw_gap) {
-                    tcand -= exp_gap(xo, gsc, k + 1);
-                    if (!(tcand > tma)) tcand = -NXB_INF;
-                }
-                const double tp = (ip >= ip0) ? u_ptm[ip] : -NXB_INF;
-                const bool haso = (io >= olo) && ((u_bcode[io] & 0xffffu) == (unsigned)e);
-                const double to = haso ? u_btm[io] : -NXB_INF;
-                const double tf = dmax2(to, tcand);
-                const double tnext = dmax2(dmax2(tp, tf), tma);
-                const bool own = (c.cls[s] == k);
-                // chunking.py:67-79: own class forces ON; ON pays the rate into class k
-                pen += c.qm[s * K + k] * rate * (tcur - tnext);
-                if (own) u0 = 0.f;
-                tcur = tnext;
-                if (tp == -NXB_INF && tf == -NXB_INF) {
-                    // top of the edge: fold into the parent's accumulator (one normalisation)
-                    const int ai = sa_slot * K + k;
-                    AccRec n; n.u0 = u0; n.u1 = u1; n.pen = pen;
-                    if ((inited >> sa_slot) & 1u) { const AccRec a = acc[ai]; n.u0 *= a.u0; n.u1 *= a.u1; n.pen += a.pen; }
-                    float m2 = fmaxf(n.u0, n.u1);
-                    if (!(m2 > 0.f)) { bad = 1; m2 = 1.f; }
-                    const float r2 = pow2_rescale_f(m2);
-                    n.u0 *= r2; n.u1 *= r2;
-                    acc[ai] = n;
-                    inited |= 1u << sa_slot;
-                    if (sb_slot >= 0) inited &= ~(1u << sb_slot);
-                    --e;
-                    fresh = true;
-                } else if (tf > tp) {
-                    bool live = true;
-                    if (to > tcand) { xold ^= 1u; --io; }
-                    else {
-                        const unsigned thr = own ? (xold ? thr_w1 : thr_w0) : (xold ? thr_o1 : thr_o0);
-                        // (a candidate that ties with a retained event is dropped: probability ~2^-50)
-                        live = (nxb_xo_next(xo) < thr) && (tcand != to);
-                        // next arrival of the dominating process (rootward): drawn by the next step;
-                        // until then the candidate slot is empty
-                        gap_due = true;
-                    }
-                    if (live) {
-                        // (messages are scale-free: with OFF impossible the factor is a pure rescaling
-                        // and is dropped, so that a long own-class segment cannot underflow ON to 0)
-                        if (pen != 0.0) { if (u0 != 0.f) u1 *= expf((float)(-pen)); pen = 0.0; }
-                        float mx = fmaxf(u0, u1);
-                        if (!(mx > 0.f)) { bad = 1; mx = 1.f; }
-                        const float r = pow2_rescale_f(mx);
-                        const float l1 = u1 * r, l0 = u0 * r;        // scale-free message below the event
-                        if (cnt < TCAP) {
-                            // Ratio by fast division (operands in [0, 2)) -- but a hard constraint must stay
-                            // exact: x / x is not guaranteed to be 1 there, and a q of 1 - 2^-24 in an own-class
-                            // segment (l0 == 0) let the downward pass switch the class off once in ~10^8
-                            // unit-sweeps.  l1 == 0 gives an exact 0.
-                            LiveEv ev; ev.t = tnext;
-                            ev.q = (l0 == 0.f) ? 1.f : fminf(__fdividef(l1, l0 + l1), 1.f);
-                            ev.e = (unsigned short)e; ev.pad = 0;
-                            cev[cnt] = ev;
-                        } else bad = 2;
-                        ++cnt;
-                        // uniformized 2x2 matrix of this context (poisson.py:92-96)
-                        if (own) { u0 = 0.5f * l0 + 0.5f * l1; u1 = l1; }
-                        else {
-                            u0 = l0 + a_on * (l1 - l0);
-                            u1 = l1 + a_off * (l0 - l1);
-                        }
-                    }
-                } else {
-                    s = (u_pcode[ip] >> 16) & 0xffu;     // rootward: the state before the event
-                    --ip;
-                }
-            }
-        }
-    }
+    TolCtx tc;
+    tc.p = c.p; tc.E = c.E; tc.P = c.P; tc.K = c.K;
+    tc.cls = c.cls; tc.qm = c.qm; tc.s_off_on = c.s_off_on; tc.k0 = c.k0; tc.k1 = c.k1;
+    TolLane<MSG> L;
+    TolUnit<MSG, SPLIT> u;
+    tol_begin<MSG, SPLIT>(tc, L, u, job, n_jobs, ub0, gb0);
+    tol_walk_up<MSG, SPLIT>(tc, L, u);
     __syncwarp();
     tick(c, T_B1);
+    tol_tree_up<MSG, SPLIT>(tc, L, u);
     phase_sync(c);
-    // ---- root draw (prior: toymodel.py:17-27 get_blink_distn) ----------------------------------------
-    unsigned x = 0u;
-    if (trk) {
-        const AccRec a = acc[c.slot[0] * K + k];
-        double w1 = (double)a.u1 * (a.u0 != 0.f ? exp(-a.pen) : 1.0) * ml.p_on;
-        double w0 = (double)a.u0 * ml.p_off;
-        if (!(((unsigned)uhdr[8] >> k) & 1u)) w1 = 0.0;
-        if (!(((unsigned)uhdr[9] >> k) & 1u)) w0 = 0.0;
-        if (c.cls[u_node_pri[0]] == k) w0 = 0.0;
-        if (!(w0 + w1 > 0.0)) bad = 1;
-        x = (nxb_u32(nxb_xo_next(xo)) * (w0 + w1) < w1) ? 1u : 0u;
-    }
-    if (trk && x) atomicOr(&newtol[0], 1u << k);
-    __syncwarp();
-
-    // ---- B2: downward sampling, edges in ascending index: the live events are read back in
-    // reverse; survivors (real transitions) are written from the top of the region downwards.
-    // The OFF-time and transition statistics are fused in (summary.py:123-131,234-243).
-    const NxbSummaryLayout& sl = p.sl;
-    int wtop = cnt - 1;            // survivors overwrite consumed records, from the last one down
-    {
-        const float a_on_f = (float)ml.a_on, a_off1_f = (float)(1.0 - ml.a_off);
-        int e = trk ? 0 : E;
-        int ir = cnt - 1;              // read cursor (descending)
-        bool fresh = true;
-        int s = 0, ip = 0, ipe = 0, vb = 0, n_on = 0, n_off = 0;
-        double tmb = 0.0, tcur = 0.0, offtime = 0.0;
-        LiveEv pf; pf.t = NXB_INF; pf.q = 0.f; pf.e = 0xffffu; pf.pad = 0;
-        if (ir >= 0) pf = cev[ir];
-        while (__any_sync(FULL, e < E)) {
-            if (e < E) {
-                if (fresh) {
-                    const NxbEdgeRec er = erec[e];
-                    vb = e + 1;
-                    const int va = er.va;
-                    x = (newtol[va] >> k) & 1u;
-                    s = u_node_pri[va];
-                    ip = poff[e]; ipe = poff[e + 1];
-                    tcur = er.tma; tmb = er.tmb;
-                    offtime = 0.0; n_on = 0; n_off = 0;
-                    fresh = false;
-                }
-                const double tp = (ip < ipe) ? u_ptm[ip] : NXB_INF;
-                const double tc = ((unsigned)pf.e == (unsigned)e) ? pf.t : NXB_INF;
-                const double tnext = dmin2(dmin2(tp, tc), tmb);
-                if (!x) offtime += tnext - tcur;
-                tcur = tnext;
-                if (tc < tp) {
-                    const float l1 = pf.q, l0 = 1.f - pf.q;
-                    --ir;
-                    // (the record at ir is in registers before a survivor may overwrite it: wtop >= ir)
-                    if (ir >= 0) pf = cev[ir];
-                    else { pf.t = NXB_INF; pf.e = 0xffffu; }
-                    const bool own = (c.cls[s] == k);
-                    const float p1 = own ? (x ? 1.f : 0.5f) : (x ? a_off1_f : a_on_f);
-                    const float w1 = p1 * l1, w0 = (1.f - p1) * l0;
-                    if (!(w0 + w1 > 0.f)) bad = 1;
-                    const float u = (float)(nxb_xo_next(xo) >> 8) * (1.0f / 16777216.0f);
-                    const unsigned xn = (u * (w0 + w1) < w1) ? 1u : 0u;
-                    if (xn != x) {
-                        LiveEv sv; sv.t = tc; sv.q = 0.f; sv.e = (unsigned short)(e | (xn ? CE_NEW1 : 0u)); sv.pad = 0;
-                        cev[wtop] = sv;
-                        --wtop;
-                        if (xn) ++n_on; else ++n_off;
-                        x = xn;
-                    }
-                } else {
-                    // primary event or the bottom of the edge: close the OFF-time segment
-                    if (accum_u && offtime > 0.0)
-                        atomicAdd(p.dwell + (sl.d_off + (e * P + s) * K + k), offtime);
-                    offtime = 0.0;
-                    if (tp != NXB_INF) {
-                        s = (u_pcode[ip] >> 24) & 0xffu;
-                        ++ip;
-                    } else {
-                        // packed word per edge (low: off->on, high: on->off), updated by halves with
-                        // native 32-bit shared atomics; a CTA books far fewer than 2^32 per launch
-                        if (accum_u && n_on) atomicAdd((unsigned*)&c.s_off_on[e], (unsigned)n_on);
-                        if (accum_u && n_off) atomicAdd((unsigned*)&c.s_off_on[e] + 1, (unsigned)n_off);
-                        if (x) atomicOr(&newtol[vb], 1u << k);
-                        ++e;
-                        fresh = true;
-                    }
-                }
-            }
-        }
-    }
-    if (trk) {
-        uhdr[10 + k] = (cnt - 1 - wtop) | (cnt << 16);   // survivors of this track | live events
-        if (bad) atomicOr(&uhdr[4], bad);
-    }
+    tol_tree_down<MSG, SPLIT>(tc, L, u);
     tick(c, T_B2);
+    tol_walk_down<MSG, SPLIT>(tc, L, u);
+    tick(c, T_BW);
 }
 
 // ---- S3 (the warp that owns the unit): write back the new retained blink events
 // SPLIT: the new list goes straight to the unit's slab (the shared-memory copy is not needed again).
-template <bool SPLIT>
+template <typename MSG, bool SPLIT>
 __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
     const NxbSweepParams& p = *c.p;
     const NxbWarpLayout& wl = p.wl;
@@ -1082,7 +782,7 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         if (flags & 2) { fail(c, NXB_ERR_SCRATCH_CAP, 0); return RC_ERROR; }
         if (flags & 1) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
     }
-    LiveEv* cev_own = (LiveEv*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
+    TolRec<MSG>* cev_own = (TolRec<MSG>*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
     const int packed = (lane < K) ? uhdr_own[10 + lane] : 0;
     const int n_mine = packed & 0xffff, n_live = packed >> 16;
     int total;
@@ -1107,13 +807,12 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         obcode = (unsigned*)(slab + p.so_bcode);
     }
     for (int q = 0; q < n_mine; ++q) {
-        const LiveEv sv = cev_own[n_live - 1 - q];      // first survivor (rootmost, earliest) on top
-        const unsigned ce = sv.e;
+        const TolRec<MSG> sv = cev_own[n_live - 1 - q];      // first survivor (rootmost, earliest) on top
+        const unsigned ce = sv.code;
         obtm[dst + q] = sv.t;
         obcode[dst + q] = (unsigned)(ce & CE_EDGE) | ((unsigned)lane << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);
     }
     __syncwarp();
-    tick(c, T_BW);
     if (spill && !SPLIT) { c.nB = -total; return RC_DEFER; }
     c.nB = total;
     return RC_OK;
@@ -1122,16 +821,17 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
 
 // TOLERANCE UPDATE of the fused kernel: the warps of a lockstep group set up their own units,
 // then carry the group's (unit, track) jobs, then write their own units back.
+template <typename MSG>
 __device__ __forceinline__ int blink_phase(Ctx& c, bool accumulate, bool active) {
     phase_sync(c);
     blink_setup<false>(c, accumulate, active, sm_ptr<const unsigned>(c.tt_ok.off), sm_ptr<const unsigned>(c.tf_ok.off), nullptr);
     tick(c, T_B0);
     phase_sync(c);            // (a named barrier orders shared memory across the group)
     const int GW = c.bar_threads >> 5;                 // 1 when the warps run independently
-    blink_job<false>(c, c.wing * 32 + c.lane, GW * c.K, c.gwbase, c.ggbase);
+    blink_job<MSG, false>(c, c.wing * 32 + c.lane, GW * c.K, c.gwbase, c.ggbase);
     phase_sync(c);
     if (!active) return RC_OK;
-    return blink_finish<false>(c, accumulate);
+    return blink_finish<MSG, false>(c, accumulate);
 }
 
 // ---------------------------------------------------------------------------

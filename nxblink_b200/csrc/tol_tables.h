@@ -1,0 +1,113 @@
+// Host-side construction of the model tables of the tolerance update (plain C++, no CUDA): the
+// prefix of the model blob that blink_kernel stages into shared memory.  Shared by nxb_api.cu (the
+// product) and oracle/hostsim (the CPU simulation of the per-lane code, test infrastructure).
+#pragma once
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/nxblink_b200.h"
+#include "nxb_types.h"
+
+// Fills the tolerance-update fields of `ml` (nslots, a_on/a_off, acc_blk, p_on/p_off, sum_w,
+// gsc_sigma, loc_steps and the off_* of the tables below) and appends to `blob`:
+//   NxbEdgeRec[E], NxbEdgeLoc[E], cumw f64[E], slot int[N], cls u8[P], qm f64[P*K]
+// ml.N/E/P/K must be set.  Returns 0, or 1 with a message.
+static inline int nxb_build_tol_tables(const nxb_model_desc* d, NxbModelLayout& ml,
+                                       std::vector<unsigned char>& blob, std::string& err) {
+    const int N = d->n_nodes, P = d->n_states, K = d->n_classes, E = N - 1;
+    auto align_up = [](int x, int a) { return (x + a - 1) / a * a; };
+    auto put = [&](const void* src, int bytes, int al) {
+        int o = align_up((int)blob.size(), al);
+        blob.resize(o + bytes);
+        memcpy(blob.data() + o, src, bytes);
+        return o;
+    };
+    std::vector<double> tm(N, 0.0);
+    for (int v = 1; v < N; ++v) tm[v] = tm[d->parent[v]] + d->blen[v];
+    // accumulator slots of the upward tree pass (edges in descending index)
+    std::vector<int> slot(N, -1);
+    {
+        std::vector<int> free_slots;
+        int next = 0;
+        for (int e = E - 1; e >= 0; --e) {
+            int vb = e + 1, va = d->parent[vb];
+            if (slot[va] < 0) {
+                if (!free_slots.empty()) {
+                    auto it = std::min_element(free_slots.begin(), free_slots.end());
+                    slot[va] = *it; free_slots.erase(it);
+                } else slot[va] = next++;
+            }
+            if (slot[vb] >= 0) free_slots.push_back(slot[vb]);
+        }
+        ml.nslots = std::max(next, 1);
+        if (ml.nslots > 32) {
+            err = "tree needs more than 32 live accumulators; renumber nodes depth-first";
+            return 1;
+        }
+    }
+    const double M = std::max(d->rate_on, d->rate_off);
+    ml.rate_on = d->rate_on; ml.rate_off = d->rate_off;
+    ml.a_on = d->rate_on / (2.0 * M);
+    ml.a_off = d->rate_off / (2.0 * M);
+    ml.acc_blk[0] = (2.0 * M - d->rate_on) / (2.0 * M);   // other class, track OFF
+    ml.acc_blk[1] = (2.0 * M - d->rate_off) / (2.0 * M);  // other class, track ON
+    ml.acc_blk[2] = d->rate_on / (2.0 * M);               // own class, OFF (infeasible state)
+    ml.acc_blk[3] = d->rate_on / M;                       // own class, ON
+    ml.p_on = d->rate_on / (d->rate_on + d->rate_off);
+    ml.p_off = d->rate_off / (d->rate_on + d->rate_off);
+
+    std::vector<NxbEdgeRec> recs(E);
+    std::vector<char> seen(N, 0);
+    for (int e = E - 1; e >= 0; --e) {
+        const int va = d->parent[e + 1];
+        memset(&recs[e], 0, sizeof(NxbEdgeRec));
+        recs[e].tma = tm[va]; recs[e].tmb = tm[va] + d->blen[e + 1]; recs[e].rate = d->rate[e + 1];
+        recs[e].va = (unsigned short)va;
+        recs[e].sa_slot = (signed char)slot[va];
+        recs[e].sb_slot = (signed char)slot[e + 1];
+        unsigned short fl = 0;
+        if (!seen[va]) { fl |= NXB_EF_FIRST; seen[va] = 1; }      // edges fold in descending index
+        // The parent of this edge is node e: the child node of edge e - 1, and this edge is the
+        // last of its children to fold (children have larger indices).  Edge 0 hangs from the root.
+        if (va == e) fl |= NXB_EF_CHAIN_UP | NXB_EF_CHAIN_DOWN;
+        recs[e].flags = fl;
+    }
+    ml.off_edgerec = put(recs.data(), (int)(sizeof(NxbEdgeRec) * E), 16);
+    // the rate-time line of the tree: edges in walk order (E-1 first), leafward to rootward
+    std::vector<NxbEdgeLoc> locs(E);
+    std::vector<double> cumw(E);
+    double run = 0.0;
+    for (int j = 0; j < E; ++j) {
+        const int e = E - 1 - j;
+        const bool active = d->rate[e + 1] > 0.0 && d->blen[e + 1] > 0.0;
+        const double w = recs[e].rate * (recs[e].tmb - recs[e].tma);   // as the device computes it
+        locs[e].cum_excl = run;
+        locs[e].inv_rate = active ? 1.0 / recs[e].rate : 0.0;
+        run += active ? w : 0.0;
+        cumw[j] = run;
+    }
+    ml.off_edgeloc = put(locs.data(), (int)(sizeof(NxbEdgeLoc) * E), 16);
+    ml.off_cumw = put(cumw.data(), 8 * E, 8);
+    ml.sum_w = run;
+    ml.gsc_sigma = (float)(0.6931471805599453 / (2.0 * M));
+    {
+        int st = 1;
+        while (2 * st <= E) st *= 2;
+        ml.loc_steps = st;
+    }
+    ml.off_slot = put(slot.data(), 4 * N, 4);
+    std::vector<unsigned char> cls(P);
+    for (int s = 0; s < P; ++s) cls[s] = (unsigned char)d->state_class[s];
+    ml.off_cls = put(cls.data(), P, 1);
+    std::vector<double> qm((size_t)P * K, 0.0);
+    for (int s = 0; s < P; ++s)
+        for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i)
+            qm[(size_t)s * K + d->state_class[d->q_col[i]]] += d->q_val[i];
+    ml.off_qm = put(qm.data(), 8 * P * K, 8);
+    blob.resize(align_up((int)blob.size(), 16));
+    ml.blink_bytes = (int)blob.size();
+    return 0;
+}

@@ -5,6 +5,7 @@ TEST INFRASTRUCTURE ONLY.  Usage (from the repo root, where /root/reference exis
 
     python -m oracle.refcompat.make_golden toy      # tests/golden/ref_toy.json
     python -m oracle.refcompat.make_golden p53 0    # tests/golden/ref_p53_site0.json
+    python -m oracle.refcompat.make_golden p53long 0 [nsamples]   # tests/golden/ref_p53_long_site0.json
     python -m oracle.refcompat.make_golden mg94     # tests/golden/ref_mg94.json
     python -m oracle.refcompat.make_golden ell      # tests/golden/ref_ell_contrib.json
 
@@ -223,6 +224,66 @@ def make_p53(site, nsamples=600, nburnin=30):
     print('p53 site', site, 'done in %.1fs' % rec['seconds'])
 
 
+def edge_vector(summary, edges):
+    """Per-edge cumulative statistics of the running summary (one row per edge)."""
+    return np.array([[
+        sum(d['weight'] for a, b, d in summary.edge_to_pri_trans[e].edges(data=True)),
+        sum(d['weight'] for a, b, d in summary.edge_to_pri_dwell[e].edges(data=True)),
+        summary.edge_to_off_xon_trans[e], summary.edge_to_xon_off_trans[e],
+        summary.edge_to_off_xon_dwell[e], summary.edge_to_xon_off_dwell[e]] for e in edges],
+        dtype=np.float64)
+
+
+EDGE_STATS = ('pri_trans', 'pri_dwell', 'off_xon_trans', 'xon_off_trans', 'off_xon_dwell',
+        'xon_off_dwell')
+
+
+def make_p53_long(site, nsamples=10000, nburnin=50, nbatches=50):
+    """A long run of the reference sampler at the p53 shape with PER-EDGE statistics and
+    batch-means standard errors (tests/golden/ref_p53_long_site*.json): the sharp parity gate
+    for the sampled quantities at the p53 shape (the 600-sample fixtures only carry 7 scalars)."""
+    loader.load()
+    from nxblink.raoteh import gen_samples
+    from nxblink.summary import Summary
+    from nxblink.util import get_node_to_tm
+    m, pm, ls, tt, tf = p53_inputs()
+    data = MaskData(pm, ls[site], tt[site], tf[site])
+    model = NxAdapter(m)
+    t0 = time.time()
+    np.random.seed(7770 + site)
+    T, root = model.get_T_and_root()
+    node_to_tm = get_node_to_tm(T, root, model.get_edge_to_blen())
+    summary = Summary(T, root, node_to_tm, model.get_primary_to_tol(), model.get_Q_primary())
+    edges = [(pm.nodes[pm.parent[v]], pm.nodes[v]) for v in range(1, pm.n_nodes)]
+    b = nsamples // nbatches
+    marks, roots = [edge_vector(summary, edges)], [(0.0, 0.0)]
+    n = 0
+    for pri, tols in gen_samples(model, data, nburnin, b * nbatches):
+        summary.on_sample(pri, tols)
+        n += 1
+        if n % b == 0:
+            marks.append(edge_vector(summary, edges))
+            roots.append((float(summary.root_off_count), float(summary.root_xon_count)))
+            print('site', site, n, 'samples, %.0fs' % (time.time() - t0))
+            sys.stdout.flush()
+    per = np.diff(np.array(marks), axis=0) / b            # [nbatches, E, 6] per-sample means
+    rper = np.diff(np.array(roots), axis=0) / b
+    rec = dict(site=site, nsamples=b * nbatches, nburnin=nburnin, nbatches=nbatches,
+            seconds=time.time() - t0, stats=list(EDGE_STATS),
+            edge_mean=per.mean(axis=0).tolist(),
+            edge_se=(per.std(axis=0, ddof=1) / np.sqrt(nbatches)).tolist(),
+            root_mean=dict(off_root=float(rper[:, 0].mean()), xon_root=float(rper[:, 1].mean())),
+            root_se=dict(off_root=float(rper[:, 0].std(ddof=1) / np.sqrt(nbatches)),
+                xon_root=float(rper[:, 1].std(ddof=1) / np.sqrt(nbatches))),
+            root_pri_to_count=dict((repr(k), int(v)) for k, v in summary.root_pri_to_count.items()),
+            leaf_states=[int(x) for x in ls[site]],
+            tol_true_ok=[int(x) for x in tt[site]], tol_false_ok=[int(x) for x in tf[site]],
+            node_order=[repr(x) for x in pm.nodes])
+    with open(os.path.join(GOLDEN, 'ref_p53_long_site%d.json' % site), 'w') as f:
+        json.dump(rec, f, sort_keys=True)
+    print('p53 long site', site, 'done in %.1fs' % rec['seconds'])
+
+
 def make_ell(nsamples=6, nburnin=5):
     """Trajectories sampled by the reference together with the reference's own per-sample
     functionals of them (summary.py:247-348 as driven by toymodel-stochastic.py:137-196)."""
@@ -299,6 +360,8 @@ if __name__ == '__main__':
         make_toy()
     elif what == 'p53':
         make_p53(int(sys.argv[2]))
+    elif what == 'p53long':
+        make_p53_long(int(sys.argv[2]), *[int(x) for x in sys.argv[3:]])
     elif what == 'mg94':
         make_mg94()
     elif what == 'ell':
