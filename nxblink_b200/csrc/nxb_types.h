@@ -56,10 +56,7 @@ struct NxbModelLayout {
     int off_lam_blk;    // f64    [E]   dominating Poisson mean, one blink track
     int off_p0_blk;     // f64    [E]   exp(-lam_blk)
     int off_gsc_blk;    // f32    [E]   ln2 / (dominating blink rate of the edge), 0 if inactive
-    int off_edgerec;    // NxbEdgeRec [E]  the per-edge constants of the tolerance update, one 32-byte record
-    int off_edgeloc;    // NxbEdgeLoc [E]  rate-time coordinate of the edge (candidate placement), 16 bytes
-    int off_cumw;       // f64    [E]   inclusive prefix of rate x length in walk order (edge E-1 first)
-    int loc_steps;      // largest power of two <= E (first step of the branch-free search in off_cumw)
+    int off_edgerec;    // NxbEdgeRec [E]  the per-edge constants of the blink walks, one 32-byte record
     int off_qval;       // f64    [nnz] normalised primary rates (CSR values)
     int off_qinfo;      // u16    [nnz] column | class(column) << 8
     int off_qptr;       // u16    [P+1]
@@ -77,33 +74,16 @@ struct NxbModelLayout {
     double inv_omega_pri;   // 1 / (2 * Rmax(all classes on))
     double acc_blk[4];      // thinning acceptance [own][fg state]
     double a_on, a_off;     // off-diagonal entries of the uniformized 2x2 blink matrix
-    double sum_w;           // sum over edges of rate x length
-    float gsc_sigma;        // ln2 / dominating blink rate, in rate-time units (gap = -log2(u) * gsc_sigma)
-    float pad_f;
     double p_on, p_off;     // blink prior at the root
 };
 
-// Per-edge constants of the tolerance update (tree passes and walks).
-enum {
-    NXB_EF_FIRST = 1,       // the first child edge to fold into its parent's accumulator (assigns it)
-    NXB_EF_CHAIN_UP = 2,    // upward pass: the next edge (e - 1) is the edge above this edge's parent,
-                            // whose accumulator is complete after this fold: it stays in registers
-    NXB_EF_CHAIN_DOWN = 4,  // downward pass: the parent of this edge is the child node of edge e - 1
-};
+// Per-edge constants read at every edge boundary of the tolerance walks.
 struct __align__(16) NxbEdgeRec {
     double tma, tmb;        // times at the rootward / leafward end
     double rate;            // edge rate scaling factor
-    unsigned short flags;   // NXB_EF_*
+    float gsc;              // ln2 / dominating blink rate (0: no events possible on this edge)
     unsigned short va;      // parent node (the child node is e + 1)
     signed char sa_slot, sb_slot;   // accumulator slots of parent and child (-1: leaf)
-    unsigned short pad;
-};
-// Where edge e lies on the rate-time line that the candidate events of a tolerance track are drawn
-// on: the edges in walk order (E-1 first, each from its leafward to its rootward end), position =
-// cumulative rate x length.
-struct __align__(16) NxbEdgeLoc {
-    double cum_excl;        // rate-time before the leafward end of this edge
-    double inv_rate;        // 1 / rate (0 for an edge without events)
 };
 
 // Per-warp shared-memory layout (bytes from the warp's base), chosen by the host

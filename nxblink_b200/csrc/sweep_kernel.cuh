@@ -726,14 +726,12 @@ __device__ __forceinline__ void blink_setup(Ctx& c, bool accumulate, bool active
         if (lane == 0) toff_own[K] = total;
     }
     if (active) {
-        // one 16-byte record per edge: data masks, old tolerance states and primary state of the
-        // lower node, whether the edge holds primary events, and the index of its first one
+        // one 16-byte record per edge for the upward walk: data masks, old tolerance states and
+        // primary state of the lower node, and the index of the edge's first primary event
         const SPtr<uint4> nrec_own = {c.wbase + wl.off_nrec};
-        for (int e = lane; e < c.E; e += 32) {
-            const unsigned lo = (unsigned)c.poff[e], hi = (unsigned)c.poff[e + 1];
+        for (int e = lane; e < c.E; e += 32)
             nrec_own[e] = make_uint4(tt[e + 1], tf[e + 1], c.node_tol[e + 1],
-                                     (unsigned)c.node_pri[e + 1] | (hi != lo ? 0x100u : 0u) | (lo << 9));
-        }
+                                     (unsigned)c.node_pri[e + 1] | ((unsigned)c.poff[e] << 8));
     }
     if (lane == 0) {
         uhdr_own[0] = active ? 1 : 0; uhdr_own[2] = c.nB; uhdr_own[3] = (int)c.unit32; uhdr_own[4] = 0;
@@ -751,19 +749,16 @@ template <typename MSG, bool SPLIT>
 __device__ __forceinline__ void blink_job(Ctx& c, int job, int n_jobs, unsigned ub0, unsigned char* gb0) {
     TolCtx tc;
     tc.p = c.p; tc.E = c.E; tc.P = c.P; tc.K = c.K;
-    tc.cls = c.cls; tc.qm = c.qm; tc.s_off_on = c.s_off_on; tc.k0 = c.k0; tc.k1 = c.k1;
+    tc.cls = c.cls; tc.qm = c.qm; tc.slot = c.slot; tc.s_off_on = c.s_off_on; tc.k0 = c.k0; tc.k1 = c.k1;
     TolLane<MSG> L;
     TolUnit<MSG, SPLIT> u;
     tol_begin<MSG, SPLIT>(tc, L, u, job, n_jobs, ub0, gb0);
-    tol_walk_up<MSG, SPLIT>(tc, L, u);
+    const unsigned x_root = tol_up<MSG, SPLIT>(tc, L, u);
     __syncwarp();
     tick(c, T_B1);
-    tol_tree_up<MSG, SPLIT>(tc, L, u);
     phase_sync(c);
-    tol_tree_down<MSG, SPLIT>(tc, L, u);
+    tol_down<MSG, SPLIT>(tc, L, u, x_root);
     tick(c, T_B2);
-    tol_walk_down<MSG, SPLIT>(tc, L, u);
-    tick(c, T_BW);
 }
 
 // ---- S3 (the warp that owns the unit): write back the new retained blink events
@@ -782,7 +777,7 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         if (flags & 2) { fail(c, NXB_ERR_SCRATCH_CAP, 0); return RC_ERROR; }
         if (flags & 1) { fail(c, NXB_ERR_INFEASIBLE, -3); return RC_ERROR; }
     }
-    TolRec<MSG>* cev_own = (TolRec<MSG>*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
+    LiveEv<MSG>* cev_own = (LiveEv<MSG>*)(c.gbase + p.g_off_ctm) + (size_t)lane * TCAP;
     const int packed = (lane < K) ? uhdr_own[10 + lane] : 0;
     const int n_mine = packed & 0xffff, n_live = packed >> 16;
     int total;
@@ -807,12 +802,13 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         obcode = (unsigned*)(slab + p.so_bcode);
     }
     for (int q = 0; q < n_mine; ++q) {
-        const TolRec<MSG> sv = cev_own[n_live - 1 - q];      // first survivor (rootmost, earliest) on top
-        const unsigned ce = sv.code;
+        const LiveEv<MSG> sv = cev_own[n_live - 1 - q];      // first survivor (rootmost, earliest) on top
+        const unsigned ce = sv.e;
         obtm[dst + q] = sv.t;
         obcode[dst + q] = (unsigned)(ce & CE_EDGE) | ((unsigned)lane << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);
     }
     __syncwarp();
+    tick(c, T_BW);
     if (spill && !SPLIT) { c.nB = -total; return RC_DEFER; }
     c.nB = total;
     return RC_OK;

@@ -11,9 +11,9 @@
 #include "../../include/nxblink_b200.h"
 #include "nxb_types.h"
 
-// Fills the tolerance-update fields of `ml` (nslots, a_on/a_off, acc_blk, p_on/p_off, sum_w,
-// gsc_sigma, loc_steps and the off_* of the tables below) and appends to `blob`:
-//   NxbEdgeRec[E], NxbEdgeLoc[E], cumw f64[E], slot int[N], cls u8[P], qm f64[P*K]
+// Fills the tolerance-update fields of `ml` (nslots, a_on/a_off, acc_blk, p_on/p_off and the off_*
+// of the tables below) and appends to `blob`:
+//   NxbEdgeRec[E], slot int[N], cls u8[P], qm f64[P*K]
 // ml.N/E/P/K must be set.  Returns 0, or 1 with a message.
 static inline int nxb_build_tol_tables(const nxb_model_desc* d, NxbModelLayout& ml,
                                        std::vector<unsigned char>& blob, std::string& err) {
@@ -60,44 +60,18 @@ static inline int nxb_build_tol_tables(const nxb_model_desc* d, NxbModelLayout& 
     ml.p_off = d->rate_off / (d->rate_on + d->rate_off);
 
     std::vector<NxbEdgeRec> recs(E);
-    std::vector<char> seen(N, 0);
-    for (int e = E - 1; e >= 0; --e) {
+    for (int e = 0; e < E; ++e) {
         const int va = d->parent[e + 1];
+        const double len = d->blen[e + 1], rate = d->rate[e + 1];
         memset(&recs[e], 0, sizeof(NxbEdgeRec));
-        recs[e].tma = tm[va]; recs[e].tmb = tm[va] + d->blen[e + 1]; recs[e].rate = d->rate[e + 1];
+        recs[e].tma = tm[va]; recs[e].tmb = tm[va] + len; recs[e].rate = rate;
+        // ln2 / (dominating rate 2 * max(on, off) * rate_e); 0: no events possible on this edge
+        recs[e].gsc = (rate > 0.0 && len > 0.0) ? (float)(0.6931471805599453 / (2.0 * M * rate)) : 0.f;
         recs[e].va = (unsigned short)va;
         recs[e].sa_slot = (signed char)slot[va];
         recs[e].sb_slot = (signed char)slot[e + 1];
-        unsigned short fl = 0;
-        if (!seen[va]) { fl |= NXB_EF_FIRST; seen[va] = 1; }      // edges fold in descending index
-        // The parent of this edge is node e: the child node of edge e - 1, and this edge is the
-        // last of its children to fold (children have larger indices).  Edge 0 hangs from the root.
-        if (va == e) fl |= NXB_EF_CHAIN_UP | NXB_EF_CHAIN_DOWN;
-        recs[e].flags = fl;
     }
     ml.off_edgerec = put(recs.data(), (int)(sizeof(NxbEdgeRec) * E), 16);
-    // the rate-time line of the tree: edges in walk order (E-1 first), leafward to rootward
-    std::vector<NxbEdgeLoc> locs(E);
-    std::vector<double> cumw(E);
-    double run = 0.0;
-    for (int j = 0; j < E; ++j) {
-        const int e = E - 1 - j;
-        const bool active = d->rate[e + 1] > 0.0 && d->blen[e + 1] > 0.0;
-        const double w = recs[e].rate * (recs[e].tmb - recs[e].tma);   // as the device computes it
-        locs[e].cum_excl = run;
-        locs[e].inv_rate = active ? 1.0 / recs[e].rate : 0.0;
-        run += active ? w : 0.0;
-        cumw[j] = run;
-    }
-    ml.off_edgeloc = put(locs.data(), (int)(sizeof(NxbEdgeLoc) * E), 16);
-    ml.off_cumw = put(cumw.data(), 8 * E, 8);
-    ml.sum_w = run;
-    ml.gsc_sigma = (float)(0.6931471805599453 / (2.0 * M));
-    {
-        int st = 1;
-        while (2 * st <= E) st *= 2;
-        ml.loc_steps = st;
-    }
     ml.off_slot = put(slot.data(), 4 * N, 4);
     std::vector<unsigned char> cls(P);
     for (int s = 0; s < P; ++s) cls[s] = (unsigned char)d->state_class[s];

@@ -79,7 +79,7 @@ static int run(const nxb_model_desc* d, hs_unit* un, uint64_t seed, uint32_t uni
     // pool: generous
     const int TCAP = 4096;
     p.gcapC = TCAP; p.g_off_ctm = 0;
-    p.gscratch_stride = (long long)sizeof(TolRec<MSG>) * TCAP * K;
+    p.gscratch_stride = (long long)sizeof(LiveEv<MSG>) * TCAP * K;
     std::vector<unsigned char> pool((size_t)p.gscratch_stride + 64);
     unsigned char* gb0 = (unsigned char*)(((uintptr_t)pool.data() + 15) & ~(uintptr_t)15);
     p.sl.d_off = 0;
@@ -108,9 +108,8 @@ static int run(const nxb_model_desc* d, hs_unit* un, uint64_t seed, uint32_t uni
     }
     for (int k = 0; k < K; ++k) toff[k + 1] += toff[k];
     for (int e = 0; e < E; ++e) {
-        const unsigned lo = (unsigned)poff[e], hi = (unsigned)poff[e + 1];
         nrec[e].x = un->tt[e + 1]; nrec[e].y = un->tf[e + 1]; nrec[e].z = un->node_tol[e + 1];
-        nrec[e].w = (unsigned)node_pri[e + 1] | (hi != lo ? 0x100u : 0u) | (lo << 9);
+        nrec[e].w = (unsigned)node_pri[e + 1] | ((unsigned)poff[e] << 8);
     }
     memset(uhdr, 0, 4 * (10 + 32));
     uhdr[0] = 1; uhdr[2] = un->n_blk; uhdr[3] = (int)unit; uhdr[4] = 0; uhdr[5] = (int)sweep; uhdr[6] = accumulate ? 1 : 0;
@@ -118,7 +117,7 @@ static int run(const nxb_model_desc* d, hs_unit* un, uint64_t seed, uint32_t uni
     // ---- lane jobs ----
     TolCtx tc;
     tc.p = &p; tc.E = E; tc.P = P; tc.K = K;
-    tc.cls.off = (unsigned)ml.off_cls; tc.qm.off = (unsigned)ml.off_qm;
+    tc.cls.off = (unsigned)ml.off_cls; tc.qm.off = (unsigned)ml.off_qm; tc.slot.off = (unsigned)ml.off_slot;
     tc.s_off_on.off = (unsigned)ml.off_stats;
     tc.k0 = (unsigned)(seed & 0xffffffffull); tc.k1 = (unsigned)(seed >> 32);
     int total_live = 0;
@@ -126,10 +125,8 @@ static int run(const nxb_model_desc* d, hs_unit* un, uint64_t seed, uint32_t uni
         TolLane<MSG> L;
         TolUnit<MSG, true> u;
         tol_begin<MSG, true>(tc, L, u, k, K, ub, gb0);
-        tol_walk_up<MSG, true>(tc, L, u);
-        tol_tree_up<MSG, true>(tc, L, u);
-        tol_tree_down<MSG, true>(tc, L, u);
-        tol_walk_down<MSG, true>(tc, L, u);
+        const unsigned x_root = tol_up<MSG, true>(tc, L, u);
+        tol_down<MSG, true>(tc, L, u, x_root);
         total_live += L.cnt;
     }
     if (n_live_out) *n_live_out = total_live;
@@ -138,12 +135,12 @@ static int run(const nxb_model_desc* d, hs_unit* un, uint64_t seed, uint32_t uni
     int dst = 0;
     for (int k = 0; k < K; ++k) {
         const int packed = uhdr[10 + k], n_mine = packed & 0xffff, n_live = packed >> 16;
-        const TolRec<MSG>* cev = (const TolRec<MSG>*)(gb0 + p.g_off_ctm) + (size_t)k * TCAP;
+        const LiveEv<MSG>* cev = (const LiveEv<MSG>*)(gb0 + p.g_off_ctm) + (size_t)k * TCAP;
         for (int q = 0; q < n_mine; ++q) {
-            const TolRec<MSG> sv = cev[n_live - 1 - q];
+            const LiveEv<MSG> sv = cev[n_live - 1 - q];
             if (dst >= un->cap_blk) return 3;
             un->btm[dst] = sv.t;
-            un->bcode[dst] = (sv.code & CE_EDGE) | ((unsigned)k << 16) | ((sv.code & CE_NEW1) ? (1u << 31) : 0u);
+            un->bcode[dst] = ((unsigned)sv.e & CE_EDGE) | ((unsigned)k << 16) | ((sv.e & CE_NEW1) ? (1u << 31) : 0u);
             ++dst;
         }
     }

@@ -2,8 +2,8 @@
 host (oracle/hostsim) and run as a Markov chain on ONE unit with a fixed primary trajectory,
 against the EXACT conditional posterior of every tolerance track (oracle/tol_exact.py): node
 marginals, expected off->on / on->off transitions per edge, OFF dwell per (edge, primary state,
-track).  This is the target of raoteh.py:413-432; it checks the device algorithm itself (events-only
-walk, per-edge transfer records, tree passes) without a GPU.  The GPU parity tests run the same
+track).  This is the target of raoteh.py:413-432; it checks the device algorithm itself (candidate
+generation by thinning, the upward walk with its node accumulators, the backward draw) without a GPU.  The GPU parity tests run the same
 source on the device.
 
 Tolerance: |mean - exact| <= 5.5 batch-means standard errors (20 batches); quantities without
@@ -105,7 +105,9 @@ def _run(pm, msg_f64, nsweep, seed, nsub=32, nbatch=20, min_rate=0.0, burn=100):
         se = got.std(axis=0, ddof=1) / np.sqrt(nbatch)
         # no spread over the batches: a hard constraint (exact match), or an event so rare that it
         # never happened in nsweep draws (its exact expectation must then be below ~8 / nsweep)
-        det = se < 1e-12
+        # (the same bound where fewer than 5 of the batches saw the event at all: a standard
+        # error from one or two occurrences is no basis for a z-score)
+        det = (se < 1e-12) | ((got != 0).sum(axis=0) < 5)
         assert np.all(np.abs(m - exact)[det] < 8.0 / nsweep), (what, np.abs(m - exact)[det].max())
         z = np.abs(m - exact)[~det] / se[~det]
         return float(z.max()) if z.size else 0.0
