@@ -151,7 +151,7 @@ int nxb_last_kernel_ms_by_kind(nxb_handle* h, float ms[4], int32_t n_launches[4]
 
 /* Per-phase cycle counters of the sweep kernel (lane 0 of every warp, summed):
  * load, P0..P5 (primary update), B0..B2 + write-back (tolerance updates), store.
- * `enable` switches collection on/off; if cycles12 is non-NULL the 12 counters are
+ * `enable` switches collection on/off; if cycles12 is non-NULL the 24 counters (12 of the sweep kernels, 12 of tolpar_kernel) are
  * copied out and cleared.  Diagnostic only. */
 int nxb_profile(nxb_handle* h, int32_t enable, uint64_t* cycles12);
 

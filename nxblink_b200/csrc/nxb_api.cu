@@ -10,9 +10,11 @@
 
 #include "../../include/nxblink_b200.h"
 #include "sweep_kernel.cuh"
+#include "tol_par.cuh"
 #include "tol_tables.h"
 
 #define NXB_MAX_THREADS 640
+#define NXB_TP_THREADS 640         /* tolpar_kernel: up to 20 warps (10 units x 2 warps at the p53 shape) */
 #define NXB_BLINK_THREADS 800      /* 25 warps at 72 registers: 40 units x 20 tracks per CTA at the p53 shape */
 
 namespace nxb {
@@ -160,7 +162,9 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             if (p.init) { hdr.sweeps_done = 0; hdr.n_pri = 0; hdr.n_blk = 0; hdr.phase = NXB_PHASE_INIT; hdr.pad = 0; }
             const bool off_schedule = (lockstep || PRIMARY_ONLY) && !p.init &&
                 (hdr.phase != NXB_PHASE_PRIMARY || hdr.sweeps_done != p.begin_sweeps);
-            if ((int)hdr.n_pri > wl.capP || (int)hdr.n_blk > wl.capB || off_schedule) {
+            if (PRIMARY_ONLY && p.unit_list && !p.init && hdr.phase == NXB_PHASE_BLINK && hdr.sweeps_done == p.begin_sweeps) {
+                has = false;        // (deferred by the tolerance kernel of the tier before: that kernel's turn)
+            } else if ((int)hdr.n_pri > wl.capP || (int)hdr.n_blk > wl.capB || off_schedule) {
                 // does not fit this tier's shared-memory arrays: untouched, next tier
                 if (lane == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)u;
                 has = false;
@@ -383,6 +387,134 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
             tick(c, T_STORE);
         }
         __syncthreads();
+    }
+    cta_epilogue(c, p, tid);
+}
+
+
+// ---------------------------------------------------------------------------
+// TOLERANCE UPDATE, event-parallel form (tol_par.cuh): a group of WPU warps owns one unit at a
+// time; the unit's trajectory and its whole event pool live in shared memory.  Units are in phase
+// BLINK at sweep p.begin_sweeps (the primary-only sweep_kernel ran just before) and in phase
+// PRIMARY of the next sweep after.  Units that are elsewhere are skipped; units whose events do not
+// fit the shared-memory capacities of this tier are listed for the next one, untouched.
+// ---------------------------------------------------------------------------
+template <typename MSG, int WPU>
+__global__ void __launch_bounds__(NXB_TP_THREADS, 1)
+tolpar_kernel(const __grid_constant__ NxbSweepParams p) {
+    const NxbModelLayout& ml = p.ml;
+    const NxbTolLayout& tl = p.tl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Ctx c;
+    cta_prologue(c, p, tid, lane);
+    TpCtx tc;
+    tc.p = &p; tc.E = ml.E; tc.P = ml.P; tc.K = ml.K;
+    tc.cls.off = ml.off_cls; tc.qm.off = ml.off_qm; tc.slot.off = ml.off_slot;
+    tc.erec.off = ml.off_edgerec; tc.grec.off = ml.off_grec; tc.etab.off = ml.off_etab; tc.pcdf.off = ml.off_pcdf;
+    tc.s_off_on = c.s_off_on; tc.s_root_misc = c.s_root_misc; tc.s_root_on_cls = c.s_root_on_cls;
+    tc.k0 = c.k0; tc.k1 = c.k1;
+    TpGroup<WPU> g;
+    g.lane = lane; g.w = warp % WPU; g.li = g.w * 32 + lane;
+    const int grp = warp / WPU;
+    g.bar = 1 + grp;
+    constexpr int G = 32 * WPU;
+    TpUnit<MSG> u;
+    u.bind((unsigned)(p.smem_warp0 + grp * tl.bytes), tl);
+    TpTimer tm;
+    tm.perf = p.perf ? p.perf + 12 : nullptr; tm.on = (g.li == 0); tm.t_last = clock64();
+    const int N = ml.N, E = ml.E, K = ml.K;
+    const long long n_work = p.unit_list ? (long long)p.n_list : p.n_units;
+    while (true) {
+        long long widx = 0;
+        if (WPU == 1) {
+            if (lane == 0) widx = (long long)atomicAdd(p.work_counter, 1ull);
+            widx = __shfl_sync(FULL, widx, 0);
+        } else {
+            if (g.li == 0) *(long long*)&u.x[6] = (long long)atomicAdd(p.work_counter, 1ull);
+            g.sync();
+            widx = *(const long long*)&u.x[6];
+            g.sync();
+        }
+        if (widx >= n_work) break;
+        const long long unit = p.unit_list ? (long long)p.unit_list[widx] : widx;
+        unsigned char* const slab = p.state + unit * p.state_stride;
+        const NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;
+        if (!(hdr.phase == NXB_PHASE_BLINK && hdr.sweeps_done == p.begin_sweeps)) continue;
+        if ((int)hdr.n_pri > tl.capP || (int)hdr.n_blk > tl.capB) {
+            if (g.li == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)unit;
+            continue;
+        }
+        // ---- load (coalesced, streaming; only the live part of the slab is read) ----
+        u.nP = hdr.n_pri; u.nB = hdr.n_blk;
+        u.unit32 = (unsigned)(p.unit_offset + unit); u.sweep = hdr.sweeps_done;
+        const bool accum = hdr.sweeps_done >= p.accum_from;
+        const long long site = unit / p.chains;
+        const unsigned* const g_tt = p.tol_true_ok + site * N;
+        const unsigned* const g_tf = p.tol_false_ok + site * N;
+        {
+            const unsigned* g_tol = (const unsigned*)(slab + p.so_tol);
+            const unsigned* g_npri = (const unsigned*)(slab + p.so_pri);
+            for (int v = g.li; v < N; v += G) u.node_tol[v] = __ldcs(g_tol + v);
+            for (int v = g.li; v < (N + 3) / 4; v += G) sm_ptr<unsigned>(u.node_pri.off)[v] = __ldcs(g_npri + v);
+            const double* g_ptm = (const double*)(slab + p.so_ptm);
+            const unsigned* g_pcode = (const unsigned*)(slab + p.so_pcode);
+            for (int i = g.li; i < u.nP; i += G) { u.ptm[i] = __ldcs(g_ptm + i); u.pcode[i] = __ldcs(g_pcode + i); }
+            const double* g_btm = (const double*)(slab + p.so_btm);
+            const unsigned* g_bcode = (const unsigned*)(slab + p.so_bcode);
+            for (int i = g.li; i < u.nB; i += G) { u.btm[i] = __ldcs(g_btm + i); u.bcode[i] = __ldcs(g_bcode + i); }
+            for (int e = g.li; e < E; e += G) { u.f0[e] = 0u; u.f1[e] = 0u; u.hasev[e] = 0u; }
+            if (g.li == 0) { u.x[4] = 0; u.x[8] = (int)__ldg(g_tt); u.x[9] = (int)__ldg(g_tf); }
+        }
+        g.sync();
+        // per-edge record: data masks of the lower node, primary states at both ends, range of the
+        // edge's primary events (sorted by (edge, time): two lower bounds)
+        for (int e = g.li; e < E; e += G) {
+            int lo = 0, hi = u.nP;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)(u.pcode[m] & 0xffffu) < e) lo = m + 1; else hi = m; }
+            const int a = lo;
+            hi = u.nP;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)(u.pcode[m] & 0xffffu) <= e) lo = m + 1; else hi = m; }
+            const int va = tc.erec[e].va;
+            u.nrec[e] = make_uint4(__ldg(g_tt + e + 1), __ldg(g_tf + e + 1),
+                                   (unsigned)u.node_pri[e + 1] | ((unsigned)u.node_pri[va] << 8),
+                                   (unsigned)a | ((unsigned)lo << 16));
+        }
+        g.sync();
+        tm.tick(TPT_LOAD);
+        int n_new = 0, detail = 0;
+        const int rc = tolpar_update<MSG, WPU>(tc, u, g, accum, slab, &n_new, &detail, tm);
+        if (rc == TP_DEFER) {
+            if (g.li == 0) p.defer_list[atomicAdd(p.defer_count, 1)] = (int)unit;
+            g.sync();
+            continue;
+        }
+        if (rc == TP_ERROR) {
+            if (g.li == 0) {
+                const int code = detail < 0 ? NXB_ERR_STATE_CAP : ((detail & 2) ? NXB_ERR_SCRATCH_CAP : NXB_ERR_INFEASIBLE);
+                if (atomicCAS(p.status, 0, code) == 0) {
+                    p.status[1] = (int)unit; p.status[2] = detail < 0 ? -detail : -3; p.status[3] = (int)hdr.sweeps_done;
+                }
+            }
+            g.sync();
+            continue;
+        }
+        // ---- store: header, node states (the new blink list is already in the slab) ----
+        {
+            NxbUnitHeader h2 = hdr;
+            h2.phase = NXB_PHASE_PRIMARY; h2.sweeps_done = hdr.sweeps_done + 1; h2.n_blk = (uint16_t)n_new;
+            if (g.li == 0) *(NxbUnitHeader*)slab = h2;
+            unsigned* g_tol = (unsigned*)(slab + p.so_tol);
+            for (int v = g.li; v < N; v += G) __stcs(g_tol + v, u.newtol[v]);
+            if (accum && g.li == 0) {
+                const int on = __popc(u.newtol[0]);
+                atomicAdd(&c.s_root_misc[0], (unsigned long long)on);
+                atomicAdd(&c.s_root_misc[1], (unsigned long long)(K - on));
+                atomicAdd(&c.s_root_on_cls[c.cls[u.node_pri[0]]], (unsigned long long)on);
+                atomicAdd(&c.s_root_misc[2], 1ull);
+            }
+        }
+        g.sync();
+        tm.tick(TPT_STORE);
     }
     cta_epilogue(c, p, tid);
 }
@@ -689,6 +821,10 @@ struct Tier {
     NxbWarpLayout bwl;
     int blink_warps = 0, blink_units = 0, blink_warp0 = 0;
     size_t blink_smem = 0;
+    // event-parallel tolerance update (every steady-state tier): one unit per group of tp_wpu warps
+    NxbTolLayout tl;
+    int tp_units = 0, tp_wpu = 1, tp_warp0 = 0;
+    size_t tp_smem = 0;
 };
 
 struct nxb_handle {
@@ -708,6 +844,7 @@ struct nxb_handle {
     int profile = 0;
     int lockstep = 0;              // warps per lockstep group in tier 0 (0: independent warps)
     bool split = true;             // tier 0: primary and tolerance updates as alternating kernels
+    bool tolpar = true;            // tolerance update by tolpar_kernel (event-parallel); false: blink_kernel (lane per track)
     // shape of the model the handle was created for (nxb_update_model accepts only the same)
     std::vector<int> shape_parent, shape_qptr, shape_qcol, shape_cls;
     std::vector<char> shape_active;     // edge has rate > 0 and length > 0
@@ -854,6 +991,38 @@ static void build_blink_layout(const NxbModelLayout& ml, bool msg_f64, int capP,
     wl->bytes = align_up(o, 16);
 }
 
+// One unit of tolpar_kernel: the trajectory, the per-edge records, the event pool (time, key,
+// uniform / map bits, 2x2 matrix per live event; the matrix slots first hold the candidates) and
+// the node accumulators of the upward tree pass.
+static void build_tol_layout(const NxbModelLayout& ml, bool msg_f64, int capP, int capB, int capQ, int capL,
+                             NxbTolLayout* tl) {
+    const int N = ml.N, E = ml.E, K = ml.K;
+    memset(tl, 0, sizeof(*tl));
+    int o = 0;
+    auto take = [&](int bytes, int al) { o = align_up(o, al); int r = o; o += bytes; return r; };
+    tl->capP = capP; tl->capB = capB; tl->capQ = capQ; tl->capL = capL;
+    tl->off_q = take((msg_f64 ? 32 : 16) * std::max(capQ, capL), 16);
+    tl->off_nrec = take(16 * E, 16);
+    tl->off_acc = take((msg_f64 ? 32 : 16) * K * ml.nslots, 16);
+    tl->off_T = take(8 * capL, 8);
+    tl->off_ptm = take(8 * capP, 8);
+    tl->off_btm = take(8 * capB, 8);
+    tl->off_aux = take((msg_f64 ? 8 : 4) * capL, 8);
+    tl->off_key = take(4 * capL, 4);
+    tl->off_pcode = take(4 * capP, 4);
+    tl->off_bcode = take(4 * capB, 4);
+    tl->off_node_tol = take(4 * N, 4);
+    tl->off_newtol = take(4 * N, 4);
+    tl->off_toff = take(4 * (K + 2), 4);
+    tl->off_f0 = take(4 * E, 4);
+    tl->off_f1 = take(4 * E, 4);
+    tl->off_hasev = take(4 * E, 4);
+    tl->off_x = take(4 * 16, 8);
+    tl->off_node_pri = take(align_up(N, 4), 4);
+    tl->off_ins = take(2 * capB, 2);
+    tl->bytes = align_up(o, 16);
+}
+
 extern "C" int nxb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -884,7 +1053,9 @@ extern "C" void nxb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], 
 static int build_model_tables(nxb_handle* h, const nxb_model_desc* d, double sums[3]) {
     const int N = d->n_nodes, P = d->n_states, K = d->n_classes, nnz = d->nnz, E = N - 1;
     // ---- derived model quantities ----
-    NxbModelLayout& ml = h->ml;
+    // (built aside and committed only after every check has passed: a refused nxb_update_model
+    // leaves the handle as it was)
+    NxbModelLayout ml;
     memset(&ml, 0, sizeof(ml));
     ml.N = N; ml.E = E; ml.P = P; ml.K = K; ml.nnz = nnz; ml.diameter = d->diameter;
     ml.rate_on = d->rate_on; ml.rate_off = d->rate_off;
@@ -905,7 +1076,7 @@ static int build_model_tables(nxb_handle* h, const nxb_model_desc* d, double sum
     std::vector<unsigned char> blob;
     {
         std::string err;
-        if (nxb_build_tol_tables(d, ml, blob, err)) { set_err(nullptr, NXB_ERR_BAD_ARG, err); return NXB_ERR_BAD_ARG; }
+        if (nxb_build_tol_tables(d, ml, blob, err, h->d_blob ? h->ml.pcdf_cap : 0)) { set_err(nullptr, NXB_ERR_BAD_ARG, err); return NXB_ERR_BAD_ARG; }
     }
     auto put = [&](const void* src, int bytes, int al) {
         int o = align_up((int)blob.size(), al);
@@ -1015,6 +1186,11 @@ static int build_model_tables(nxb_handle* h, const nxb_model_desc* d, double sum
         ml.off_stats = ml.bytes;
         ml.stats_words = 2 * E + P + 4 + K;
     }
+    if (h->d_blob && (ml.bytes != h->ml.bytes || ml.blink_bytes != h->ml.blink_bytes)) {
+        set_err(nullptr, NXB_ERR_BAD_ARG, "model tables changed size");
+        return NXB_ERR_BAD_ARG;
+    }
+    h->ml = ml;
     if (!h->d_blob) CUDA_TRY_M(cudaMalloc(&h->d_blob, blob.size()));
     CUDA_TRY_M(cudaMemcpy(h->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     {
@@ -1024,9 +1200,9 @@ static int build_model_tables(nxb_handle* h, const nxb_model_desc* d, double sum
         CUDA_TRY_M(cudaMemcpyToSymbol(c_inv_n, inv_n, sizeof(inv_n)));
     }
     // ---- L2-resident table of uniformization rates, one entry per tolerance mask ----
-    ml.table_bits = 0;
+    h->ml.table_bits = 0;
     if (K <= 22) {
-        ml.table_bits = K;
+        h->ml.table_bits = K;
         const unsigned n_masks = 1u << K;
         int *dq_ptr, *dq_cls; double* dq_val;
         std::vector<int> qcls(nnz);
@@ -1092,6 +1268,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     // 0: automatic group size (group_warps_for / run_split); negative switches lockstep off
     h->lockstep = d->lockstep_warps == 0 ? -1 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);   // -1: automatic
     h->split = d->split_phases >= 0;
+    if (const char* ev = getenv("NXB_TOLPAR")) h->tolpar = atoi(ev) != 0;
+    if (E > 8191) return (delete h, set_err(nullptr, NXB_ERR_BAD_ARG, "more than 8191 edges"));
 #define CUDA_TRY_C(call)                                                                  \
     do {                                                                                  \
         cudaError_t e_ = (call);                                                          \
@@ -1147,8 +1325,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     CUDA_TRY_C(cudaMalloc(&h->d_work, 8));
     CUDA_TRY_C(cudaMalloc(&h->d_defer_count, 4));
     CUDA_TRY_C(cudaMalloc(&h->d_scratch, 64));
-    CUDA_TRY_C(cudaMalloc(&h->d_perf, 16 * 8));
-    CUDA_TRY_C(cudaMemset(h->d_perf, 0, 16 * 8));
+    CUDA_TRY_C(cudaMalloc(&h->d_perf, 32 * 8));
+    CUDA_TRY_C(cudaMemset(h->d_perf, 0, 32 * 8));
 
     // ---- capacity tiers ----
     {
@@ -1212,6 +1390,30 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
                         tier.blink_smem = (size_t)bfixed + (size_t)bu * tier.bwl.bytes;
                     }
                 }
+                if (pass == 0 && h->tolpar) {
+                    // candidates of one sweep (all tracks) and live events (accepted candidates + retained):
+                    // the acceptance probability is that of the stationary mix of ON and OFF
+                    const double Mx = std::max(on, off);
+                    const double acc_mean = (off / (on + off)) * (2.0 * Mx - on) / (2.0 * Mx)
+                                          + (on / (on + off)) * (2.0 * Mx - off) / (2.0 * Mx);
+                    const int capQ0 = cap(cand_blk, 3.5, 16.0);
+                    const int capL0 = cap(mean_blk + acc_mean * cand_blk, 3.5, 16.0);
+                    const int cQ = std::min(65528, capQ0 * f), cL = std::min(65528, capL0 * f);
+                    build_tol_layout(ml, h->msg_f64, tier.wl.capP, tier.wl.capB, cQ, cL, &tier.tl);
+                    const int bfixed = ml.blink_bytes + stats_bytes;
+                    tier.tp_warp0 = bfixed;
+                    const int fit = (h->max_smem - bfixed) / tier.tl.bytes;
+                    int wpu = (cand_blk + mean_blk >= 128.0) ? 2 : 1;
+                    if (const char* ev = getenv("NXB_TP_WPU")) wpu = atoi(ev) == 2 ? 2 : 1;
+                    int maxw = NXB_TP_THREADS / 32;
+                    if (d->max_warps > 0) maxw = std::max(wpu, std::min(maxw, d->max_warps));
+                    int nu = std::min(fit, maxw / wpu);
+                    if (wpu == 2) nu = std::min(nu, 15);          // one named barrier per unit group
+                    if (nu >= 1) {
+                        tier.tp_units = nu; tier.tp_wpu = wpu;
+                        tier.tp_smem = (size_t)bfixed + (size_t)nu * tier.tl.bytes;
+                    }
+                }
                 (pass == 0 ? h->tiers : h->init_tiers).push_back(tier);
             }
         }
@@ -1262,6 +1464,13 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             ? cudaFuncSetAttribute(blink_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
             : cudaFuncSetAttribute(blink_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
         if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }
+    }
+    if (h->msg_f64) {
+        cudaFuncSetAttribute(tolpar_kernel<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+        cudaFuncSetAttribute(tolpar_kernel<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+    } else {
+        cudaFuncSetAttribute(tolpar_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+        cudaFuncSetAttribute(tolpar_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
     }
     cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
     h->shape_parent.assign(d->parent, d->parent + N);
@@ -1364,9 +1573,11 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
     memset(&p, 0, sizeof(p));
     p.ml = h->ml; p.wl = (kind == KIND_BLINK) ? tier.bwl : tier.wl; p.sl = h->sl;
     p.smem_warp0 = tier.smem_warp0;
+    const bool tolpar = kind == KIND_BLINK && h->tolpar && tier.tp_units > 0;
     if (kind == KIND_BLINK) {       // only the tolerance tables of the model are staged
         p.ml.bytes = h->ml.blink_bytes; p.ml.off_stats = h->ml.blink_bytes;
-        p.smem_warp0 = tier.blink_warp0;
+        p.smem_warp0 = tolpar ? tier.tp_warp0 : tier.blink_warp0;
+        p.tl = tier.tl;
     }
     p.blob = h->d_blob; p.rmax_tab = h->d_rmax;
     p.pri_ok = h->d_pri_ok; p.tol_true_ok = h->d_tt; p.tol_false_ok = h->d_tf;
@@ -1390,11 +1601,23 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
     p.perf = h->profile ? h->d_perf : nullptr;
     p.gscratch = h->d_gscratch; p.gscratch_stride = h->gscratch_stride;
     p.g_off_msg = h->g_off_msg; p.g_off_ctm = h->g_off_ctm; p.gcapF = h->gcapF; p.gcapC = h->gcapC;
+    p.dbg_unit = -1; p.dbg_sweep = 0;
+    if (const char* ev = getenv("NXB_DBG_UNIT")) { p.dbg_unit = atoll(ev); p.dbg_sweep = getenv("NXB_DBG_SWEEP") ? atoi(getenv("NXB_DBG_SWEEP")) : 0; }
     CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
     if (!append) CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
     const long long n_work = list ? n_list : h->n_units;
     CUDA_TRY(h, cudaEventRecord(no_wait ? h->ev2 : h->ev0, h->stream));
-    if (kind == KIND_BLINK) {
+    if (tolpar) {
+        const int grid = (int)std::max<long long>(1, std::min<long long>(h->num_sms, (n_work + tier.tp_units - 1) / tier.tp_units));
+        const int threads = tier.tp_units * tier.tp_wpu * 32;
+        if (h->msg_f64) {
+            if (tier.tp_wpu == 2) tolpar_kernel<double, 2><<<grid, threads, tier.tp_smem, h->stream>>>(p);
+            else tolpar_kernel<double, 1><<<grid, threads, tier.tp_smem, h->stream>>>(p);
+        } else {
+            if (tier.tp_wpu == 2) tolpar_kernel<float, 2><<<grid, threads, tier.tp_smem, h->stream>>>(p);
+            else tolpar_kernel<float, 1><<<grid, threads, tier.tp_smem, h->stream>>>(p);
+        }
+    } else if (kind == KIND_BLINK) {
         int grid = (int)std::min<long long>(h->num_sms, (n_work + tier.blink_units - 1) / tier.blink_units);
         if (h->msg_f64) blink_kernel<double><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
         else blink_kernel<float><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
@@ -1478,7 +1701,30 @@ static int run_split(nxb_handle* h, unsigned target, unsigned accum_from) {
         rc = launch_one(h, KIND_BLINK, t0, 1, nullptr, 0, h->d_defer[0], true, h->sweeps, h->sweeps + 1,
                         accum_from, 0, &nd);
         if (rc) return rc;
-        if (nd > 0) {
+        if (nd > 0 && h->tolpar) {
+            // Units that did not fit tier 0 of either kernel: the same two kernels with the
+            // capacities of the next tiers (fewer units per CTA).  A unit deferred by the primary
+            // kernel is still in phase PRIMARY and is skipped by the tolerance kernel of the tier,
+            // and the other way round, so each tier takes every unit as far as its capacities allow.
+            h->deferred_total += nd;
+            const int* list = h->d_defer[0];
+            int n_list = nd;
+            size_t t = 1;
+            for (; t < h->tiers.size() && n_list > 0; ++t) {
+                const Tier& tt = h->tiers[t];
+                if (tt.tp_units <= 0) break;
+                int* out = h->d_defer[t & 1];
+                int nd2 = 0;
+                rc = launch_one(h, KIND_PRIMARY, tt, 1, list, n_list, out, false, h->sweeps, h->sweeps + 1,
+                                accum_from, 0, &nd2, true);
+                if (rc) return rc;
+                rc = launch_one(h, KIND_BLINK, tt, 1, list, n_list, out, true, h->sweeps, h->sweeps + 1,
+                                accum_from, 0, &nd2);
+                if (rc) return rc;
+                list = out; n_list = nd2;
+            }
+            if (n_list > 0) return set_err(h, NXB_ERR_SCRATCH_CAP, status_text(NXB_ERR_SCRATCH_CAP));
+        } else if (nd > 0) {
             h->deferred_total += nd;
             rc = run_tiers(h, h->sweeps + 1, accum_from, 0, 1, h->d_defer[0], nd);
             if (rc) return rc;
@@ -1522,7 +1768,7 @@ extern "C" int nxb_sweep(nxb_handle* h, int32_t n_sweeps, int32_t accumulate) {
     const unsigned accum_from = accumulate ? h->sweeps : 0xffffffffu;
     h->last_ms = 0.f; h->last_launches = 0;
     for (int i = 0; i < 4; ++i) { h->kind_ms[i] = 0.f; h->kind_launches[i] = 0; }
-    if (h->split && h->tiers[0].blink_units > 0) return run_split(h, target, accum_from);
+    if (h->split && (h->tiers[0].blink_units > 0 || (h->tolpar && h->tiers[0].tp_units > 0))) return run_split(h, target, accum_from);
     int rc = run_tiers(h, target, accum_from, 0);
     if (rc == NXB_OK) h->sweeps = target;
     return rc;
@@ -1745,8 +1991,8 @@ extern "C" int nxb_profile(nxb_handle* h, int32_t enable, uint64_t* cycles12) {
     if (!h) return NXB_ERR_BAD_ARG;
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (cycles12) {
-        CUDA_TRY(h, cudaMemcpy(cycles12, h->d_perf, 12 * 8, cudaMemcpyDeviceToHost));
-        CUDA_TRY(h, cudaMemset(h->d_perf, 0, 16 * 8));
+        CUDA_TRY(h, cudaMemcpy(cycles12, h->d_perf, 24 * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(h, cudaMemset(h->d_perf, 0, 32 * 8));
     }
     h->profile = enable;
     return NXB_OK;

@@ -75,6 +75,42 @@ struct NxbModelLayout {
     double acc_blk[4];      // thinning acceptance [own][fg state]
     double a_on, a_off;     // off-diagonal entries of the uniformized 2x2 blink matrix
     double p_on, p_off;     // blink prior at the root
+    // event-parallel tolerance update (tol_par.cuh): the dominating Poisson process of all K
+    // tracks laid out on one axis (track-major, edges in index order, rate-length units)
+    int off_grec;           // NxbGenRec [E]   per-edge constants of the candidate generator
+    int off_pcdf;           // u32 [pcdf_cap]  Poisson(tp_W) CDF thresholds (count = first j with word < pcdf[j]); n_pcdf used
+    int n_pcdf, pcdf_cap;
+    int off_etab;           // u16 [NXB_TP_NBIN]  first guess of the edge from the position on the track's axis
+    double tp_inv_lam, tp_inv_bin;
+    double tp_lam;          // length of one track on the axis: sum_e 2 max(on,off) rate_e len_e
+    double tp_W;            // slice width = K * tp_lam / NXB_TP_NSLICE
+    unsigned tp_thr[4];     // thinning thresholds [own][fg state] as u32 (accept iff word < thr)
+};
+
+#define NXB_TP_NSLICE 64
+#define NXB_TP_NBIN 256
+// Per-edge constants of the candidate generator of tol_par.cuh.
+struct __align__(16) NxbGenRec {
+    double cum;             // start of the edge on the track's axis (rate-length units)
+    double inv_om;          // time per rate-length unit on this edge (0: inactive edge)
+    double tma, tmb;
+};
+
+// Shared-memory layout of one unit in tolpar_kernel (bytes from the unit's base).
+struct NxbTolLayout {
+    int capP, capB;         // retained primary / blink events
+    int capQ;               // candidates of one sweep (staging) = matrix slots
+    int capL;               // live events (accepted candidates + retained)
+    int off_ptm, off_pcode, off_btm, off_bcode;
+    int off_node_tol, off_newtol, off_node_pri;
+    int off_nrec;           // uint4[E]
+    int off_ins;            // u16[capB]
+    int off_toff;           // int[K + 2]
+    int off_f0, off_f1, off_hasev;   // u32[E]
+    int off_acc;            // AccRec<MSG>[nslots * K]
+    int off_T, off_key, off_aux, off_q;
+    int off_x;              // int[16] exchange slots / unit header
+    int bytes;
 };
 
 // Per-edge constants read at every edge boundary of the tolerance walks.
@@ -128,6 +164,7 @@ struct NxbSummaryLayout {
 struct NxbSweepParams {
     NxbModelLayout ml;
     NxbWarpLayout wl;
+    NxbTolLayout tl;
     NxbSummaryLayout sl;
     int smem_warp0;                     // byte offset of warp 0's region in shared memory
     const unsigned char* blob;          // model blob (global)
@@ -169,4 +206,6 @@ struct NxbSweepParams {
     long long gscratch_stride;
     int g_off_msg, g_off_ctm;          // global scratch: chunk messages, event pool
     int gcapF, gcapC;
+    long long dbg_unit;                 // development: dump the event list of this unit (tolpar_kernel), -1: none
+    int dbg_sweep;
 };

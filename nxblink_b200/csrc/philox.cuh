@@ -72,4 +72,7 @@ NXB_HD uint32_t nxb_xo_next(NxbXo& g) {
 #define NXB_STREAM_BLK_COUNT  0x06000000u   // | pair group  : 4 candidate counts per block
 #define NXB_STREAM_BLK_FFBS   0x04000000u   // | k<<16       : block 0 seeds the track's xoshiro stream
 #define NXB_STREAM_INIT_BLK   0x05000000u   // | k<<16 | edge
+#define NXB_STREAM_TOL_SLICE  0x07000000u   // | slice       : block 0 seeds the xoshiro stream of one slice of the candidate axis
+#define NXB_STREAM_TOL_RET    0x08000000u   //               : backward-sampling words of the retained events (block = index / 4)
+#define NXB_STREAM_TOL_ROOT   0x09000000u   //               : root draws of the tracks (block = track / 4)
 #define NXB_SWEEP_INIT        0xFFFFFFFFu   // counter word c1 used by the initialisation pass

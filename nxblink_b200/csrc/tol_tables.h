@@ -16,7 +16,7 @@
 //   NxbEdgeRec[E], slot int[N], cls u8[P], qm f64[P*K]
 // ml.N/E/P/K must be set.  Returns 0, or 1 with a message.
 static inline int nxb_build_tol_tables(const nxb_model_desc* d, NxbModelLayout& ml,
-                                       std::vector<unsigned char>& blob, std::string& err) {
+                                       std::vector<unsigned char>& blob, std::string& err, int pcdf_cap = 0) {
     const int N = d->n_nodes, P = d->n_states, K = d->n_classes, E = N - 1;
     auto align_up = [](int x, int a) { return (x + a - 1) / a * a; };
     auto put = [&](const void* src, int bytes, int al) {
@@ -81,6 +81,62 @@ static inline int nxb_build_tol_tables(const nxb_model_desc* d, NxbModelLayout& 
         for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i)
             qm[(size_t)s * K + d->state_class[d->q_col[i]]] += d->q_val[i];
     ml.off_qm = put(qm.data(), 8 * P * K, 8);
+    // ---- candidate generator of the event-parallel update (tol_par.cuh) ----
+    {
+        std::vector<NxbGenRec> g(E);
+        double cum = 0.0;
+        for (int e = 0; e < E; ++e) {
+            const double len = d->blen[e + 1], rate = d->rate[e + 1];
+            const bool active = rate > 0.0 && len > 0.0;
+            const double om = 2.0 * M * rate;            // dominating rate per unit time
+            g[e].cum = cum;
+            g[e].inv_om = active ? 1.0 / om : 0.0;
+            g[e].tma = recs[e].tma; g[e].tmb = recs[e].tmb;
+            if (active) cum += om * len;
+        }
+        ml.tp_lam = cum;
+        ml.tp_W = (double)K * cum / (double)NXB_TP_NSLICE;
+        ml.off_grec = put(g.data(), (int)(sizeof(NxbGenRec) * E), 16);
+        // Poisson(W) thresholds: count = first j with word < pcdf[j]; the last entry catches everything
+        std::vector<unsigned> pcdf;
+        {
+            const double W = ml.tp_W;
+            if (W > 2000.0) { err = "tolerance update: more than 2000 expected candidates per slice of the event axis"; return 1; }
+            long double pr = expl(-(long double)W), cdf = pr;
+            int j = 0;
+            while (true) {
+                const long double x = cdf * 4294967296.0L;
+                if (x >= 4294967295.0L || j > 8000) { pcdf.push_back(0xffffffffu); break; }
+                pcdf.push_back((unsigned)x);
+                ++j;
+                pr *= (long double)W / (long double)j;
+                cdf += pr;
+            }
+        }
+        ml.n_pcdf = (int)pcdf.size();
+        // The table has a fixed capacity so that the blob keeps its size when nxb_update_model
+        // changes the rates: room for about twice the rates the handle was created with.
+        if (pcdf_cap <= 0) pcdf_cap = ((int)(2.0 * ml.tp_W + 12.0 * sqrt(2.0 * ml.tp_W + 1.0)) + 64 + 7) / 8 * 8;
+        if (ml.n_pcdf > pcdf_cap) { err = "the blink rates grew beyond what the handle was created for; create a new handle"; return 1; }
+        pcdf.resize(pcdf_cap, 0xffffffffu);
+        ml.pcdf_cap = pcdf_cap;
+        ml.off_pcdf = put(pcdf.data(), 4 * pcdf_cap, 4);
+        // first guess of the edge: the last edge that starts before the upper end of the bin
+        {
+            std::vector<unsigned short> etab(NXB_TP_NBIN, 0);
+            const double bw = cum / (double)NXB_TP_NBIN;
+            for (int b = 0; b < NXB_TP_NBIN; ++b) {
+                int e = E - 1;
+                while (e > 0 && g[e].cum > (double)(b + 1) * bw) --e;
+                etab[b] = (unsigned short)e;
+            }
+            ml.off_etab = put(etab.data(), 2 * NXB_TP_NBIN, 2);
+            ml.tp_inv_lam = cum > 0.0 ? 1.0 / cum : 0.0;
+            ml.tp_inv_bin = cum > 0.0 ? (double)NXB_TP_NBIN / cum : 0.0;
+        }
+        for (int i = 0; i < 4; ++i)
+            ml.tp_thr[i] = (unsigned)fmin(ml.acc_blk[i] * 4294967296.0, 4294967295.0);
+    }
     blob.resize(align_up((int)blob.size(), 16));
     ml.blink_bytes = (int)blob.size();
     return 0;

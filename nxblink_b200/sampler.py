@@ -169,11 +169,15 @@ class BlinkSampler(object):
             'P4 downward', 'P5 writeback+stats', 'B0 pool', 'B1 upward', 'B2 downward+stats',
             'BW writeback', 'store')
 
+    # tolpar_kernel books its phases into slots 12..23
+    TP_PHASES = ('T load', 'T candidates', 'T merge', 'T thinning', 'T matrices', 'T suffix scan',
+            'T tree up', 'T maps', 'T tree down', 'T survivors', 'T event-free', 'T store')
+
     def profile(self, enable=True):
         """Switch the per-phase cycle counters on/off; returns the counters so far."""
-        out = np.zeros(12, dtype=np.uint64)
+        out = np.zeros(24, dtype=np.uint64)
         self._check(self.lib.nxb_profile(self._h, 1 if enable else 0, out.ctypes.data))
-        return dict(zip(self.PHASES, out.tolist()))
+        return dict(zip(self.PHASES + self.TP_PHASES, out.tolist()))
 
     # ------------------------------------------------------------------
     def export_unit(self, unit, cap=4096):
