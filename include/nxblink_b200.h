@@ -142,6 +142,14 @@ int nxb_forward_sample_rooted(nxb_handle* h, int64_t n_units, uint64_t seed, int
 /* Node states of every unit: node_pri[n_units*N], node_tol[n_units*N] (bit k: class k on). */
 int nxb_read_node_states(nxb_handle* h, int32_t* node_pri, uint32_t* node_tol);
 
+/* Run every later launch and copy of this handle on the caller's CUDA stream (a cudaStream_t
+ * passed as an integer, e.g. torch.cuda.current_stream().cuda_stream) instead of the handle's
+ * own stream, so that the caller's events and collectives order with the sweeps without extra
+ * synchronisation.  0 restores the handle's own stream.  The handle never destroys a caller's
+ * stream.  (The reference has no streams; this is what a torch-side caller of the E-step needs,
+ * examples/p53/run-stochastic.py:172-195.) */
+int nxb_set_stream(nxb_handle* h, uint64_t cuda_stream);
+
 int nxb_get_stats(nxb_handle* h, nxb_stats* out);
 /* Last sweep-kernel launch times (ms, CUDA events on the launching stream). */
 int nxb_last_kernel_ms(nxb_handle* h, float* total_ms, int32_t* n_launches);
@@ -176,6 +184,42 @@ int nxb_pruning_loglik(int device, int32_t n, int32_t n_nodes, const int32_t* pa
                        const double* P, const double* prior, int64_t n_sites,
                        const uint64_t* masks, double* loglik);
 const char* nxb_dense_last_error(void);
+/* Duration (ms, CUDA events around the launch) of the kernel of the last dense call above. */
+float nxb_dense_last_kernel_ms(void);
+
+/* ---- M-step on the device ----------------------------------------------------
+ * Structure of the MG94 codon parametrisation of examples/p53/p53em.py:188-229 (get_pre_Q): for
+ * entry i of the CSR pattern (q_ptr, q_col) of the primary rate matrix,
+ *   q_i = nt[nt_to[i]] * (is_ts[i] ? kappa : 1) * (is_non[i] ? omega : 1),
+ * and the codon distribution is prod_j nt_j^nt_counts[s][j], normalised (p53em.py:232-257).
+ * xon_weight[k] is 1 if an ON track of class k at the root counts towards `root_xon_count`
+ * (summary.py:221), else 0. */
+typedef struct {
+    int32_t n_edges, n_states, n_classes, nnz;
+    const int32_t* q_ptr;        /* [n_states + 1] */
+    const int32_t* q_col;        /* [nnz] */
+    const int32_t* state_class;  /* [n_states] */
+    const int32_t* nt_to;        /* [nnz] target nucleotide 0..3 */
+    const uint8_t* is_ts;        /* [nnz] transition? */
+    const uint8_t* is_non;       /* [nnz] nonsynonymous? */
+    const double* nt_counts;     /* [n_states * 4] */
+    const double* xon_weight;    /* [n_classes] */
+} nxb_mstep_desc;
+/* Objective f(x) = -(em.get_ll_root + em.get_ll_dwell + em.get_ll_trans) / nsamples
+ * (nxblink/em.py:19-198 as assembled by examples/p53/p53em.py:58-91) and its gradient in the
+ * log-parameters x = log(kappa, omega, A, C, G, T, blink on, blink off, edge rates[n_edges])
+ * (p53em.py:143-185), evaluated on the DEVICE-resident statistics (counts_dev / dwell_dev: the
+ * buffers of nxb_summary_device_ptrs or all-reduced copies of them, laid out as `layout`).
+ * eval_only != 0: evaluate at x (f_out, grad_out[8 + n_edges]).  Otherwise minimise from x by
+ * L-BFGS inside one kernel launch (replaces scipy.optimize.minimize(..., 'L-BFGS-B') with algopy
+ * gradients, p53em.py:94-140) and return the optimum in x, f_out, grad_out (may be NULL);
+ * info[0] iterations, info[1] evaluations, info[2] 1: gradient below 1e-5, 2: relative decrease
+ * below 2.2e-9 (scipy's defaults), 3: line search failed, 4: iteration limit.  Host x / outputs. */
+int nxb_mstep(int device, const nxb_mstep_desc* d, const nxb_summary_layout* layout,
+              const void* counts_dev, const void* dwell_dev, double* x, int32_t maxiter,
+              int32_t eval_only, double* f_out, double* grad_out, int32_t* info);
+const char* nxb_mstep_last_error(void);
+float nxb_mstep_last_kernel_ms(void);
 
 /* Known-answer hook for the counter-based generator (host code path). */
 void nxb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -57,6 +57,15 @@ class Stats(C.Structure):
     ]
 
 
+class MStepDesc(C.Structure):
+    _fields_ = [
+        ('n_edges', C.c_int32), ('n_states', C.c_int32), ('n_classes', C.c_int32), ('nnz', C.c_int32),
+        ('q_ptr', C.c_void_p), ('q_col', C.c_void_p), ('state_class', C.c_void_p),
+        ('nt_to', C.c_void_p), ('is_ts', C.c_void_p), ('is_non', C.c_void_p),
+        ('nt_counts', C.c_void_p), ('xon_weight', C.c_void_p),
+    ]
+
+
 # every symbol include/nxblink_b200.h declares
 EXPORTS = (
     'nxb_device_count', 'nxb_create', 'nxb_destroy', 'nxb_update_model', 'nxb_last_error',
@@ -66,6 +75,8 @@ EXPORTS = (
     'nxb_last_kernel_ms', 'nxb_last_kernel_ms_by_kind', 'nxb_profile', 'nxb_philox4x32_10',
     'nxb_expm_batched', 'nxb_expm_frechet_batched', 'nxb_pruning_loglik', 'nxb_dense_last_error',
     'nxb_forward_sample', 'nxb_forward_sample_rooted', 'nxb_read_node_states',
+    'nxb_dense_last_kernel_ms', 'nxb_set_stream',
+    'nxb_mstep', 'nxb_mstep_last_error', 'nxb_mstep_last_kernel_ms',
 )
 
 _lib = None
@@ -108,6 +119,12 @@ def load():
     lib.nxb_pruning_loglik.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.nxb_dense_last_error.restype = C.c_char_p
+    lib.nxb_dense_last_kernel_ms.restype = C.c_float
+    lib.nxb_set_stream.argtypes = [H, C.c_uint64]
+    lib.nxb_mstep.argtypes = [C.c_int, C.POINTER(MStepDesc), C.POINTER(SummaryLayout), C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+    lib.nxb_mstep_last_error.restype = C.c_char_p
+    lib.nxb_mstep_last_kernel_ms.restype = C.c_float
     lib.nxb_forward_sample.argtypes = [H, C.c_int64, C.c_uint64, C.c_int64]
     lib.nxb_forward_sample_rooted.argtypes = [H, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.nxb_read_node_states.argtypes = [H, C.c_void_p, C.c_void_p]

@@ -300,6 +300,18 @@ static std::string g_dense_err;
 
 extern "C" const char* nxb_dense_last_error(void) { return g_dense_err.c_str(); }
 
+// duration of the kernel of the last dense call (CUDA events around the launch, default stream)
+static float g_dense_ms = 0.f;
+extern "C" float nxb_dense_last_kernel_ms(void) { return g_dense_ms; }
+namespace {
+struct KernelTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    KernelTimer() { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, 0); }
+    void stop() { cudaEventRecord(b, 0); cudaEventSynchronize(b); cudaEventElapsedTime(&g_dense_ms, a, b); }
+    ~KernelTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+}  // namespace
+
 #define DTRY(call)                                                                   \
     do {                                                                             \
         cudaError_t e_ = (call);                                                     \
@@ -323,7 +335,11 @@ extern "C" int nxb_expm_batched(int device, int32_t n, int32_t batch, const doub
     DTRY(cudaMemcpy(dt, t, sizeof(double) * batch, cudaMemcpyHostToDevice));
     const size_t smem = sizeof(double) * 3 * ND * ND;
     DTRY(cudaFuncSetAttribute(nxbd::expm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nxbd::expm_kernel<<<batch, 256, smem>>>(n, dQ, dt, dout);
+    {
+        KernelTimer kt;
+        nxbd::expm_kernel<<<batch, 256, smem>>>(n, dQ, dt, dout);
+        kt.stop();
+    }
     DTRY(cudaGetLastError());
     DTRY(cudaMemcpy(out, dout, sizeof(double) * (size_t)batch * n * n, cudaMemcpyDeviceToHost));
     cudaFree(dQ); cudaFree(dt); cudaFree(dout);
@@ -348,7 +364,11 @@ extern "C" int nxb_expm_frechet_batched(int device, int32_t n, int32_t batch, co
     DTRY(cudaMemcpy(dE, E, mat, cudaMemcpyHostToDevice));
     const size_t smem = sizeof(double) * 6 * ND * ND;
     DTRY(cudaFuncSetAttribute(nxbd::frechet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nxbd::frechet_kernel<<<batch, 256, smem>>>(n, dQ, dt, dE, dP, dL);
+    {
+        KernelTimer kt;
+        nxbd::frechet_kernel<<<batch, 256, smem>>>(n, dQ, dt, dE, dP, dL);
+        kt.stop();
+    }
     DTRY(cudaGetLastError());
     DTRY(cudaMemcpy(outL, dL, mat, cudaMemcpyDeviceToHost));
     if (outP) DTRY(cudaMemcpy(outP, dP, mat, cudaMemcpyDeviceToHost));
@@ -409,8 +429,12 @@ extern "C" int nxb_pruning_loglik(int device, int32_t n, int32_t n_nodes, const 
     DTRY(cudaMemcpy(dmask, masks, 8 * (size_t)n_sites * n_nodes, cudaMemcpyHostToDevice));
     DTRY(cudaFuncSetAttribute(nxbd::pruning_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((n_sites + ST - 1) / ST);
-    nxbd::pruning_kernel<<<grid, 256, smem>>>(n, n_nodes, nslots, dparent, dslot, dlast, dP, dprior,
-                                              n_sites, dmask, dll);
+    {
+        KernelTimer kt;
+        nxbd::pruning_kernel<<<grid, 256, smem>>>(n, n_nodes, nslots, dparent, dslot, dlast, dP, dprior,
+                                                  n_sites, dmask, dll);
+        kt.stop();
+    }
     DTRY(cudaGetLastError());
     DTRY(cudaMemcpy(loglik, dll, sizeof(double) * n_sites, cudaMemcpyDeviceToHost));
     cudaFree(dparent); cudaFree(dslot); cudaFree(dlast); cudaFree(dP); cudaFree(dprior); cudaFree(dll); cudaFree(dmask);

@@ -97,6 +97,13 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     const NxbWarpLayout& wl = p.wl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // list length from the device (launch enqueued before the list was written): nothing to do?
+    int n_list = p.n_list;
+    if (p.n_list_dev) {
+        n_list = *(volatile const int*)p.n_list_dev;
+        if (n_list <= 0) return;
+        if (p.defer_total && blockIdx.x == 0 && tid == 0) atomicAdd(p.defer_total, (unsigned long long)n_list);
+    }
     Ctx c;
     cta_prologue(c, p, tid, lane);
     c.wbase = (unsigned)(p.smem_warp0 + warp * wl.bytes);
@@ -117,7 +124,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     unsigned* d_tf = sm_ptr<unsigned>(c.wbase + wl.off_dtf);
     c.pri_ok.off = c.wbase + wl.off_dpri; c.tt_ok.off = c.wbase + wl.off_dtt; c.tf_ok.off = c.wbase + wl.off_dtf;
     const int N = ml.N;
-    const long long n_work = p.unit_list ? (long long)p.n_list : p.n_units;
+    const long long n_work = p.unit_list ? (long long)n_list : p.n_units;
     // Lockstep groups: GW consecutive warps take a batch of GW units and run every sub-phase
     // together (named barrier per group).  GW == 1: independent warps (deferral tiers).
     const int GW = p.group_warps > 1 ? p.group_warps : 1;
@@ -844,7 +851,7 @@ struct nxb_handle {
     int profile = 0;
     int lockstep = 0;              // warps per lockstep group in tier 0 (0: independent warps)
     bool split = true;             // tier 0: primary and tolerance updates as alternating kernels
-    bool tolpar = true;            // tolerance update by tolpar_kernel (event-parallel); false: blink_kernel (lane per track)
+    bool tolpar = false;           // true (NXB_TOLPAR=1): tolerance update by tolpar_kernel (event-parallel, experimental: exact but slower); false: blink_kernel (lane per track)
     // shape of the model the handle was created for (nxb_update_model accepts only the same)
     std::vector<int> shape_parent, shape_qptr, shape_qcol, shape_cls;
     std::vector<char> shape_active;     // edge has rate > 0 and length > 0
@@ -870,8 +877,13 @@ struct nxb_handle {
     unsigned long long* d_work = nullptr;
     int* d_defer[2] = {nullptr, nullptr};
     int* d_defer_count = nullptr;
+    unsigned long long* d_ctl = nullptr;           // run_split_async: work counters u64[4] | list lengths int[4]
+    unsigned long long* d_defer_total = nullptr;   // units listed for a higher tier during the current chunk
+    bool sync_sweeps = false;                      // NXB_SYNC_SWEEPS=1: the host-synchronised split path (one wait per sweep)
+    std::vector<cudaEvent_t> evpool;
     unsigned long long* d_scratch = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;         // the stream every launch and copy goes to
+    cudaStream_t own_stream = nullptr;     // created by nxb_create; `stream` may be a caller's (nxb_set_stream)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;     // a launch whose result is collected by the next one
     int pending_kind = -1;
@@ -900,6 +912,12 @@ static int set_err(nxb_handle* h, int code, const std::string& msg) {
     } while (0)
 
 static int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// device temporaries of one call, released on every exit path
+struct DevFree {
+    std::vector<void*> ptrs;
+    ~DevFree() { for (void* q : ptrs) cudaFree(q); }
+};
 
 static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, int capB,
                               int capR, int capF, int capC, NxbWarpLayout* wl) {
@@ -1269,13 +1287,14 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     h->lockstep = d->lockstep_warps == 0 ? -1 : (d->lockstep_warps < 0 ? 0 : d->lockstep_warps);   // -1: automatic
     h->split = d->split_phases >= 0;
     if (const char* ev = getenv("NXB_TOLPAR")) h->tolpar = atoi(ev) != 0;
+    if (const char* ev = getenv("NXB_SYNC_SWEEPS")) h->sync_sweeps = atoi(ev) != 0;
     if (E > 8191) return (delete h, set_err(nullptr, NXB_ERR_BAD_ARG, "more than 8191 edges"));
 #define CUDA_TRY_C(call)                                                                  \
     do {                                                                                  \
         cudaError_t e_ = (call);                                                          \
         if (e_ != cudaSuccess) {                                                          \
             set_err(nullptr, NXB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
-            delete h;                                                                     \
+            nxb_destroy(h);                                                               \
             return NXB_ERR_CUDA;                                                          \
         }                                                                                 \
     } while (0)
@@ -1284,7 +1303,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     CUDA_TRY_C(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
-    CUDA_TRY_C(cudaStreamCreate(&h->stream));
+    CUDA_TRY_C(cudaStreamCreate(&h->own_stream));
+    h->stream = h->own_stream;
     CUDA_TRY_C(cudaEventCreate(&h->ev0));
     CUDA_TRY_C(cudaEventCreate(&h->ev1));
     CUDA_TRY_C(cudaEventCreate(&h->ev2));
@@ -1324,6 +1344,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     CUDA_TRY_C(cudaMemset(h->d_status, 0, 4 * sizeof(int)));
     CUDA_TRY_C(cudaMalloc(&h->d_work, 8));
     CUDA_TRY_C(cudaMalloc(&h->d_defer_count, 4));
+    CUDA_TRY_C(cudaMalloc(&h->d_ctl, 48));
+    CUDA_TRY_C(cudaMalloc(&h->d_defer_total, 8));
     CUDA_TRY_C(cudaMalloc(&h->d_scratch, 64));
     CUDA_TRY_C(cudaMalloc(&h->d_perf, 32 * 8));
     CUDA_TRY_C(cudaMemset(h->d_perf, 0, 32 * 8));
@@ -1520,12 +1542,22 @@ extern "C" int nxb_destroy(nxb_handle* h) {
     cudaFree(h->d_state); cudaFree(h->d_counts); cudaFree(h->d_dwell); cudaFree(h->d_status);
     cudaFree(h->d_work); cudaFree(h->d_defer[0]); cudaFree(h->d_defer[1]); cudaFree(h->d_defer_count);
     cudaFree(h->d_scratch); cudaFree(h->d_perf); cudaFree(h->d_gscratch);
+    cudaFree(h->d_ctl); cudaFree(h->d_defer_total);
+    for (auto& e : h->evpool) if (e) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->ev3) cudaEventDestroy(h->ev3);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
+    return NXB_OK;
+}
+
+extern "C" int nxb_set_stream(nxb_handle* h, uint64_t cuda_stream) {
+    if (!h) return NXB_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));      // nothing of ours is left in flight on the old stream
+    h->stream = cuda_stream ? (cudaStream_t)(uintptr_t)cuda_stream : h->own_stream;
     return NXB_OK;
 }
 
@@ -1535,8 +1567,15 @@ extern "C" int nxb_set_data(nxb_handle* h, int64_t n_sites, const uint64_t* pri_
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t n = (size_t)n_sites * h->ml.N;
     if (n_sites != h->n_sites) {
+        // the unit states belong to the old sites (unit u is chain u % chains of site u / chains):
+        // drop them, so that a sweep without a new nxb_init_chains fails instead of reading the
+        // data of other sites or past the end of the new buffers
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (h->d_state) { cudaFree(h->d_state); h->d_state = nullptr; }
+        h->n_units = 0;
         cudaFree(h->d_pri_ok); cudaFree(h->d_tt); cudaFree(h->d_tf);
         h->d_pri_ok = nullptr; h->d_tt = nullptr; h->d_tf = nullptr;
+        h->n_sites = 0;
         CUDA_TRY(h, cudaMalloc(&h->d_pri_ok, 8 * n));
         CUDA_TRY(h, cudaMalloc(&h->d_tt, 4 * n));
         CUDA_TRY(h, cudaMalloc(&h->d_tf, 4 * n));
@@ -1562,14 +1601,10 @@ static const char* status_text(int code) {
 
 enum { KIND_FUSED = 0, KIND_PRIMARY = 1, KIND_BLINK = 2, KIND_CHECK = 3 };
 
-// One kernel launch over `list` (or every unit): fills the defer list `out` (appending when
-// `append`), adds the kernel time, returns the number of listed units through *n_deferred.
-// `no_wait`: do not wait for the kernel; its time, status and listed units are collected by the
-// next (waiting) launch on the same stream.
-static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps, const int* list, int n_list,
-                      int* out, bool append, unsigned begin, unsigned target, unsigned accum_from, int init,
-                      int* n_deferred, bool no_wait = false) {
-    NxbSweepParams p;
+// Kernel parameters of one launch over `list` (or every unit).
+static void fill_params(nxb_handle* h, NxbSweepParams& p, int kind, const Tier& tier, int group_warps,
+                        const int* list, int n_list, int* out, unsigned begin, unsigned target,
+                        unsigned accum_from, int init) {
     memset(&p, 0, sizeof(p));
     p.ml = h->ml; p.wl = (kind == KIND_BLINK) ? tier.bwl : tier.wl; p.sl = h->sl;
     p.smem_warp0 = tier.smem_warp0;
@@ -1603,10 +1638,11 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
     p.g_off_msg = h->g_off_msg; p.g_off_ctm = h->g_off_ctm; p.gcapF = h->gcapF; p.gcapC = h->gcapC;
     p.dbg_unit = -1; p.dbg_sweep = 0;
     if (const char* ev = getenv("NXB_DBG_UNIT")) { p.dbg_unit = atoll(ev); p.dbg_sweep = getenv("NXB_DBG_SWEEP") ? atoi(getenv("NXB_DBG_SWEEP")) : 0; }
-    CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
-    if (!append) CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
-    const long long n_work = list ? n_list : h->n_units;
-    CUDA_TRY(h, cudaEventRecord(no_wait ? h->ev2 : h->ev0, h->stream));
+}
+
+// Enqueue the kernel of `kind` for `n_work` work items (grid sizing only) on the handle's stream.
+static cudaError_t enqueue_kernel(nxb_handle* h, int kind, const Tier& tier, const NxbSweepParams& p, long long n_work) {
+    const bool tolpar = kind == KIND_BLINK && h->tolpar && tier.tp_units > 0;
     if (tolpar) {
         const int grid = (int)std::max<long long>(1, std::min<long long>(h->num_sms, (n_work + tier.tp_units - 1) / tier.tp_units));
         const int threads = tier.tp_units * tier.tp_wpu * 32;
@@ -1622,7 +1658,7 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
         if (h->msg_f64) blink_kernel<double><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
         else blink_kernel<float><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
     } else {
-        const int gw = std::max(group_warps, 1);
+        const int gw = std::max(p.group_warps, 1);
         const int launch_warps = tier.warps / gw * gw;       // whole groups only
         int grid = (int)std::min<long long>(h->num_sms, (n_work + launch_warps - 1) / launch_warps);
         grid = std::max(grid, 1);
@@ -1634,7 +1670,23 @@ static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps
             else sweep_kernel<float, true><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
         }
     }
-    CUDA_TRY(h, cudaGetLastError());
+    return cudaGetLastError();
+}
+
+// One kernel launch over `list` (or every unit): fills the defer list `out` (appending when
+// `append`), adds the kernel time, returns the number of listed units through *n_deferred.
+// `no_wait`: do not wait for the kernel; its time, status and listed units are collected by the
+// next (waiting) launch on the same stream.
+static int launch_one(nxb_handle* h, int kind, const Tier& tier, int group_warps, const int* list, int n_list,
+                      int* out, bool append, unsigned begin, unsigned target, unsigned accum_from, int init,
+                      int* n_deferred, bool no_wait = false) {
+    NxbSweepParams p;
+    fill_params(h, p, kind, tier, group_warps, list, n_list, out, begin, target, accum_from, init);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_work, 0, 8, h->stream));
+    if (!append) CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
+    const long long n_work = list ? n_list : h->n_units;
+    CUDA_TRY(h, cudaEventRecord(no_wait ? h->ev2 : h->ev0, h->stream));
+    CUDA_TRY(h, enqueue_kernel(h, kind, tier, p, n_work));
     CUDA_TRY(h, cudaEventRecord(no_wait ? h->ev3 : h->ev1, h->stream));
     if (no_wait) { h->pending_kind = kind; *n_deferred = 0; return NXB_OK; }
     int hs[5];
@@ -1740,6 +1792,87 @@ static int run_split(nxb_handle* h, unsigned target, unsigned accum_from) {
     return NXB_OK;
 }
 
+// Split mode without a host round trip per sweep: the launches of up to NXB_ASYNC_CHUNK sweeps are
+// enqueued back to back.  Per sweep: primary-only kernel, blink_kernel (both list the units that
+// do not fit tier 0), then the fused kernel of the next (up to two) tiers over that list, whose
+// length the kernels read on the device (NxbSweepParams::n_list_dev) -- an empty list costs an
+// empty launch.  A unit that is still listed after those tiers stays behind, is listed again by
+// the primary kernel of the following sweeps (it is off schedule) and, if it is still behind when
+// the chunk ends, is finished by the host-driven escalation through the remaining tiers.
+// Status, listed units and kernel times are collected once per chunk.
+#define NXB_ASYNC_CHUNK 32
+static int run_split_async(nxb_handle* h, unsigned target, unsigned accum_from) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const Tier& t0 = h->tiers[0];
+    const int gw = (h->lockstep < 0 && t0.warps >= 8) ? (t0.warps % 10 == 0 ? 10 : t0.warps / 2) : group_warps_for(h, t0.warps);
+    const int nblind = (int)std::min<size_t>(2, h->tiers.size() - 1);
+    if (h->evpool.empty()) {
+        h->evpool.resize(4 * NXB_ASYNC_CHUNK);
+        for (auto& e : h->evpool) CUDA_TRY(h, cudaEventCreate(&e));
+    }
+    unsigned long long* const work = h->d_ctl;
+    int* const cnt = (int*)(h->d_ctl + 4);
+    int* const lists[2] = {h->d_defer[0], h->d_defer[1]};
+    while (h->sweeps < target) {
+        const int nsw = (int)std::min<unsigned>(NXB_ASYNC_CHUNK, target - h->sweeps);
+        CUDA_TRY(h, cudaMemsetAsync(h->d_defer_total, 0, 8, h->stream));
+        for (int i = 0; i < nsw; ++i) {
+            const unsigned sw = h->sweeps + (unsigned)i;
+            NxbSweepParams p;
+            CUDA_TRY(h, cudaMemsetAsync(h->d_ctl, 0, 48, h->stream));
+            CUDA_TRY(h, cudaEventRecord(h->evpool[4 * i + 0], h->stream));
+            fill_params(h, p, KIND_PRIMARY, t0, gw, nullptr, 0, lists[0], sw, sw + 1, accum_from, 0);
+            p.work_counter = work + 0; p.defer_count = cnt + 0;
+            CUDA_TRY(h, enqueue_kernel(h, KIND_PRIMARY, t0, p, h->n_units));
+            CUDA_TRY(h, cudaEventRecord(h->evpool[4 * i + 1], h->stream));
+            fill_params(h, p, KIND_BLINK, t0, 1, nullptr, 0, lists[0], sw, sw + 1, accum_from, 0);
+            p.work_counter = work + 1; p.defer_count = cnt + 0;
+            CUDA_TRY(h, enqueue_kernel(h, KIND_BLINK, t0, p, h->n_units));
+            CUDA_TRY(h, cudaEventRecord(h->evpool[4 * i + 2], h->stream));
+            for (int b = 0; b < nblind; ++b) {
+                const Tier& tt = h->tiers[1 + b];
+                fill_params(h, p, KIND_FUSED, tt, 1, lists[b & 1], 0, lists[(b + 1) & 1], sw, sw + 1, accum_from, 0);
+                p.n_list_dev = cnt + b; p.defer_count = cnt + b + 1; p.work_counter = work + 2 + b;
+                if (b == 0) p.defer_total = h->d_defer_total;
+                // (full grid: the list length is not known here; CTAs without work leave at once)
+                CUDA_TRY(h, enqueue_kernel(h, KIND_FUSED, tt, p, h->n_units));
+            }
+            CUDA_TRY(h, cudaEventRecord(h->evpool[4 * i + 3], h->stream));
+        }
+        struct { int status[4]; int cnt[4]; unsigned long long total; } hs;
+        CUDA_TRY(h, cudaMemcpyAsync(hs.status, h->d_status, 16, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(hs.cnt, cnt, 16, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(&hs.total, h->d_defer_total, 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < nsw; ++i) {
+            float a = 0.f, b = 0.f, c = 0.f;
+            cudaEventElapsedTime(&a, h->evpool[4 * i + 0], h->evpool[4 * i + 1]);
+            cudaEventElapsedTime(&b, h->evpool[4 * i + 1], h->evpool[4 * i + 2]);
+            cudaEventElapsedTime(&c, h->evpool[4 * i + 2], h->evpool[4 * i + 3]);
+            h->kind_ms[KIND_PRIMARY] += a; h->kind_ms[KIND_BLINK] += b; h->kind_ms[KIND_FUSED] += c;
+            h->last_ms += a + b + c;
+        }
+        h->kind_launches[KIND_PRIMARY] += nsw; h->kind_launches[KIND_BLINK] += nsw; h->kind_launches[KIND_FUSED] += nsw * nblind;
+        h->last_launches += nsw * (2 + nblind); h->launches_total += nsw * (2 + nblind);
+        if (hs.status[0] != 0) {
+            char buf[256];
+            snprintf(buf, sizeof(buf), "%s (code %d, unit %d, detail %d, sweep %d)", status_text(hs.status[0]),
+                     hs.status[0], hs.status[1], hs.status[2], hs.status[3]);
+            cudaMemsetAsync(h->d_status, 0, 16, h->stream);
+            return set_err(h, hs.status[0], buf);
+        }
+        h->deferred_total += (long long)hs.total;
+        h->sweeps += (unsigned)nsw;
+        const int left = hs.cnt[nblind];            // still behind after the last sweep of the chunk
+        if (left > 0) {
+            h->deferred_total += left;
+            int rc = run_tiers(h, h->sweeps, accum_from, 0, (size_t)nblind + 1, lists[nblind & 1], left);
+            if (rc) return rc;
+        }
+    }
+    return NXB_OK;
+}
+
 extern "C" int nxb_init_chains(nxb_handle* h, int32_t chains, uint64_t seed, int64_t unit_offset) {
     if (!h || chains <= 0) return set_err(h, NXB_ERR_BAD_ARG, "bad argument");
     if (!h->d_pri_ok) return set_err(h, NXB_ERR_BAD_ARG, "call nxb_set_data first");
@@ -1768,6 +1901,7 @@ extern "C" int nxb_sweep(nxb_handle* h, int32_t n_sweeps, int32_t accumulate) {
     const unsigned accum_from = accumulate ? h->sweeps : 0xffffffffu;
     h->last_ms = 0.f; h->last_launches = 0;
     for (int i = 0; i < 4; ++i) { h->kind_ms[i] = 0.f; h->kind_launches[i] = 0; }
+    if (h->split && !h->tolpar && !h->validate && !h->sync_sweeps && h->tiers[0].blink_units > 0) return run_split_async(h, target, accum_from);
     if (h->split && (h->tiers[0].blink_units > 0 || (h->tolpar && h->tiers[0].tp_units > 0))) return run_split(h, target, accum_from);
     int rc = run_tiers(h, target, accum_from, 0);
     if (rc == NXB_OK) h->sweeps = target;
@@ -1896,8 +2030,11 @@ extern "C" int nxb_forward_sample_rooted(nxb_handle* h, int64_t n_units, uint64_
     h->n_units = n_units; h->chains = 1; h->seed = seed; h->unit_offset = unit_offset; h->sweeps = 0;
     const int cap_events = h->gcapB;
     unsigned short* tmp_code = nullptr; double* tmp_time = nullptr;
+    DevFree tmp;                        // temporaries are released on every exit path
     CUDA_TRY(h, cudaMalloc(&tmp_code, 2 * (size_t)n_units * cap_events));
+    tmp.ptrs.push_back(tmp_code);
     CUDA_TRY(h, cudaMalloc(&tmp_time, 8 * (size_t)n_units * cap_events));
+    tmp.ptrs.push_back(tmp_time);
     NxbSweepParams p;
     memset(&p, 0, sizeof(p));
     p.ml = h->ml; p.sl = h->sl; p.blob = h->d_blob;
@@ -1911,7 +2048,9 @@ extern "C" int nxb_forward_sample_rooted(nxb_handle* h, int64_t n_units, uint64_
     int* d_rpri = nullptr; unsigned* d_rtol = nullptr;
     if (root_pri) {
         CUDA_TRY(h, cudaMalloc(&d_rpri, 4 * (size_t)n_units));
+        tmp.ptrs.push_back(d_rpri);
         CUDA_TRY(h, cudaMalloc(&d_rtol, 4 * (size_t)n_units));
+        tmp.ptrs.push_back(d_rtol);
         CUDA_TRY(h, cudaMemcpyAsync(d_rpri, root_pri, 4 * (size_t)n_units, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(h, cudaMemcpyAsync(d_rtol, root_tol, 4 * (size_t)n_units, cudaMemcpyHostToDevice, h->stream));
     }
@@ -1921,7 +2060,6 @@ extern "C" int nxb_forward_sample_rooted(nxb_handle* h, int64_t n_units, uint64_
     int hs[4];
     CUDA_TRY(h, cudaMemcpyAsync(hs, h->d_status, 16, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(tmp_code); cudaFree(tmp_time); cudaFree(d_rpri); cudaFree(d_rtol);
     if (hs[0] != 0) {
         cudaMemsetAsync(h->d_status, 0, 16, h->stream);
         return set_err(h, hs[0], "forward sample outgrew the slab capacity; re-create the handle with a larger cap_scale");
@@ -1934,15 +2072,17 @@ extern "C" int nxb_read_node_states(nxb_handle* h, int32_t* node_pri, uint32_t* 
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t n = (size_t)h->n_units * h->ml.N;
     int* d_pri = nullptr; unsigned* d_tol = nullptr;
+    DevFree tmp;
     CUDA_TRY(h, cudaMalloc(&d_pri, 4 * n));
+    tmp.ptrs.push_back(d_pri);
     CUDA_TRY(h, cudaMalloc(&d_tol, 4 * n));
+    tmp.ptrs.push_back(d_tol);
     node_states_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
         h->d_state, h->stride, h->n_units, h->ml.N, h->so_tol, h->so_pri, d_pri, d_tol);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemcpyAsync(node_pri, d_pri, 4 * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(node_tol, d_tol, 4 * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(d_pri); cudaFree(d_tol);
     return NXB_OK;
 }
 

@@ -183,6 +183,9 @@ struct NxbSweepParams {
     int chains;                         // chains per site
     const int* unit_list;               // optional: deferred units to process
     int n_list;
+    const int* n_list_dev;              // optional: length of unit_list, read on the device (written by the
+                                        // kernels before it on the stream: no host round trip); 0 -> the launch does nothing
+    unsigned long long* defer_total;    // optional: running total of listed units (block 0 adds *n_list_dev)
     int* defer_list;                    // out: units that overflowed this tier
     int* defer_count;
     unsigned long long seed;

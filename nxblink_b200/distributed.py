@@ -33,11 +33,15 @@ class _DevArray(object):
                 shape=(n,), typestr=typestr, data=(int(ptr), False), version=2)
 
 
-def device_summary_tensors(sampler):
-    """torch views (int64 counts, float64 dwell) of the sampler's device buffers."""
+def device_summary_tensors(sampler, device=None):
+    """torch views (int64 counts, float64 dwell) of the sampler's device buffers (zero copy).
+    ``device``: the CUDA device index the sampler was created on (default: its ``device``
+    attribute, else torch's current device)."""
     import torch
     c_ptr, d_ptr = sampler.summary_device_ptrs()
-    dev = torch.device('cuda', torch.cuda.current_device())
+    if device is None:
+        device = getattr(sampler, 'device', None)
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else int(device))
     counts = torch.as_tensor(_DevArray(c_ptr, sampler.layout.n_counts, '<i8'), device=dev)
     dwell = torch.as_tensor(_DevArray(d_ptr, sampler.layout.n_dwell, '<f8'), device=dev)
     return counts, dwell
@@ -88,9 +92,11 @@ class ShardedSampler(object):
         self.sampler.sweep(n_sweeps, accumulate=accumulate)
 
     def allreduce(self):
-        """NCCL all-reduce of the device statistics; returns the global Summary inputs."""
+        """NCCL all-reduce of the device statistics; returns the GLOBAL (counts, dwell) as host
+        arrays.  The reduction works on copies: the sampler's own accumulators keep this rank's
+        statistics, so accumulating further sweeps and reducing again never counts anything twice."""
         import torch
         counts, dwell = device_summary_tensors(self.sampler)
+        counts, dwell = counts.clone(), dwell.clone()
         allreduce_summary(counts, dwell)
-        torch.cuda.synchronize()
-        return self.sampler.read_summary()
+        return counts.cpu().numpy().view(np.uint64), dwell.cpu().numpy()

@@ -167,13 +167,101 @@ def maximization_step(mstep, kappa, omega, A, C, G, T, blink_on, blink_off, edge
             rate_off=off, edge_rates=rates, neg_ll=res.fun, penalty=penalty, result=res)
 
 
+class DeviceMStep(object):
+    """The same objective and minimisation on the DEVICE-resident statistics (``nxb_mstep``:
+    csrc/mstep_kernel.cu): objective + closed-form gradient from the flat statistic buffers, L-BFGS
+    inside one kernel launch.  ``counts_ptr`` / ``dwell_ptr``: device pointers (default: the
+    sampler's own accumulators; after an all-reduce pass the reduced copies)."""
+
+    def __init__(self, sampler, genetic_code, counts_ptr=None, dwell_ptr=None):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        pm = self.pm = sampler.pm
+        self.device = getattr(sampler, 'device', 0)
+        self.layout = sampler.layout
+        if counts_ptr is None:
+            counts_ptr, dwell_ptr = sampler.summary_device_ptrs()
+        self.counts_ptr, self.dwell_ptr = int(counts_ptr), int(dwell_ptr)
+        rows, cols, nt_to, is_ts, is_non, nt_counts = mg94_tables(genetic_code)
+        assert (rows == pm.q_row).all() and (cols == pm.q_col).all()
+        # summary.py:221 (SURVEY quirk 1): an ON track counts unless the class NAME equals True
+        xon_w = np.array([0.0 if (name == True) else 1.0 for name in pm.tols])     # noqa: E712
+        self._keep = dict(q_ptr=np.ascontiguousarray(pm.q_ptr, dtype=np.int32),
+                q_col=np.ascontiguousarray(pm.q_col, dtype=np.int32),
+                cls=np.ascontiguousarray(pm.state_class, dtype=np.int32),
+                nt_to=np.ascontiguousarray(nt_to, dtype=np.int32),
+                is_ts=np.ascontiguousarray(is_ts, dtype=np.uint8),
+                is_non=np.ascontiguousarray(is_non, dtype=np.uint8),
+                nt_counts=np.ascontiguousarray(nt_counts, dtype=np.float64),
+                xon_w=np.ascontiguousarray(xon_w, dtype=np.float64))
+        k = self._keep
+        d = self.desc = _lib.MStepDesc()
+        d.n_edges, d.n_states, d.n_classes, d.nnz = pm.n_nodes - 1, pm.n_states, pm.n_classes, pm.nnz
+        d.q_ptr, d.q_col, d.state_class = k['q_ptr'].ctypes.data, k['q_col'].ctypes.data, k['cls'].ctypes.data
+        d.nt_to, d.is_ts, d.is_non = k['nt_to'].ctypes.data, k['is_ts'].ctypes.data, k['is_non'].ctypes.data
+        d.nt_counts, d.xon_weight = k['nt_counts'].ctypes.data, k['xon_w'].ctypes.data
+        self.n = 8 + d.n_edges
+        self._C = C
+
+    def _call(self, x, maxiter, eval_only):
+        C = self._C
+        x = np.array(x, dtype=np.float64)
+        assert x.shape == (self.n,)
+        f = C.c_double()
+        g = np.zeros(self.n)
+        info = np.zeros(3, dtype=np.int32)
+        rc = self.lib.nxb_mstep(int(self.device), C.byref(self.desc), C.byref(self.layout),
+                self.counts_ptr, self.dwell_ptr, x.ctypes.data, int(maxiter), int(eval_only),
+                C.byref(f), g.ctypes.data, info.ctypes.data)
+        if rc:
+            from ._lib import NxbError
+            raise NxbError(rc, self.lib.nxb_mstep_last_error().decode())
+        return x, f.value, g, info
+
+    def neg_ll_and_grad(self, log_params):
+        _, f, g, _ = self._call(log_params, 0, 1)
+        return f, g
+
+    def minimize(self, x0, maxiter=200):
+        x, f, g, info = self._call(x0, maxiter, 0)
+        return x, f, g, dict(iterations=int(info[0]), evaluations=int(info[1]), status=int(info[2]),
+                kernel_ms=float(self.lib.nxb_mstep_last_kernel_ms()))
+
+
+def m_step(sampler, summary, genetic_code, kappa, omega, A, C, G, T, blink_on, blink_off, edge_rates,
+        maxiter=200, where='device', counts_ptr=None, dwell_ptr=None):
+    """The M-step of one EM iteration (p53em.py:94-140).  ``where='device'``: on the statistics
+    resident on the GPU (``DeviceMStep``); ``'host'``: numpy objective + scipy L-BFGS-B on
+    ``summary`` (the check of the device path, tests/test_gpu_em.py)."""
+    if where == 'host':
+        mstep = MStep(sampler.pm, summary, genetic_code)
+        new = maximization_step(mstep, kappa, omega, A, C, G, T, blink_on, blink_off, edge_rates, maxiter)
+        new['mstep'] = mstep
+        new['where'] = 'host (numpy objective + closed-form gradient, scipy L-BFGS-B)'
+        return new
+    dm = DeviceMStep(sampler, genetic_code, counts_ptr, dwell_ptr)
+    rates = np.maximum(np.asarray(edge_rates, dtype=float), 1e-12)
+    x0 = np.log(np.concatenate([[kappa, omega, A, C, G, T, blink_on, blink_off], rates]))
+    x, f, g, info = dm.minimize(x0, maxiter)
+    kappa, omega, nt, on, off, rates, penalty = unpack_params(x)
+    return dict(kappa=kappa, omega=omega, A=nt[0], C=nt[1], G=nt[2], T=nt[3], rate_on=on,
+            rate_off=off, edge_rates=rates, neg_ll=f, penalty=penalty, result=info, x=x, grad=g,
+            mstep=dm, where='device (nxb_mstep: objective, gradient and L-BFGS in one kernel launch)')
+
+
 def em_iteration(model, packed_data, params, chains=8, nburnin=10, nsamples=10, seed=0,
-        device=0, reduce_fn=None, sampler=None):
+        device=0, reduce_fn=None, sampler=None, mstep='device', reduce_device_fn=None):
     """One EM iteration (run-stochastic.py:154-208): build the model from ``params``, run
-    the E-step on the device, maximise.  ``reduce_fn(counts, dwell)`` may all-reduce the
-    statistics across ranks (nxblink_b200.distributed).  Pass the ``sampler`` of the previous
-    iteration (returned as ``new['sampler']`` when one was given) to reuse its device buffers:
-    only the model values are replaced (``BlinkSampler.update_model``)."""
+    the E-step on the device, maximise.  Pass the ``sampler`` of the previous iteration
+    (returned as ``new['sampler']`` when one was given) to reuse its device buffers: only the
+    model values are replaced (``BlinkSampler.update_model``).
+
+    ``mstep='device'`` (default): the M-step runs on the statistics where they are, on the GPU
+    (``DeviceMStep``); with several GPUs ``reduce_device_fn(sampler)`` all-reduces them on the
+    device and returns the (counts, dwell) device pointers of the reduced buffers.
+    ``mstep='host'``: statistics are copied out (``reduce_fn(counts, dwell)`` may all-reduce host
+    copies) and the numpy/scipy M-step runs on them -- the checker of the device path."""
     pm0 = PackedModel(model)
     edge_to_rate = dict(zip(pm0.edges, params['edge_rates']))
     m = Model(params['kappa'], params['omega'], params['A'], params['C'], params['G'], params['T'],
@@ -186,24 +274,31 @@ def em_iteration(model, packed_data, params, chains=8, nburnin=10, nsamples=10, 
         sampler.reset_summary()
     else:
         sampler = BlinkSampler(pm, device=device)
+    if reduce_fn is not None:
+        mstep = 'host'
+    args = (params['kappa'], params['omega'], params['A'], params['C'], params['G'], params['T'],
+            params['rate_on'], params['rate_off'], params['edge_rates'])
     try:
         if not keep or sampler.data is not packed_data:
             sampler.set_data(packed_data)
         sampler.init_chains(chains=chains, seed=seed)
         sampler.sweep(nburnin, accumulate=False)
         sampler.sweep(nsamples, accumulate=True)
-        counts, dwell = sampler.read_summary()
-        if reduce_fn is not None:
-            counts, dwell = reduce_fn(counts, dwell)
-        summary = sampler.summary(counts, dwell)
+        if mstep == 'device':
+            ptrs = reduce_device_fn(sampler) if reduce_device_fn is not None else (None, None)
+            new = m_step(sampler, None, m.genetic_code, *args, where='device',
+                    counts_ptr=ptrs[0], dwell_ptr=ptrs[1])
+            summary = sampler.summary()
+        else:
+            counts, dwell = sampler.read_summary()
+            if reduce_fn is not None:
+                counts, dwell = reduce_fn(counts, dwell)
+            summary = sampler.summary(counts, dwell)
+            new = m_step(sampler, summary, m.genetic_code, *args, where='host')
     finally:
         if not keep:
             sampler.close()
-    mstep = MStep(pm, summary, m.genetic_code)
-    new = maximization_step(mstep, params['kappa'], params['omega'], params['A'], params['C'],
-            params['G'], params['T'], params['rate_on'], params['rate_off'], params['edge_rates'])
     new['summary'] = summary
-    new['mstep'] = mstep
     if keep:
         new['sampler'] = sampler
     return new

@@ -42,6 +42,7 @@ class BlinkSampler(object):
     def __init__(self, model, device=0, msg_f64=False, cap_scale=1.0,
             validate=False, max_warps=0, lockstep_warps=0, split_phases=0):
         self.lib = _lib.load()
+        self.device = int(device)
         self.pm = model if isinstance(model, PackedModel) else PackedModel(model)
         self._h = C.c_void_p()
         self._desc_kwargs = dict(msg_f64=msg_f64, cap_scale=cap_scale,
@@ -90,16 +91,26 @@ class BlinkSampler(object):
         """``data``: PackedData, or a sequence of reference-style data objects."""
         if not isinstance(data, PackedData):
             data = pack_data(self.pm, list(data))
+        if self.data is not None and data.n_sites != self.data.n_sites:
+            self.chains, self.n_units = 0, 0      # the device drops the chains of the old sites
         self.data = data
         self._check(self.lib.nxb_set_data(self._h, data.n_sites,
             data.pri_ok.ctypes.data, data.tol_true_ok.ctypes.data,
             data.tol_false_ok.ctypes.data))
 
     def init_chains(self, chains=1, seed=0, unit_offset=0):
+        if self.data is None:
+            # (after forward_sample the device holds unconstrained data of its own)
+            raise NxbError(5, 'init_chains: call set_data first')
         self._check(self.lib.nxb_init_chains(self._h, int(chains), int(seed),
             int(unit_offset)))
         self.chains = int(chains)
         self.n_units = self.data.n_sites * self.chains
+
+    def set_stream(self, cuda_stream=0):
+        """Run this sampler's launches and copies on the caller's CUDA stream (an integer
+        ``cudaStream_t``, e.g. ``torch.cuda.current_stream().cuda_stream``); 0 = its own."""
+        self._check(self.lib.nxb_set_stream(self._h, int(cuda_stream)))
 
     def forward_sample(self, n_units, seed=0, unit_offset=0, root_pri=None, root_tol=None):
         """Prior simulation of ``n_units`` trajectories on the device (fwdsample.py:67-262).

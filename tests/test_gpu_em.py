@@ -19,7 +19,7 @@ def test_em_iteration_p53_shape(nb):
     prm = p53.jeff_params()
     params = dict(kappa=prm['kappa'], omega=prm['omega'], A=prm['A'], C=prm['C'], G=prm['G'],
             T=prm['T'], rate_on=1.5, rate_off=0.5, edge_rates=np.maximum(pm.rate[1:], 1e-6))
-    new = p53em.em_iteration(m, data, params, chains=8, nburnin=8, nsamples=8, seed=3)
+    new = p53em.em_iteration(m, data, params, chains=8, nburnin=8, nsamples=8, seed=3, mstep='host')
     mstep, summary = new['mstep'], new['summary']
     assert summary.nsamples == 64 * 8 * 8
     # (1) vectorised objective == the em.py mirror on the same summary
@@ -111,3 +111,57 @@ def test_em_iterations_reuse_the_sampler(nb):
             nsamples=4, seed=10, sampler=sampler)
     assert second['summary'].nsamples == 32 * 4 * 4 and np.isfinite(second['neg_ll'])
     sampler.close()
+
+
+def test_device_mstep_matches_the_host_objective_and_optimum(nb):
+    """nxb_mstep (csrc/mstep_kernel.cu) on the device-resident statistics against the numpy
+    objective / closed-form gradient (p53em.MStep) and the em.py mirror: values and gradients to
+    1e-10, and the on-device L-BFGS lands on the optimum scipy's L-BFGS-B finds."""
+    m = p53.p53_model()
+    pm = packing.PackedModel(m)
+    leaf = pm.node_index[m.name_to_leaf['Has']]
+    ls, tt, tf = p53.synthetic_alignment(pm, 64, seed=1, reference_leaf=leaf)
+    data = packing.pack_alignment(pm, ls, tt, tf)
+    prm = p53.jeff_params()
+    s = nb.BlinkSampler(pm)
+    s.set_data(data)
+    s.init_chains(chains=8, seed=3)
+    s.sweep(8, accumulate=False)
+    s.sweep(8, accumulate=True)
+    summary = s.summary()
+    host = p53em.MStep(pm, summary, m.genetic_code)
+    dev = p53em.DeviceMStep(s, m.genetic_code)
+    x0 = np.log(np.concatenate([[prm['kappa'], prm['omega'], prm['A'], prm['C'], prm['G'], prm['T'], 1.5, 0.5],
+        np.maximum(pm.rate[1:], 1e-6)]))
+    rng = np.random.default_rng(0)
+    for x in (x0, x0 + 0.3 * rng.standard_normal(len(x0))):
+        fh, gh = host.neg_ll_and_grad(x)
+        fd, gd = dev.neg_ll_and_grad(x)
+        assert_allclose(fd, fh, rtol=1e-10)
+        assert_allclose(gd, gh, rtol=1e-8, atol=1e-11 * max(1.0, np.abs(gh).max()))
+    # the em.py mirror (nxblink/em.py:19-198) at x0
+    kappa, omega, nt, on, off, rates, _ = p53em.unpack_params(x0)
+    P = pm.n_states
+    pre_Q = np.zeros((P, P))
+    pre_Q[pm.q_row, pm.q_col] = host.pre_Q(kappa, omega, nt)
+    distn = host.distn(nt)
+    ref = -(em.get_ll_root(summary, distn, on, off)
+            + em.get_ll_dwell(summary, pre_Q, distn, on, off, pm.edges, rates)
+            + em.get_ll_trans(summary, pre_Q, distn, on, off, pm.edges, rates))     # (per sample)
+    assert_allclose(dev.neg_ll_and_grad(x0)[0], ref, rtol=1e-10)
+    # optimum
+    sci = p53em.maximization_step(host, prm['kappa'], prm['omega'], prm['A'], prm['C'], prm['G'], prm['T'],
+            1.5, 0.5, np.maximum(pm.rate[1:], 1e-6))
+    x, f, g, info = dev.minimize(x0, maxiter=200)
+    assert info['status'] in (1, 2), info
+    assert_allclose(host.neg_ll(x), f, rtol=1e-10)              # the device's own value is right
+    assert abs(f - sci['neg_ll']) <= 2e-6 * abs(sci['neg_ll']), (f, sci['neg_ll'], info)
+    assert np.abs(g).max() < 1e-3
+    new = p53em.m_step(s, None, m.genetic_code, prm['kappa'], prm['omega'], prm['A'], prm['C'], prm['G'],
+            prm['T'], 1.5, 0.5, np.maximum(pm.rate[1:], 1e-6))
+    assert new['where'].startswith('device')
+    for k in ('kappa', 'omega', 'rate_on', 'rate_off'):
+        assert_allclose(new[k], sci[k], rtol=2e-2)
+    big = host.trans_total > 50
+    assert_allclose(new['edge_rates'][big], sci['edge_rates'][big], rtol=5e-2)
+    s.close()

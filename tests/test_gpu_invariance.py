@@ -127,3 +127,28 @@ def test_hard_constraints_survive_a_long_soak(nb):
         s.init_chains(chains=65536, seed=7000 + seed)
         s.sweep(150, accumulate=False)          # raises on the first violated invariant
         s.close()
+
+
+def test_event_parallel_kernel_geometry_invariance(nb, monkeypatch):
+    """NXB_TOLPAR=1 (tolpar_kernel): its random streams are keyed by (seed, global unit, sweep,
+    slice | retained index | track), so one or two warps per unit, the capacity tier (deferral) and
+    sharding leave the integer statistics bit-identical.  (It is a different exact sampler from
+    the lane-per-track walk, so the two are compared statistically, not bitwise:
+    tests/test_gpu_precision.py.)"""
+    pm, data = _p53_inputs(24)
+    monkeypatch.setenv('NXB_TOLPAR', '1')
+    monkeypatch.setenv('NXB_TP_WPU', '2')
+    base = _run(nb, pm, data, chains=8, validate=True)
+    assert base[0][-1] == 24 * 8 * 6
+    small = _run(nb, pm, data, chains=8, cap_scale=0.55)
+    assert small[2]['deferred_units'] > 0
+    few = _run(nb, pm, data, chains=8, max_warps=4)
+    monkeypatch.setenv('NXB_TP_WPU', '1')
+    one = _run(nb, pm, data, chains=8)
+    lo = packing.PackedData(data.pri_ok[:8], data.tol_true_ok[:8], data.tol_false_ok[:8])
+    hi = packing.PackedData(data.pri_ok[8:], data.tol_true_ok[8:], data.tol_false_ok[8:])
+    a = _run(nb, pm, lo, chains=8, unit_offset=0)
+    b = _run(nb, pm, hi, chains=8, unit_offset=8 * 8)
+    for other in (small, few, one, (a[0] + b[0], a[1] + b[1], None)):
+        assert (base[0] == other[0]).all()
+        np.testing.assert_allclose(base[1], other[1], rtol=1e-11, atol=1e-9)
