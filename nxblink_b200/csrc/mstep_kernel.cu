@@ -72,6 +72,11 @@ __device__ void block_sum4(MsShared& sh, double v[4], int nv) {
 
 // n*LL and its gradient in the log-parameters at xs[]; dynamic shared arrays q/G [nnz],
 // distn/rowsum/dld [P].  Returns f = -LL/n through sh.bc[0]; gradient of f in gout[].
+// PROFILE: the edge rates are not read from xs but set to their closed-form stationary point
+// given the other parameters, rate_e = ER * transitions_e / D_e (1e-12 for an edge without
+// transitions, which the reference sets to zero: p53em.py:25-27); by the envelope theorem the
+// gradient in the 8 global parameters is the same expression evaluated at those rates.
+template <bool PROFILE>
 __device__ void ms_eval(const MsArgs& a, MsShared& sh, const double* xs, double* gout, double* dyn) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, NW = MS_THREADS / 32;
     const int E = a.E, P = a.P, nnz = a.nnz;
@@ -92,7 +97,7 @@ __device__ void ms_eval(const MsArgs& a, MsShared& sh, const double* xs, double*
     const double p_off = off / (on + off), p_on = on / (on + off);
     for (int i = tid; i < nnz; i += MS_THREADS)
         q[i] = nt[a.nt_to[i]] * (a.is_ts[i] ? kappa : 1.0) * (a.is_non[i] ? omega : 1.0);
-    for (int e = tid; e < E; e += MS_THREADS) sh.rate[e] = exp(xs[8 + e]);
+    if (!PROFILE) for (int e = tid; e < E; e += MS_THREADS) sh.rate[e] = exp(xs[8 + e]);
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     for (int s = tid; s < P; s += MS_THREADS) {
         double wgt = 1.0;
@@ -126,11 +131,16 @@ __device__ void ms_eval(const MsArgs& a, MsShared& sh, const double* xs, double*
     }
     block_sum4(sh, v, 2);
     const double ER = v[0], ll_root_pri = v[1];
+    if (PROFILE) {
+        for (int e = tid; e < E; e += MS_THREADS)
+            sh.rate[e] = (a.tt[e] > 0.0 && sh.De[e] > 0.0) ? ER * a.tt[e] / sh.De[e] : 1e-12;
+        __syncthreads();
+    }
     v[0] = 0.0; v[1] = 0.0; v[2] = 0.0; v[3] = 0.0;
     for (int e = tid; e < E; e += MS_THREADS) {
         const double r = sh.rate[e];
         v[0] += sh.De[e] * r;                                   // A
-        v[1] += a.tt[e] * (xs[8 + e] - log(ER));                // sum_e TT_e log(rate_e / ER)
+        if (a.tt[e] > 0.0) v[1] += a.tt[e] * (log(r) - log(ER));   // sum_e TT_e log(rate_e / ER)
         v[2] += r * a.offx[e];
         v[3] += r * a.xoff[e];
     }
@@ -183,8 +193,9 @@ __device__ void ms_eval(const MsArgs& a, MsShared& sh, const double* xs, double*
         gout[7] = -(root_off * p_on - root_xon * p_off - r_xoff * off / ER + OnOff) / nsamp;
         sh.bc[0] = -ll / nsamp;
     }
-    for (int e = tid; e < E; e += MS_THREADS)
-        gout[8 + e] = -(-sh.rate[e] * sh.De[e] / ER + a.tt[e]) / nsamp;
+    if (!PROFILE)
+        for (int e = tid; e < E; e += MS_THREADS)
+            gout[8 + e] = -(-sh.rate[e] * sh.De[e] / ER + a.tt[e]) / nsamp;
     __syncthreads();
 }
 
@@ -248,83 +259,107 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mstep_kernel(const MsArgs a) {
     }
     for (int i = tid; i < n; i += MS_THREADS) sh.x[i] = a.x[i];
     __syncthreads();
-    ms_eval(a, sh, sh.x, sh.g, dyn);
-    double f = sh.bc[0];
     int evals = 1, iters = 0, status = 0, hist = 0, head = 0;
-    double rho[MS_HIST], alpha[MS_HIST];         // (every thread holds the same values)
-    for (int j = 0; j < MS_HIST; ++j) { rho[j] = 0.0; alpha[j] = 0.0; }
-    if (!a.eval_only) {
-        // ---- L-BFGS (two-loop recursion, Armijo backtracking with a curvature check) ----
+    double f;
+    if (a.eval_only) {
+        ms_eval<false>(a, sh, sh.x, sh.g, dyn);
+        f = sh.bc[0];
+    } else {
+        // ---- L-BFGS over the 8 global parameters of the profile objective (two-loop recursion,
+        // weak-Wolfe line search by bisection / doubling) ----
+        const int m = 8;
+        for (int i = tid; i < n; i += MS_THREADS) { sh.g[i] = 0.0; sh.gn[i] = 0.0; }
+        __syncthreads();
+        ms_eval<true>(a, sh, sh.x, sh.g, dyn);
+        f = sh.bc[0];
+        double rho[MS_HIST], alpha[MS_HIST];         // (every thread holds the same values)
+        for (int j = 0; j < MS_HIST; ++j) { rho[j] = 0.0; alpha[j] = 0.0; }
         for (; iters < a.maxiter; ++iters) {
             double gmax = 0.0;
-            for (int i = 0; i < n; ++i) gmax = fmax(gmax, fabs(sh.g[i]));
+            for (int i = 0; i < m; ++i) gmax = fmax(gmax, fabs(sh.g[i]));
             if (gmax <= a.gtol) { status = 1; break; }
             // direction d = -H g
-            for (int i = tid; i < n; i += MS_THREADS) sh.d[i] = sh.g[i];
+            for (int i = tid; i < m; i += MS_THREADS) sh.d[i] = sh.g[i];
             __syncthreads();
             for (int j = 0; j < hist; ++j) {
                 const int k = (head - 1 - j + MS_HIST) % MS_HIST;
-                const double al = rho[k] * ms_dot(sh, sh.S[k], sh.d, n);
+                const double al = rho[k] * ms_dot(sh, sh.S[k], sh.d, m);
                 alpha[k] = al;
-                for (int i = tid; i < n; i += MS_THREADS) sh.d[i] -= al * sh.Y[k][i];
+                for (int i = tid; i < m; i += MS_THREADS) sh.d[i] -= al * sh.Y[k][i];
                 __syncthreads();
             }
             if (hist > 0) {
                 const int k = (head - 1 + MS_HIST) % MS_HIST;
-                const double yy = ms_dot(sh, sh.Y[k], sh.Y[k], n);
+                const double yy = ms_dot(sh, sh.Y[k], sh.Y[k], m);
                 const double gam = 1.0 / (rho[k] * yy);
-                for (int i = tid; i < n; i += MS_THREADS) sh.d[i] *= gam;
+                for (int i = tid; i < m; i += MS_THREADS) sh.d[i] *= gam;
                 __syncthreads();
             }
             for (int j = hist - 1; j >= 0; --j) {
                 const int k = (head - 1 - j + MS_HIST) % MS_HIST;
-                const double be = rho[k] * ms_dot(sh, sh.Y[k], sh.d, n);
+                const double be = rho[k] * ms_dot(sh, sh.Y[k], sh.d, m);
                 const double al = alpha[k];
-                for (int i = tid; i < n; i += MS_THREADS) sh.d[i] += (al - be) * sh.S[k][i];
+                for (int i = tid; i < m; i += MS_THREADS) sh.d[i] += (al - be) * sh.S[k][i];
                 __syncthreads();
             }
-            for (int i = tid; i < n; i += MS_THREADS) sh.d[i] = -sh.d[i];
+            for (int i = tid; i < m; i += MS_THREADS) sh.d[i] = -sh.d[i];
             __syncthreads();
-            double gd = ms_dot(sh, sh.g, sh.d, n);
+            double gd = ms_dot(sh, sh.g, sh.d, m);
             if (!(gd < 0.0)) {                  // not a descent direction: restart from steepest descent
                 hist = 0;
-                for (int i = tid; i < n; i += MS_THREADS) sh.d[i] = -sh.g[i];
+                for (int i = tid; i < m; i += MS_THREADS) sh.d[i] = -sh.g[i];
                 __syncthreads();
-                gd = ms_dot(sh, sh.g, sh.d, n);
+                gd = ms_dot(sh, sh.g, sh.d, m);
             }
             double step = 1.0;
-            if (hist == 0) { const double gn2 = sqrt(ms_dot(sh, sh.g, sh.g, n)); step = fmin(1.0, 1.0 / gn2); }
-            // line search: backtrack until Armijo holds; expand once if the slope is still steep
-            double fn = f;
+            if (hist == 0) { const double gn2 = sqrt(ms_dot(sh, sh.g, sh.g, m)); step = fmin(1.0, 1.0 / gn2); }
+            // weak Wolfe: f(x + t d) <= f + c1 t g.d  and  g(x + t d).d >= c2 g.d
+            double lo = 0.0, hi = INFINITY, fn = f;
             bool ok = false;
             for (int ls = 0; ls < 40; ++ls) {
-                for (int i = tid; i < n; i += MS_THREADS) sh.xn[i] = sh.x[i] + step * sh.d[i];
+                for (int i = tid; i < m; i += MS_THREADS) sh.xn[i] = sh.x[i] + step * sh.d[i];
                 __syncthreads();
-                ms_eval(a, sh, sh.xn, sh.gn, dyn);
+                ms_eval<true>(a, sh, sh.xn, sh.gn, dyn);
                 ++evals;
                 fn = sh.bc[0];
-                if (isfinite(fn) && fn <= f + 1e-4 * step * gd) { ok = true; break; }
-                step *= 0.5;
+                if (!(isfinite(fn) && fn <= f + 1e-4 * step * gd)) { hi = step; step = 0.5 * (lo + hi); continue; }
+                const double gdn = ms_dot(sh, sh.gn, sh.d, m);
+                if (gdn < 0.9 * gd) { lo = step; step = isinf(hi) ? 2.0 * step : 0.5 * (lo + hi); continue; }
+                ok = true;
+                break;
+            }
+            if (!ok && lo > 0.0) {              // no Wolfe point found: the largest step with sufficient decrease
+                for (int i = tid; i < m; i += MS_THREADS) sh.xn[i] = sh.x[i] + lo * sh.d[i];
+                __syncthreads();
+                ms_eval<true>(a, sh, sh.xn, sh.gn, dyn);
+                ++evals;
+                fn = sh.bc[0];
+                ok = true;
             }
             if (!ok) { status = 3; break; }
-            // curvature: s.y > 0 -> history update
             const int k = head;
-            for (int i = tid; i < n; i += MS_THREADS) { sh.S[k][i] = sh.xn[i] - sh.x[i]; sh.Y[k][i] = sh.gn[i] - sh.g[i]; }
+            for (int i = tid; i < m; i += MS_THREADS) { sh.S[k][i] = sh.xn[i] - sh.x[i]; sh.Y[k][i] = sh.gn[i] - sh.g[i]; }
             __syncthreads();
-            const double sy = ms_dot(sh, sh.S[k], sh.Y[k], n);
-            const double yy = ms_dot(sh, sh.Y[k], sh.Y[k], n);
+            const double sy = ms_dot(sh, sh.S[k], sh.Y[k], m);
+            const double yy = ms_dot(sh, sh.Y[k], sh.Y[k], m);
             if (sy > 1e-10 * yy && sy > 0.0) {
                 rho[k] = 1.0 / sy;
                 head = (head + 1) % MS_HIST;
                 if (hist < MS_HIST) ++hist;
             }
             const double fold = f;
-            for (int i = tid; i < n; i += MS_THREADS) { sh.x[i] = sh.xn[i]; sh.g[i] = sh.gn[i]; }
+            for (int i = tid; i < m; i += MS_THREADS) { sh.x[i] = sh.xn[i]; sh.g[i] = sh.gn[i]; }
             f = fn;
             __syncthreads();
             if ((fold - f) <= a.ftol * fmax(fmax(fabs(fold), fabs(f)), 1.0)) { ++iters; status = 2; break; }
         }
         if (status == 0) status = 4;            // iteration limit
+        // the accepted point once more: its rates (the last evaluation may have been a rejected trial)
+        ms_eval<true>(a, sh, sh.x, sh.g, dyn);
+        ++evals;
+        f = sh.bc[0];
+        for (int e = tid; e < E; e += MS_THREADS) { sh.x[8 + e] = log(sh.rate[e]); sh.g[8 + e] = 0.0; }
+        __syncthreads();
     }
     double gmax = 0.0;
     for (int i = 0; i < n; ++i) gmax = fmax(gmax, fabs(sh.g[i]));
