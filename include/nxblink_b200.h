@@ -72,6 +72,7 @@ typedef struct {
     int32_t capP, capB, capF, capC;
     int64_t deferred_units;      /* units that needed a higher capacity tier so far */
     int64_t kernel_launches;     /* sweep-kernel launches so far */
+    int64_t capacity_doublings;  /* times a unit outgrew its HBM slab and every capacity was doubled (see nxb_sweep) */
 } nxb_stats;
 
 int nxb_device_count(void);
@@ -85,9 +86,10 @@ int nxb_destroy(nxb_handle* h);
  * buffers, capacity tiers, data and unit states are kept; chains may be continued (warm start)
  * or initialised again with nxb_init_chains.  If an edge switched between zero and positive
  * rate x length the unit states are dropped and nxb_init_chains must be called.  Capacities
- * (shared-memory tiers, slab sizes: 4x the expected event counts) remain those of the model the
- * handle was created for: a model with several times higher rates may exhaust them
- * (NXB_ERR_STATE_CAP / NXB_ERR_SCRATCH_CAP); create a new handle in that case. */
+ * (shared-memory tiers, slab sizes: 4x the expected event counts) follow the model: when the new
+ * rates mean more events per unit than the handle was sized for, they are derived again and the
+ * unit states are moved to the larger slabs.  The update is atomic: a refused model (e.g. edge
+ * rate x length too large) leaves the handle exactly as it was. */
 int nxb_update_model(nxb_handle* h, const nxb_model_desc* desc);
 const char* nxb_last_error(const nxb_handle* h);   /* h may be NULL: last create error */
 
@@ -106,7 +108,11 @@ int nxb_init_chains(nxb_handle* h, int32_t chains, uint64_t seed, int64_t unit_o
 
 /* n_sweeps full Gibbs sweeps (raoteh.py:392-435) of every unit.  If `accumulate`
  * the sufficient statistics of every sweep are added to the device summary
- * (nxblink/summary.py:190-243 Summary.on_sample). */
+ * (nxblink/summary.py:190-243 Summary.on_sample).  The launches of up to 32 sweeps are enqueued
+ * back to back; status and timings are collected once per such chunk.  A unit whose trajectory
+ * outgrows its HBM slab does not end the call: every capacity is doubled, the states move to the
+ * larger slabs and the unit is run again from where it stood, its already booked statistics
+ * skipped -- results are identical to those of a handle that was large enough from the start. */
 int nxb_sweep(nxb_handle* h, int32_t n_sweeps, int32_t accumulate);
 
 int nxb_summary_layout_get(const nxb_handle* h, nxb_summary_layout* out);

@@ -54,6 +54,7 @@ class Stats(C.Structure):
         ('capP', C.c_int32), ('capB', C.c_int32),
         ('capF', C.c_int32), ('capC', C.c_int32),
         ('deferred_units', C.c_int64), ('kernel_launches', C.c_int64),
+        ('capacity_doublings', C.c_int64),
     ]
 
 

@@ -205,6 +205,11 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
         if (PRIMARY_ONLY && p.validate && has && hdr.phase != NXB_PHASE_INIT) rc = validate_unit(c);
         tick(c, T_LOAD);
         bool spilled = false;
+        // phases from the slab state on whose statistics were booked by an earlier, failed launch
+        // (the unit outgrew its slab: NXB_ERR_STATE_CAP), and phases completed by this launch
+        const unsigned booked_before = has ? hdr.pad : 0u;
+        unsigned done_phases = 0u;
+        bool statecap = false;
         // One phase per iteration, so that every phase function has a single call site.  In
         // lockstep mode every warp of the group runs the same number of iterations and arrives
         // at every barrier, whether or not its unit is still active.
@@ -222,7 +227,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             if (lockstep && p.init && (step & 1u) == 0u) continue;     // init: one primary pass only
             if ((lockstep || PRIMARY_ONLY) && active && blink_turn != (hdr.phase == NXB_PHASE_BLINK)) active = false;
             c.sweep = init ? NXB_SWEEP_INIT : hdr.sweeps_done;
-            const bool accum = !init && hdr.sweeps_done >= p.accum_from;
+            const bool accum = !init && hdr.sweeps_done >= p.accum_from && done_phases >= booked_before;
             c.nbar = 0;
             // the barriers of the tolerance update are not optional: its lanes work on other warps' units
             c.sync_mask = blink_turn ? 0xffffffffu : p.sync_mask;
@@ -230,7 +235,7 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
                 if (active && init) rc = init_blink(c);
                 if (active && rc == RC_OK) {
                     rc = primary_phase<MSG>(c, init, accum);
-                    if (rc == RC_OK) hdr.phase = init ? NXB_PHASE_PRIMARY : NXB_PHASE_BLINK;
+                    if (rc == RC_OK) { hdr.phase = init ? NXB_PHASE_PRIMARY : NXB_PHASE_BLINK; if (!init) ++done_phases; }
                 }
                 phase_drain(c, NXB_NBAR_PRIMARY);
             } else if (!PRIMARY_ONLY) {
@@ -239,10 +244,11 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
                     const int brc = blink_phase<MSG>(c, accum, active);
                     if (active) {
                         rc = brc;
-                        if (rc == RC_DEFER && c.nB < 0) {     // sweep complete, blink list spilled to HBM
-                            hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
+                        if (rc == RC_STATECAP) { statecap = true; ++done_phases; rc = RC_ERROR; }
+                        else if (rc == RC_DEFER && c.nB < 0) {     // sweep complete, blink list spilled to HBM
+                            hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++; ++done_phases;
                             spilled = true;
-                        } else if (rc == RC_OK) { hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++; }
+                        } else if (rc == RC_OK) { hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++; ++done_phases; }
                     }
                 }
                 phase_drain(c, NXB_NBAR_BLINK);
@@ -253,8 +259,11 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
         if (has && rc != RC_ERROR && !(PRIMARY_ONLY && p.validate_only)) {
             if (c.nP > p.gcapP || (!spilled && c.nB > p.gcapB)) {
                 fail(c, NXB_ERR_STATE_CAP, c.nP > p.gcapP ? c.nP : c.nB);
+                statecap = true;
             } else {
                 __syncwarp();
+                // (a unit that is handed to the next tier in the middle of its already booked phases keeps the rest)
+                hdr.pad = booked_before > done_phases ? booked_before - done_phases : 0u;
                 hdr.n_pri = (uint16_t)c.nP;
                 hdr.n_blk = (uint16_t)(spilled ? -c.nB : c.nB);
                 if (lane == 0) *(NxbUnitHeader*)slab = hdr;
@@ -277,6 +286,10 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
                 __syncwarp();
             }
         }
+        // the slab keeps the state the unit was loaded with; record how many phases from there on
+        // are booked, so that the rerun after the slabs have grown does not book them again
+        if (statecap && has && lane == 0 && !p.init)
+            ((NxbUnitHeader*)slab)->pad = booked_before > done_phases ? booked_before : done_phases;
         tick(c, T_STORE);
     }
     cta_epilogue(c, p, tid);
@@ -343,7 +356,7 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
                         active = true;
                         c.unit = u; c.unit32 = (unsigned)(p.unit_offset + u);
                         c.nP = hdr.n_pri; c.nB = hdr.n_blk; c.sweep = hdr.sweeps_done;
-                        accum = hdr.sweeps_done >= p.accum_from;
+                        accum = hdr.sweeps_done >= p.accum_from && hdr.pad == 0u;     // (pad: already booked, see sweep_kernel)
                         const long long site = u / p.chains;
                         g_tt = p.tol_true_ok + site * N;
                         g_tf = p.tol_false_ok + site * N;
@@ -382,9 +395,10 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
             unsigned char* slab = p.state + c.unit * p.state_stride;
             int rc = blink_finish<MSG, true>(c, accum);          // new blink list written to the slab
             tick(c, T_BW);
+            if (rc == RC_STATECAP) { if (lane == 0) ((NxbUnitHeader*)slab)->pad = 1u; continue; }
             if (rc == RC_ERROR) continue;
             NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;
-            hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++;
+            hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++; hdr.pad = hdr.pad > 0u ? hdr.pad - 1u : 0u;
             hdr.n_blk = (uint16_t)c.nB;
             __syncwarp();
             if (lane == 0) *(NxbUnitHeader*)slab = hdr;
@@ -454,7 +468,7 @@ tolpar_kernel(const __grid_constant__ NxbSweepParams p) {
         // ---- load (coalesced, streaming; only the live part of the slab is read) ----
         u.nP = hdr.n_pri; u.nB = hdr.n_blk;
         u.unit32 = (unsigned)(p.unit_offset + unit); u.sweep = hdr.sweeps_done;
-        const bool accum = hdr.sweeps_done >= p.accum_from;
+        const bool accum = hdr.sweeps_done >= p.accum_from && hdr.pad == 0u;
         const long long site = unit / p.chains;
         const unsigned* const g_tt = p.tol_true_ok + site * N;
         const unsigned* const g_tf = p.tol_false_ok + site * N;
@@ -508,7 +522,7 @@ tolpar_kernel(const __grid_constant__ NxbSweepParams p) {
         // ---- store: header, node states (the new blink list is already in the slab) ----
         {
             NxbUnitHeader h2 = hdr;
-            h2.phase = NXB_PHASE_PRIMARY; h2.sweeps_done = hdr.sweeps_done + 1; h2.n_blk = (uint16_t)n_new;
+            h2.phase = NXB_PHASE_PRIMARY; h2.sweeps_done = hdr.sweeps_done + 1; h2.n_blk = (uint16_t)n_new; h2.pad = hdr.pad > 0u ? hdr.pad - 1u : 0u;
             if (g.li == 0) *(NxbUnitHeader*)slab = h2;
             unsigned* g_tol = (unsigned*)(slab + p.so_tol);
             for (int v = g.li; v < N; v += G) __stcs(g_tol + v, u.newtol[v]);
@@ -834,7 +848,11 @@ struct Tier {
     size_t tp_smem = 0;
 };
 
+// what the capacities are derived from: the options of nxb_create and the event-rate sums of the current model
+struct CapCfg { double cap_scale = 1.0, rate_on = 1.0, rate_off = 1.0; int diameter = 1, max_warps = 0; double sums[3] = {0, 0, 0}; };
+
 struct nxb_handle {
+    CapCfg capcfg;
     int device = 0;
     int num_sms = 0;
     int max_smem = 0;
@@ -879,6 +897,12 @@ struct nxb_handle {
     int* d_defer_count = nullptr;
     unsigned long long* d_ctl = nullptr;           // run_split_async: work counters u64[4] | list lengths int[4]
     unsigned long long* d_defer_total = nullptr;   // units listed for a higher tier during the current chunk
+    unsigned reached = 0;                          // after NXB_ERR_STATE_CAP: the sweep count the other units have reached
+    bool need_reconfig = false;                    // the model blob changed size: tiers must be rebuilt
+    double cap_boost = 1.0;                        // doubled when a unit outgrows its slab or the largest tier
+    double cap_means[2] = {0.0, 0.0};              // expected primary / blink events per unit the capacities were sized for
+    int blink_ctas = 1;                            // co-resident blink_kernel CTAs per SM (NXB_BLINK_CTAS)
+    int smem_per_sm = 0;
     bool sync_sweeps = false;                      // NXB_SYNC_SWEEPS=1: the host-synchronised split path (one wait per sweep)
     std::vector<cudaEvent_t> evpool;
     unsigned long long* d_scratch = nullptr;
@@ -892,6 +916,7 @@ struct nxb_handle {
     float kind_ms[4] = {0.f, 0.f, 0.f, 0.f};   // of the last call: fused, primary-only, blink, check
     int kind_launches[4] = {0, 0, 0, 0};
     long long deferred_total = 0, launches_total = 0;
+    long long grown_total = 0;                     // times the capacities were doubled because a unit outgrew its slab
     std::string err;
 };
 
@@ -1094,7 +1119,16 @@ static int build_model_tables(nxb_handle* h, const nxb_model_desc* d, double sum
     std::vector<unsigned char> blob;
     {
         std::string err;
-        if (nxb_build_tol_tables(d, ml, blob, err, h->d_blob ? h->ml.pcdf_cap : 0)) { set_err(nullptr, NXB_ERR_BAD_ARG, err); return NXB_ERR_BAD_ARG; }
+        // (an update keeps the size of the Poisson table while the new rates fit it; otherwise the
+        // blob is rebuilt with a new size and the capacities are configured again)
+        bool okb = false;
+        if (h->d_blob) {
+            std::vector<unsigned char> b2;
+            NxbModelLayout ml2 = ml;
+            std::string err2;
+            if (nxb_build_tol_tables(d, ml2, b2, err2, h->ml.pcdf_cap) == 0) { ml = ml2; blob.swap(b2); okb = true; }
+        }
+        if (!okb && nxb_build_tol_tables(d, ml, blob, err, 0)) { set_err(nullptr, NXB_ERR_BAD_ARG, err); return NXB_ERR_BAD_ARG; }
     }
     auto put = [&](const void* src, int bytes, int al) {
         int o = align_up((int)blob.size(), al);
@@ -1205,8 +1239,12 @@ static int build_model_tables(nxb_handle* h, const nxb_model_desc* d, double sum
         ml.stats_words = 2 * E + P + 4 + K;
     }
     if (h->d_blob && (ml.bytes != h->ml.bytes || ml.blink_bytes != h->ml.blink_bytes)) {
-        set_err(nullptr, NXB_ERR_BAD_ARG, "model tables changed size");
-        return NXB_ERR_BAD_ARG;
+        // the tables changed size: new device blob; the shared-memory tiers depend on it
+        unsigned char* nb = nullptr;
+        CUDA_TRY_M(cudaMalloc(&nb, blob.size()));
+        cudaFree(h->d_blob);
+        h->d_blob = nb;
+        h->need_reconfig = true;
     }
     h->ml = ml;
     if (!h->d_blob) CUDA_TRY_M(cudaMalloc(&h->d_blob, blob.size()));
@@ -1268,6 +1306,212 @@ static int check_desc(const nxb_model_desc* d) {
     return NXB_OK;
 }
 
+// units that have completed fewer than `reached` sweeps (they outgrew their slab and were left behind)
+__global__ void collect_behind_kernel(const unsigned char* state, long long stride, long long n_units,
+                                      unsigned reached, int* list, int* count) {
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const NxbUnitHeader* h = (const NxbUnitHeader*)(state + u * stride);
+    if (h->sweeps_done < reached) list[atomicAdd(count, 1)] = (int)u;
+}
+
+// move the live part of every unit slab to a new slab layout (larger event capacities)
+struct ReslabArgs {
+    const unsigned char* src; unsigned char* dst;
+    long long src_stride, dst_stride, n_units;
+    int so[6], dn[6];       // tol, pri, ptm, pcode, btm, bcode offsets: old / new
+    int N;
+};
+__global__ void reslab_kernel(const ReslabArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long u = w0; u < a.n_units; u += nw) {
+        const unsigned char* s = a.src + u * a.src_stride;
+        unsigned char* d = a.dst + u * a.dst_stride;
+        const NxbUnitHeader hdr = *(const NxbUnitHeader*)s;
+        if (lane == 0) *(NxbUnitHeader*)d = hdr;
+        for (int v = lane; v < a.N; v += 32) {
+            ((unsigned*)(d + a.dn[0]))[v] = ((const unsigned*)(s + a.so[0]))[v];
+            d[a.dn[1] + v] = s[a.so[1] + v];
+        }
+        for (int i = lane; i < (int)hdr.n_pri; i += 32) {
+            ((double*)(d + a.dn[2]))[i] = ((const double*)(s + a.so[2]))[i];
+            ((unsigned*)(d + a.dn[3]))[i] = ((const unsigned*)(s + a.so[3]))[i];
+        }
+        for (int i = lane; i < (int)hdr.n_blk; i += 32) {
+            ((double*)(d + a.dn[4]))[i] = ((const double*)(s + a.so[4]))[i];
+            ((unsigned*)(d + a.dn[5]))[i] = ((const unsigned*)(s + a.so[5]))[i];
+        }
+    }
+}
+
+// Capacity tiers (shared memory), slab layout and global scratch from the expected event counts
+// of the current model; `h->cap_boost` scales every capacity (doubled when a unit outgrows its
+// slab or the largest tier).  Called by nxb_create, by nxb_update_model when the new rates need
+// more room than the handle has, and by the sweep when a unit hits a capacity: existing unit
+// states are moved to the new slab layout (reslab_kernel), so chains continue.
+static int configure_capacities(nxb_handle* h, const CapCfg& cfg) {
+    const NxbModelLayout& ml = h->ml;
+    const int N = ml.N, E = ml.E, K = ml.K;
+    const double sum_rt = cfg.sums[0], lam_pri_sum = cfg.sums[1], lam_blk_sum = cfg.sums[2];
+    // the layout the existing unit states were written with
+    const int old_off[6] = {h->so_tol, h->so_pri, h->so_ptm, h->so_pcode, h->so_btm, h->so_bcode};
+    const long long old_stride = h->stride;
+    // ---- capacity tiers ----
+    {
+        const double scale = ((cfg.cap_scale > 0.0) ? cfg.cap_scale : 1.0) * h->cap_boost;
+        const double on = cfg.rate_on, off = cfg.rate_off;
+        const double mean_blk = K * sum_rt * 2.0 * on * off / (on + off);
+        const double mean_pri = sum_rt;
+        const double cand_pri = lam_pri_sum, cand_blk = K * lam_blk_sum;
+        auto cap = [&](double mean, double nsig, double slack) {
+            return align_up((int)ceil(scale * (mean + nsig * sqrt(std::max(mean, 1.0)) + slack)), 8);
+        };
+        int capP = cap(mean_pri, 4.0, 8.0);
+        int capB = cap(mean_blk, 4.0, 2.0 * E < 32 ? 2.0 * E * K : 16.0);
+        // the initial trajectory holds up to two blink events per (track, active edge)
+        // for tracks that the data force off (raoteh.py:205-229)
+        int capF = cap(mean_pri + 0.75 * cand_pri + (double)cfg.diameter * 0, 4.0, 8.0);
+        int capR = cap(mean_pri + cand_pri, 4.0, 8.0) + capP;
+        int capC = cap(mean_blk + cand_blk, 4.0, 16.0);
+        h->gcapP = std::max(h->gcapP, std::min(65535, align_up(4 * capP + 32, 8)));      // (slabs never shrink)
+        h->gcapB = std::max(h->gcapB, std::min(65535, align_up(4 * capB + 64, 8)));
+        h->tiers.clear(); h->init_tiers.clear();
+        const int stats_bytes = align_up(8 * (ml.stats_words + 16), 16);   // + lockstep batch slots
+        const int fixed = ml.bytes + stats_bytes;
+        const int max_warps = (cfg.max_warps > 0) ? std::min(cfg.max_warps, NXB_MAX_THREADS / 32)
+                                                 : NXB_MAX_THREADS / 32;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int t = 0; t < 8; ++t) {
+                Tier tier;
+                const int f = 1 << t;
+                int cP = capP * f, cB = capB * f, cR = capR * f, cF = capF * f, cC = capC * f;
+                if (pass == 1) {
+                    // init pass: `diameter` forced events on every edge, all of which may
+                    // survive; up to two blink events per (track, edge)
+                    cF = std::max(cF, E * cfg.diameter + 8);
+                    cR = std::max(cR, E * cfg.diameter + 8);
+                    cP = std::max(cP, std::min(E * cfg.diameter + 8, 4 * capP + 32));
+                }
+                build_warp_layout(ml, h->msg_f64, std::min(cP, h->gcapP), std::min(cB, h->gcapB),
+                                  cR, cF, cC, &tier.wl);
+                tier.smem_warp0 = fixed;
+                int w = (h->max_smem - fixed) / tier.wl.bytes;
+                if (w < 1) break;
+                tier.warps = std::min(w, max_warps);
+                tier.smem = (size_t)fixed + (size_t)tier.warps * tier.wl.bytes;
+                if (pass == 0 && t == 0) {
+                    build_blink_layout(ml, h->msg_f64, tier.wl.capP, tier.wl.capB, &tier.bwl);
+                    const int bfixed = ml.blink_bytes + stats_bytes;      // model prefix + statistic partials
+                    tier.blink_warp0 = bfixed;
+                    // NXB_BLINK_CTAS=2: two co-resident CTAs per SM, each with half of the shared memory, so
+                    // that one CTA's load / set-up / write-back overlaps the other's walks
+                    int smem_budget = h->max_smem;
+                    if (h->blink_ctas > 1) smem_budget = std::min(h->max_smem, h->smem_per_sm / h->blink_ctas - 1024);
+                    const int fit = (smem_budget - bfixed) / tier.bwl.bytes;
+                    int bw = (cfg.max_warps > 0) ? std::min(cfg.max_warps, NXB_BLINK_THREADS / 32)
+                                                : NXB_BLINK_THREADS / 32;
+                    if (const char* ev = getenv("NXB_BLINK_WARPS")) bw = std::max(1, std::min(atoi(ev), NXB_BLINK_THREADS / 32));
+                    // one (unit, track) job per lane of the CTA
+                    int bu = std::min(fit, (32 * bw) / K);
+                    // prefer a batch whose jobs fill whole warps (p53: 32 units x 20 tracks = 20 warps;
+                    // measured 14.9 M unit-sweeps/s against 14.1-14.6 M with 21-23 ragged warps)
+                    for (int cand = bu; cand >= 1 && 4 * cand >= 3 * bu; --cand)
+                        if ((cand * K) % 32 == 0) { bu = cand; break; }
+                    if (bu >= 1) {
+                        tier.blink_units = bu;
+                        tier.blink_warps = std::min(bw, (bu * K + 31) / 32);
+                        tier.blink_smem = (size_t)bfixed + (size_t)bu * tier.bwl.bytes;
+                    }
+                }
+                if (pass == 0 && h->tolpar) {
+                    // candidates of one sweep (all tracks) and live events (accepted candidates + retained):
+                    // the acceptance probability is that of the stationary mix of ON and OFF
+                    const double Mx = std::max(on, off);
+                    const double acc_mean = (off / (on + off)) * (2.0 * Mx - on) / (2.0 * Mx)
+                                          + (on / (on + off)) * (2.0 * Mx - off) / (2.0 * Mx);
+                    const int capQ0 = cap(cand_blk, 3.5, 16.0);
+                    const int capL0 = cap(mean_blk + acc_mean * cand_blk, 3.5, 16.0);
+                    const int cQ = std::min(65528, capQ0 * f), cL = std::min(65528, capL0 * f);
+                    build_tol_layout(ml, h->msg_f64, tier.wl.capP, tier.wl.capB, cQ, cL, &tier.tl);
+                    const int bfixed = ml.blink_bytes + stats_bytes;
+                    tier.tp_warp0 = bfixed;
+                    const int fit = (h->max_smem - bfixed) / tier.tl.bytes;
+                    int wpu = (cand_blk + mean_blk >= 128.0) ? 2 : 1;
+                    if (const char* ev = getenv("NXB_TP_WPU")) wpu = atoi(ev) == 2 ? 2 : 1;
+                    int maxw = NXB_TP_THREADS / 32;
+                    if (cfg.max_warps > 0) maxw = std::max(wpu, std::min(maxw, cfg.max_warps));
+                    int nu = std::min(fit, maxw / wpu);
+                    if (wpu == 2) nu = std::min(nu, 15);          // one named barrier per unit group
+                    if (nu >= 1) {
+                        tier.tp_units = nu; tier.tp_wpu = wpu;
+                        tier.tp_smem = (size_t)bfixed + (size_t)nu * tier.tl.bytes;
+                    }
+                }
+                (pass == 0 ? h->tiers : h->init_tiers).push_back(tier);
+            }
+        }
+        if (h->tiers.empty() || h->init_tiers.empty()) {
+            set_err(nullptr, NXB_ERR_BAD_ARG, "model too large: one unit does not fit in shared memory");
+            return NXB_ERR_BAD_ARG;
+        }
+        // global scratch per warp slot: chunk messages + candidate pool
+        {
+            int max_w = 1;
+            for (auto& t : h->tiers) max_w = std::max(max_w, t.warps);
+            for (auto& t : h->init_tiers) max_w = std::max(max_w, t.warps);
+            max_w = std::max(max_w, h->tiers[0].blink_units * h->blink_ctas);
+            h->gcapF = std::max(8 * capF, E * cfg.diameter + 8);
+            // live events per track and sweep: retained + accepted candidates
+            {
+                const double per_track = (mean_blk + cand_blk) / K;
+                h->gcapC = std::min(32760, align_up((int)(4.0 * per_track + 10.0 * sqrt(per_track + 1.0) + 64.0), 8));
+            }
+            int o = 0;
+            h->g_off_msg = o; o += (h->msg_f64 ? 8 : 4) * (h->gcapF + 1) * NXB_PPAD;
+            o = align_up(o, 16);
+            h->g_off_ctm = o; o += (h->msg_f64 ? 32 : 16) * h->gcapC * K;      // one region per track, 16 B (f32) / 32 B (f64) records
+            h->gscratch_stride = align_up(o, 256);
+            if (h->d_gscratch) { cudaFree(h->d_gscratch); h->d_gscratch = nullptr; }
+            cudaError_t e1 = cudaMalloc(&h->d_gscratch, (size_t)h->gscratch_stride * max_w * h->num_sms);
+            if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); return NXB_ERR_CUDA; }
+        }
+        // slab layout
+        int o = (int)sizeof(NxbUnitHeader);
+        h->so_tol = o; o += 4 * N;
+        h->so_pri = o; o += align_up(N, 4);
+        o = align_up(o, 8);
+        h->so_ptm = o; o += 8 * h->gcapP;
+        h->so_pcode = o; o += 4 * h->gcapP;
+        o = align_up(o, 8);
+        h->so_btm = o; o += 8 * h->gcapB;
+        h->so_bcode = o; o += 4 * h->gcapB;
+        h->stride = align_up(o, 16);
+    }
+    h->cap_means[0] = sum_rt; h->cap_means[1] = K * sum_rt * 2.0 * cfg.rate_on * cfg.rate_off / (cfg.rate_on + cfg.rate_off);
+    if (h->d_state && h->n_units > 0 && old_stride > 0) {
+        const int new_off[6] = {h->so_tol, h->so_pri, h->so_ptm, h->so_pcode, h->so_btm, h->so_bcode};
+        bool same = old_stride == h->stride;
+        for (int i = 0; i < 6; ++i) same = same && old_off[i] == new_off[i];
+        if (!same) {
+            unsigned char* ns = nullptr;
+            cudaError_t e1 = cudaMalloc(&ns, (size_t)h->n_units * h->stride);
+            if (e1 != cudaSuccess) { set_err(h, NXB_ERR_CUDA, cudaGetErrorString(e1)); return NXB_ERR_CUDA; }
+            ReslabArgs ra;
+            ra.src = h->d_state; ra.dst = ns; ra.src_stride = old_stride; ra.dst_stride = h->stride;
+            for (int i = 0; i < 6; ++i) { ra.so[i] = old_off[i]; ra.dn[i] = new_off[i]; }
+            ra.N = N; ra.n_units = h->n_units;
+            reslab_kernel<<<(unsigned)std::min<long long>((h->n_units + 7) / 8, 148LL * 32), 256, 0, h->stream>>>(ra);
+            e1 = cudaStreamSynchronize(h->stream);
+            if (e1 != cudaSuccess) { cudaFree(ns); set_err(h, NXB_ERR_CUDA, cudaGetErrorString(e1)); return NXB_ERR_CUDA; }
+            cudaFree(h->d_state);
+            h->d_state = ns;
+        }
+    }
+    return NXB_OK;
+}
+
 extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out) {
     if (!d || !out) return set_err(nullptr, NXB_ERR_BAD_ARG, "null argument");
     *out = nullptr;
@@ -1303,6 +1547,8 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     CUDA_TRY_C(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    if (const char* ev = getenv("NXB_BLINK_CTAS")) h->blink_ctas = std::max(1, std::min(4, atoi(ev)));
     CUDA_TRY_C(cudaStreamCreate(&h->own_stream));
     h->stream = h->own_stream;
     CUDA_TRY_C(cudaEventCreate(&h->ev0));
@@ -1350,130 +1596,13 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     CUDA_TRY_C(cudaMalloc(&h->d_perf, 32 * 8));
     CUDA_TRY_C(cudaMemset(h->d_perf, 0, 32 * 8));
 
-    // ---- capacity tiers ----
+    // ---- capacity tiers, slab layout, global scratch ----
+    h->capcfg.cap_scale = d->cap_scale; h->capcfg.rate_on = d->rate_on; h->capcfg.rate_off = d->rate_off;
+    h->capcfg.diameter = d->diameter; h->capcfg.max_warps = d->max_warps;
+    h->capcfg.sums[0] = sum_rt; h->capcfg.sums[1] = lam_pri_sum; h->capcfg.sums[2] = lam_blk_sum;
     {
-        const double scale = (d->cap_scale > 0.0) ? d->cap_scale : 1.0;
-        const double on = d->rate_on, off = d->rate_off;
-        const double mean_blk = K * sum_rt * 2.0 * on * off / (on + off);
-        const double mean_pri = sum_rt;
-        const double cand_pri = lam_pri_sum, cand_blk = K * lam_blk_sum;
-        auto cap = [&](double mean, double nsig, double slack) {
-            return align_up((int)ceil(scale * (mean + nsig * sqrt(std::max(mean, 1.0)) + slack)), 8);
-        };
-        int capP = cap(mean_pri, 4.0, 8.0);
-        int capB = cap(mean_blk, 4.0, 2.0 * E < 32 ? 2.0 * E * K : 16.0);
-        // the initial trajectory holds up to two blink events per (track, active edge)
-        // for tracks that the data force off (raoteh.py:205-229)
-        int capF = cap(mean_pri + 0.75 * cand_pri + (double)d->diameter * 0, 4.0, 8.0);
-        int capR = cap(mean_pri + cand_pri, 4.0, 8.0) + capP;
-        int capC = cap(mean_blk + cand_blk, 4.0, 16.0);
-        h->gcapP = std::min(65535, align_up(4 * capP + 32, 8));
-        h->gcapB = std::min(65535, align_up(4 * capB + 64, 8));
-        const int stats_bytes = align_up(8 * (ml.stats_words + 16), 16);   // + lockstep batch slots
-        const int fixed = ml.bytes + stats_bytes;
-        const int max_warps = (d->max_warps > 0) ? std::min(d->max_warps, NXB_MAX_THREADS / 32)
-                                                 : NXB_MAX_THREADS / 32;
-        for (int pass = 0; pass < 2; ++pass) {
-            for (int t = 0; t < 8; ++t) {
-                Tier tier;
-                const int f = 1 << t;
-                int cP = capP * f, cB = capB * f, cR = capR * f, cF = capF * f, cC = capC * f;
-                if (pass == 1) {
-                    // init pass: `diameter` forced events on every edge, all of which may
-                    // survive; up to two blink events per (track, edge)
-                    cF = std::max(cF, E * d->diameter + 8);
-                    cR = std::max(cR, E * d->diameter + 8);
-                    cP = std::max(cP, std::min(E * d->diameter + 8, 4 * capP + 32));
-                }
-                build_warp_layout(ml, h->msg_f64, std::min(cP, h->gcapP), std::min(cB, h->gcapB),
-                                  cR, cF, cC, &tier.wl);
-                tier.smem_warp0 = fixed;
-                int w = (h->max_smem - fixed) / tier.wl.bytes;
-                if (w < 1) break;
-                tier.warps = std::min(w, max_warps);
-                tier.smem = (size_t)fixed + (size_t)tier.warps * tier.wl.bytes;
-                if (pass == 0 && t == 0) {
-                    build_blink_layout(ml, h->msg_f64, tier.wl.capP, tier.wl.capB, &tier.bwl);
-                    const int bfixed = ml.blink_bytes + stats_bytes;      // model prefix + statistic partials
-                    tier.blink_warp0 = bfixed;
-                    const int fit = (h->max_smem - bfixed) / tier.bwl.bytes;
-                    int bw = (d->max_warps > 0) ? std::min(d->max_warps, NXB_BLINK_THREADS / 32)
-                                                : NXB_BLINK_THREADS / 32;
-                    if (const char* ev = getenv("NXB_BLINK_WARPS")) bw = std::max(1, std::min(atoi(ev), NXB_BLINK_THREADS / 32));
-                    // one (unit, track) job per lane of the CTA
-                    int bu = std::min(fit, (32 * bw) / K);
-                    // prefer a batch whose jobs fill whole warps (p53: 32 units x 20 tracks = 20 warps;
-                    // measured 14.9 M unit-sweeps/s against 14.1-14.6 M with 21-23 ragged warps)
-                    for (int cand = bu; cand >= 1 && 4 * cand >= 3 * bu; --cand)
-                        if ((cand * K) % 32 == 0) { bu = cand; break; }
-                    if (bu >= 1) {
-                        tier.blink_units = bu;
-                        tier.blink_warps = std::min(bw, (bu * K + 31) / 32);
-                        tier.blink_smem = (size_t)bfixed + (size_t)bu * tier.bwl.bytes;
-                    }
-                }
-                if (pass == 0 && h->tolpar) {
-                    // candidates of one sweep (all tracks) and live events (accepted candidates + retained):
-                    // the acceptance probability is that of the stationary mix of ON and OFF
-                    const double Mx = std::max(on, off);
-                    const double acc_mean = (off / (on + off)) * (2.0 * Mx - on) / (2.0 * Mx)
-                                          + (on / (on + off)) * (2.0 * Mx - off) / (2.0 * Mx);
-                    const int capQ0 = cap(cand_blk, 3.5, 16.0);
-                    const int capL0 = cap(mean_blk + acc_mean * cand_blk, 3.5, 16.0);
-                    const int cQ = std::min(65528, capQ0 * f), cL = std::min(65528, capL0 * f);
-                    build_tol_layout(ml, h->msg_f64, tier.wl.capP, tier.wl.capB, cQ, cL, &tier.tl);
-                    const int bfixed = ml.blink_bytes + stats_bytes;
-                    tier.tp_warp0 = bfixed;
-                    const int fit = (h->max_smem - bfixed) / tier.tl.bytes;
-                    int wpu = (cand_blk + mean_blk >= 128.0) ? 2 : 1;
-                    if (const char* ev = getenv("NXB_TP_WPU")) wpu = atoi(ev) == 2 ? 2 : 1;
-                    int maxw = NXB_TP_THREADS / 32;
-                    if (d->max_warps > 0) maxw = std::max(wpu, std::min(maxw, d->max_warps));
-                    int nu = std::min(fit, maxw / wpu);
-                    if (wpu == 2) nu = std::min(nu, 15);          // one named barrier per unit group
-                    if (nu >= 1) {
-                        tier.tp_units = nu; tier.tp_wpu = wpu;
-                        tier.tp_smem = (size_t)bfixed + (size_t)nu * tier.tl.bytes;
-                    }
-                }
-                (pass == 0 ? h->tiers : h->init_tiers).push_back(tier);
-            }
-        }
-        if (h->tiers.empty() || h->init_tiers.empty()) {
-            set_err(nullptr, NXB_ERR_BAD_ARG, "model too large: one unit does not fit in shared memory");
-            nxb_destroy(h); return NXB_ERR_BAD_ARG;
-        }
-        // global scratch per warp slot: chunk messages + candidate pool
-        {
-            int max_w = 1;
-            for (auto& t : h->tiers) max_w = std::max(max_w, t.warps);
-            for (auto& t : h->init_tiers) max_w = std::max(max_w, t.warps);
-            max_w = std::max(max_w, h->tiers[0].blink_units);
-            h->gcapF = std::max(8 * capF, E * d->diameter + 8);
-            // live events per track and sweep: retained + accepted candidates
-            {
-                const double per_track = (mean_blk + cand_blk) / K;
-                h->gcapC = std::min(32760, align_up((int)(4.0 * per_track + 10.0 * sqrt(per_track + 1.0) + 64.0), 8));
-            }
-            int o = 0;
-            h->g_off_msg = o; o += (h->msg_f64 ? 8 : 4) * (h->gcapF + 1) * NXB_PPAD;
-            o = align_up(o, 16);
-            h->g_off_ctm = o; o += (h->msg_f64 ? 32 : 16) * h->gcapC * K;      // one region per track, 16 B (f32) / 32 B (f64) records
-            h->gscratch_stride = align_up(o, 256);
-            cudaError_t e1 = cudaMalloc(&h->d_gscratch, (size_t)h->gscratch_stride * max_w * h->num_sms);
-            if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }
-        }
-        // slab layout
-        int o = (int)sizeof(NxbUnitHeader);
-        h->so_tol = o; o += 4 * N;
-        h->so_pri = o; o += align_up(N, 4);
-        o = align_up(o, 8);
-        h->so_ptm = o; o += 8 * h->gcapP;
-        h->so_pcode = o; o += 4 * h->gcapP;
-        o = align_up(o, 8);
-        h->so_btm = o; o += 8 * h->gcapB;
-        h->so_bcode = o; o += 4 * h->gcapB;
-        h->stride = align_up(o, 16);
+        int rc = configure_capacities(h, h->capcfg);
+        if (rc) { nxb_destroy(h); return rc; }
     }
     {
         cudaError_t e1 = h->msg_f64
@@ -1523,6 +1652,21 @@ extern "C" int nxb_update_model(nxb_handle* h, const nxb_model_desc* d) {
     double sums[3];
     int rc = build_model_tables(h, d, sums);
     if (rc) { h->err = g_create_err; return rc; }
+    // Capacities follow the model: when the new rates mean more events per unit than the
+    // shared-memory tiers and slabs were sized for (or far fewer), they are derived again and the
+    // unit states move to the new slab layout; chains continue.
+    {
+        h->capcfg.rate_on = d->rate_on; h->capcfg.rate_off = d->rate_off;
+        for (int i = 0; i < 3; ++i) h->capcfg.sums[i] = sums[i];
+        const double mp = sums[0], mb = ml.K * sums[0] * 2.0 * d->rate_on * d->rate_off / (d->rate_on + d->rate_off);
+        const bool grew = mp > 1.1 * h->cap_means[0] + 1.0 || mb > 1.1 * h->cap_means[1] + 1.0;
+        const bool shrank = mp < 0.5 * h->cap_means[0] - 1.0 || mb < 0.5 * h->cap_means[1] - 1.0;
+        if (h->need_reconfig || grew || shrank) {
+            h->need_reconfig = false;
+            rc = configure_capacities(h, h->capcfg);
+            if (rc) return rc;
+        }
+    }
     // Trajectories stay valid under new rates unless an edge switched between active and
     // inactive (events on a zero-rate edge); then the chains have to be initialised again.
     bool same_active = true;
@@ -1654,7 +1798,7 @@ static cudaError_t enqueue_kernel(nxb_handle* h, int kind, const Tier& tier, con
             else tolpar_kernel<float, 1><<<grid, threads, tier.tp_smem, h->stream>>>(p);
         }
     } else if (kind == KIND_BLINK) {
-        int grid = (int)std::min<long long>(h->num_sms, (n_work + tier.blink_units - 1) / tier.blink_units);
+        int grid = (int)std::min<long long>((long long)h->num_sms * h->blink_ctas, (n_work + tier.blink_units - 1) / tier.blink_units);
         if (h->msg_f64) blink_kernel<double><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
         else blink_kernel<float><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
     } else {
@@ -1750,6 +1894,7 @@ static int run_split(nxb_handle* h, unsigned target, unsigned accum_from) {
         int rc = launch_one(h, KIND_PRIMARY, t0, gw, nullptr, 0, h->d_defer[0], false, h->sweeps, h->sweeps + 1,
                             accum_from, 0, &nd, true);
         if (rc) return rc;
+        h->reached = h->sweeps + 1;
         rc = launch_one(h, KIND_BLINK, t0, 1, nullptr, 0, h->d_defer[0], true, h->sweeps, h->sweeps + 1,
                         accum_from, 0, &nd);
         if (rc) return rc;
@@ -1859,6 +2004,7 @@ static int run_split_async(nxb_handle* h, unsigned target, unsigned accum_from) 
             snprintf(buf, sizeof(buf), "%s (code %d, unit %d, detail %d, sweep %d)", status_text(hs.status[0]),
                      hs.status[0], hs.status[1], hs.status[2], hs.status[3]);
             cudaMemsetAsync(h->d_status, 0, 16, h->stream);
+            h->reached = h->sweeps + (unsigned)nsw;        // where the units that did fit are now
             return set_err(h, hs.status[0], buf);
         }
         h->deferred_total += (long long)hs.total;
@@ -1890,7 +2036,55 @@ extern "C" int nxb_init_chains(nxb_handle* h, int32_t chains, uint64_t seed, int
     h->sweeps = 0;
     h->last_ms = 0.f; h->last_launches = 0;
     for (int i = 0; i < 4; ++i) { h->kind_ms[i] = 0.f; h->kind_launches[i] = 0; }
-    return run_tiers(h, 0u, 0xffffffffu, 1);
+    int rc = run_tiers(h, 0u, 0xffffffffu, 1);
+    for (int attempt = 0; rc == NXB_ERR_STATE_CAP && attempt < 6; ++attempt) {
+        // an initial trajectory does not fit the slab: larger slabs, draw all of them again
+        cudaFree(h->d_state); h->d_state = nullptr;
+        h->cap_boost *= 2.0;
+        h->grown_total++;
+        rc = configure_capacities(h, h->capcfg);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaMalloc(&h->d_state, (size_t)n_units * h->stride));
+        rc = run_tiers(h, 0u, 0xffffffffu, 1);
+    }
+    return rc;
+}
+
+static int sweep_to(nxb_handle* h, unsigned target, unsigned accum_from) {
+    if (h->sweeps >= target) return NXB_OK;
+    if (h->split && !h->tolpar && !h->validate && !h->sync_sweeps && h->tiers[0].blink_units > 0) return run_split_async(h, target, accum_from);
+    if (h->split && (h->tiers[0].blink_units > 0 || (h->tolpar && h->tiers[0].tp_units > 0))) return run_split(h, target, accum_from);
+    h->reached = target;
+    int rc = run_tiers(h, target, accum_from, 0);
+    if (rc == NXB_OK) h->sweeps = target;
+    return rc;
+}
+
+// A unit outgrew its HBM slab (NXB_ERR_STATE_CAP): double every capacity, move the unit states to
+// the larger slabs, and run the units that were left behind up to the sweep count the others have
+// reached.  Their random streams depend only on (seed, unit, sweep), and the statistics that the
+// failed attempt had already booked are skipped (NxbUnitHeader::pad), so the result is what slabs
+// that were large enough from the start would have given.
+static int recover_state_cap(nxb_handle* h, unsigned accum_from) {
+    const unsigned reached = h->reached;
+    h->cap_boost *= 2.0;
+    int rc = configure_capacities(h, h->capcfg);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_defer_count, 0, 4, h->stream));
+    collect_behind_kernel<<<(unsigned)((h->n_units + 255) / 256), 256, 0, h->stream>>>(
+        h->d_state, h->stride, h->n_units, reached, h->d_defer[0], h->d_defer_count);
+    int n = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&n, h->d_defer_count, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->grown_total++;
+    if (n > 0) {
+        h->reached = reached;
+        if (h->tiers.size() < 2) return set_err(h, NXB_ERR_SCRATCH_CAP, status_text(NXB_ERR_SCRATCH_CAP));
+        rc = run_tiers(h, reached, accum_from, 0, 1, h->d_defer[0], n);
+        if (rc) return rc;
+    }
+    h->sweeps = reached;
+    return NXB_OK;
 }
 
 extern "C" int nxb_sweep(nxb_handle* h, int32_t n_sweeps, int32_t accumulate) {
@@ -1901,10 +2095,11 @@ extern "C" int nxb_sweep(nxb_handle* h, int32_t n_sweeps, int32_t accumulate) {
     const unsigned accum_from = accumulate ? h->sweeps : 0xffffffffu;
     h->last_ms = 0.f; h->last_launches = 0;
     for (int i = 0; i < 4; ++i) { h->kind_ms[i] = 0.f; h->kind_launches[i] = 0; }
-    if (h->split && !h->tolpar && !h->validate && !h->sync_sweeps && h->tiers[0].blink_units > 0) return run_split_async(h, target, accum_from);
-    if (h->split && (h->tiers[0].blink_units > 0 || (h->tolpar && h->tiers[0].tp_units > 0))) return run_split(h, target, accum_from);
-    int rc = run_tiers(h, target, accum_from, 0);
-    if (rc == NXB_OK) h->sweeps = target;
+    int rc = sweep_to(h, target, accum_from);
+    for (int attempt = 0; rc == NXB_ERR_STATE_CAP && attempt < 6; ++attempt) {
+        rc = recover_state_cap(h, accum_from);
+        if (rc == NXB_OK) rc = sweep_to(h, target, accum_from);
+    }
     return rc;
 }
 
@@ -2108,6 +2303,7 @@ extern "C" int nxb_get_stats(nxb_handle* h, nxb_stats* o) {
     o->n_tiers = (int32_t)h->tiers.size();
     o->capP = t0.wl.capP; o->capB = t0.wl.capB; o->capF = t0.wl.capF; o->capC = t0.wl.capC;
     o->deferred_units = h->deferred_total; o->kernel_launches = h->launches_total;
+    o->capacity_doublings = h->grown_total;
     return NXB_OK;
 }
 

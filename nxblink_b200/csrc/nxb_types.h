@@ -36,7 +36,8 @@ struct NxbUnitHeader {
     uint16_t n_pri;         // retained primary events
     uint16_t n_blk;         // retained blink events
     uint32_t phase;         // NXB_PHASE_*: PRIMARY = at a sweep boundary
-    uint32_t pad;
+    uint32_t pad;           // number of phases from this state on whose statistics are ALREADY booked (a unit that
+                            // outgrew its slab is run again after the slabs have grown; see nxb_sweep); normally 0
 };
 
 // Offsets (bytes) of the model tables inside the model blob that every CTA

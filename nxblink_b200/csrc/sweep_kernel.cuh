@@ -38,7 +38,8 @@
 
 namespace nxb {
 
-enum { RC_OK = 0, RC_DEFER = 1, RC_ERROR = 2 };
+enum { RC_OK = 0, RC_DEFER = 1, RC_ERROR = 2,
+       RC_STATECAP = 3 };   // the new blink list does not fit the unit's HBM slab; the statistics of the update ARE booked
 
 __constant__ double c_inv_n[64];
 
@@ -796,7 +797,7 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         // The sweep is complete and its statistics are booked; only the shared-memory
         // arrays are too small.  Spill the new blink list straight to the HBM slab and
         // let the next capacity tier pick the unit up at the next sweep boundary.
-        if (total > p.gcapB) { fail(c, NXB_ERR_STATE_CAP, total); return RC_ERROR; }
+        if (total > p.gcapB) { fail(c, NXB_ERR_STATE_CAP, total); return RC_STATECAP; }
         unsigned char* slab = p.state + c.unit * p.state_stride;
         obtm = (double*)(slab + p.so_btm);
         obcode = (unsigned*)(slab + p.so_bcode);

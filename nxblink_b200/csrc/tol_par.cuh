@@ -656,7 +656,7 @@ NXB_DEV int tolpar_update(const TpCtx& c, TpUnit<MSG>& u, const TpGroup<WPU>& g,
             // root draw (prior: toymodel.py:17-27 get_blink_distn)
             MSG a0 = 1, a1 = 1; double apen = 0.0;
             if (inited & (1u << c.slot[0])) { const AccRec<MSG> a = u.acc[c.slot[0] * K + k]; a0 = a.u0; a1 = a.u1; apen = a.pen; }
-            double w1 = (double)a1 * (a0 != (MSG)0 ? exp(-apen) : 1.0) * ml.p_on;
+            double w1 = (double)a1 * (a0 != (MSG)0 ? fmax(exp(-apen), 2.2250738585072014e-308) : 1.0) * ml.p_on;
             double w0 = (double)a0 * ml.p_off;
             if (!(((unsigned)u.x[8] >> k) & 1u)) w1 = 0.0;
             if (!(((unsigned)u.x[9] >> k) & 1u)) w0 = 0.0;

@@ -48,7 +48,11 @@ NXB_DEV void nxb_ev_pad(LiveEv<double>& e) { e.pad2 = 0u; e.pad3 = 0.0; }
 
 template <typename MSG> struct TolMath;
 template <> struct TolMath<float> {
-    static NXB_DEV float expneg(double pen) { return nxb_fast_expf((float)(-pen)); }
+    // exp(-pen), never exactly 0: zeros in a message are HARD constraints (data, own class); a
+    // penalty beyond the f32 range (exponent > 87) must not create one, or a unit whose OFF state is
+    // excluded by data would turn infeasible.  Messages are rescaled by powers of two at every fold,
+    // so the smallest normal number is as good as the true 1e-40.
+    static NXB_DEV float expneg(double pen) { return fmaxf(nxb_fast_expf((float)(-pen)), 1.17549435e-38f); }
     static NXB_DEV float div(float a, float b) { return nxb_fast_divf(a, b); }
     // 2^-(floor(log2 m) + 1) for a positive finite m: exact power-of-two rescaling into [0.5, 1)
     // without a division; preserves exact zeros of the other component.
@@ -58,7 +62,7 @@ template <> struct TolMath<float> {
     static NXB_DEV float uniform(NxbXo& xo) { return (float)(nxb_xo_next(xo) >> 8) * (1.0f / 16777216.0f); }
 };
 template <> struct TolMath<double> {
-    static NXB_DEV double expneg(double pen) { return exp(-pen); }
+    static NXB_DEV double expneg(double pen) { return fmax(exp(-pen), 2.2250738585072014e-308); }
     static NXB_DEV double div(double a, double b) { return a / b; }
     static NXB_DEV double pow2_rescale(double m) {
         return nxb_ll_as_double((0x7fdLL << 52) - (nxb_double_as_ll(m) & (0x7ffLL << 52)));
@@ -319,7 +323,7 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
     unsigned x = 0u;
     if (trk) {
         const AccRec<MSG> a = u.acc[c.slot[0] * K + k];
-        double w1 = (double)a.u1 * (a.u0 != (MSG)0 ? exp(-a.pen) : 1.0) * ml.p_on;
+        double w1 = (double)a.u1 * (a.u0 != (MSG)0 ? fmax(exp(-a.pen), 2.2250738585072014e-308) : 1.0) * ml.p_on;
         double w0 = (double)a.u0 * ml.p_off;
         if (!(((unsigned)u.uhdr[8] >> k) & 1u)) w1 = 0.0;
         if (!(((unsigned)u.uhdr[9] >> k) & 1u)) w0 = 0.0;

@@ -152,3 +152,67 @@ def test_event_parallel_kernel_geometry_invariance(nb, monkeypatch):
     for other in (small, few, one, (a[0] + b[0], a[1] + b[1], None)):
         assert (base[0] == other[0]).all()
         np.testing.assert_allclose(base[1], other[1], rtol=1e-11, atol=1e-9)
+
+
+@pytest.mark.parametrize('kw', [{}, {'split_phases': -1}, {'validate': True}], ids=['split', 'fused', 'validated'])
+@pytest.mark.parametrize('cap_scale', [0.06, 0.02])
+def test_slab_overflow_grows_the_slabs_and_continues_exactly(nb, cap_scale, kw):
+    """HBM slabs far too small for the trajectories: while the chains move from their initial
+    trajectories to the stationary event load, units outgrow their slabs (once at cap_scale 0.06,
+    three times at 0.02).  The engine doubles every capacity, moves the unit states to the larger
+    slabs and runs the units that were left behind again from where they stood, skipping the
+    statistics the failed attempt had booked -- here the statistics are accumulated from the very
+    first sweep, so that path is exercised.  The result is bit-identical (integers) to the run
+    whose slabs were large enough from the start."""
+    pm, data = _p53_inputs(24)
+
+    def run(**opts):
+        s = nb.BlinkSampler(pm, **opts)
+        s.set_data(data)
+        s.init_chains(chains=8, seed=5)
+        d0 = s.stats()['capacity_doublings']
+        s.sweep(9, accumulate=True)
+        c, d = s.read_summary()
+        st = s.stats()
+        s.close()
+        return c, d, st, d0
+    base = run()
+    assert base[2]['capacity_doublings'] == 0
+    tiny = run(cap_scale=cap_scale, **kw)
+    assert tiny[2]['capacity_doublings'] > tiny[3]          # grown during the accumulating sweeps
+    assert (base[0] == tiny[0]).all()
+    np.testing.assert_allclose(base[1], tiny[1], rtol=1e-11, atol=1e-9)
+    assert base[2]['n_blk_events'] == tiny[2]['n_blk_events']
+    assert base[2]['n_pri_events'] == tiny[2]['n_pri_events']
+
+
+def test_update_model_with_much_higher_rates_resizes_the_handle(nb):
+    """An EM step may multiply the rates (run-stochastic.py:154-208 builds a new model per
+    iteration): nxb_update_model derives the capacities again, so the handle created for the slow
+    model gives exactly what a handle created for the fast model gives."""
+    m = p53.p53_model()
+    pm = packing.PackedModel(m)
+    prm = p53.jeff_params()
+    fast_rates = dict((e, 5.0 * r) for e, r in m.get_edge_to_rate().items())
+    m5 = p53.Model(prm['kappa'], prm['omega'], prm['A'], prm['C'], prm['G'], prm['T'], 3.0, 1.0,
+            m._tree, m._root, m.get_edge_to_blen(), fast_rates, m.genetic_code)
+    pm5 = packing.PackedModel(m5)
+    _, data = _p53_inputs(8)
+
+    def run(s):
+        s.set_data(data)
+        s.init_chains(chains=4, seed=21)
+        s.sweep(2, accumulate=False)
+        s.reset_summary()
+        s.sweep(3, accumulate=True)
+        return s.read_summary()
+    fresh = nb.BlinkSampler(pm5)
+    c0, d0 = run(fresh)
+    fresh.close()
+    s = nb.BlinkSampler(pm)
+    run(s)
+    s.update_model(pm5)
+    c1, d1 = run(s)
+    assert (c0 == c1).all()
+    np.testing.assert_allclose(d0, d1, rtol=1e-11, atol=1e-9)
+    s.close()

@@ -139,3 +139,41 @@ def test_f32_and_f64_messages_agree_p53_shape(nb):
     lim = 5 * se + 1e-3 * np.maximum(1.0, np.abs(a.mean(axis=0)))
     bad = np.abs(a.mean(axis=0) - b.mean(axis=0)) > lim
     assert not bad.any(), (np.argwhere(bad), a.mean(axis=0)[bad], b.mean(axis=0)[bad], se[bad])
+
+
+def test_large_penalty_exponents_do_not_make_f32_infeasible(nb):
+    """Toy model B with every edge rate x100 and slow blinking (on 0.02, off 0.005): few blink
+    events per edge, so the penalty exponent rate * Q_meta * dt between two live events reaches
+    ~100, beyond the f32 range of exp().  A penalty factor must never turn into a hard zero
+    (chunking.py:32-36 computes exp(-x) in f64, which is tiny but positive): the f32 path clamps it
+    to the smallest normal number, so data that exclude OFF stay feasible.  f32 and f64 statistics
+    agree within Monte Carlo error."""
+    class Fast(toymodel.BlinkModelB):
+        @classmethod
+        def get_edge_to_rate(cls):
+            return dict((e, 100.0 * r) for e, r in toymodel.BlinkModelB.get_edge_to_rate().items())
+
+        @classmethod
+        def get_rate_on(cls):
+            return 0.02
+
+        @classmethod
+        def get_rate_off(cls):
+            return 0.005
+    res = {}
+    for f64 in (False, True):
+        mats = []
+        for seed in range(4):
+            with _env(False):
+                s = nb.BlinkSampler(Fast, validate=True, msg_f64=f64)
+            s.set_data([toydata.DataC, toydata.DataD])
+            s.init_chains(chains=512, seed=70 + seed)
+            s.sweep(30, accumulate=False)           # raises NxbError on an infeasible unit
+            s.sweep(30, accumulate=True)
+            mats.append(_edge_matrix(s.summary()))
+            s.close()
+        res[f64] = np.array(mats)
+    a, b = res[False], res[True]
+    se = np.hypot(a.std(axis=0, ddof=1), b.std(axis=0, ddof=1)) / np.sqrt(a.shape[0])
+    lim = 5 * se + 2e-3 * np.maximum(1.0, np.abs(a.mean(axis=0)))
+    assert (np.abs(a.mean(axis=0) - b.mean(axis=0)) <= lim).all()
