@@ -100,3 +100,21 @@ class ShardedSampler(object):
         counts, dwell = counts.clone(), dwell.clone()
         allreduce_summary(counts, dwell)
         return counts.cpu().numpy().view(np.uint64), dwell.cpu().numpy()
+
+    def allreduce_device(self):
+        """All-reduce on the device and STAY there: returns the device pointers (counts, dwell) of
+        the reduced copies, for the on-device M-step (``p53em.em_iteration(reduce_device_fn=...)``).
+        The copies live until the next call."""
+        return allreduce_device(self.sampler, self)
+
+
+def allreduce_device(sampler, keep=None):
+    """``reduce_device_fn`` for ``p53em.em_iteration``: device all-reduce of copies of the sampler's
+    statistics; returns their device pointers.  ``keep`` (default: the sampler) holds the tensors."""
+    import torch
+    counts, dwell = device_summary_tensors(sampler)
+    counts, dwell = counts.clone(), dwell.clone()
+    allreduce_summary(counts, dwell)
+    torch.cuda.synchronize()
+    (keep if keep is not None else sampler)._reduced = (counts, dwell)
+    return counts.data_ptr(), dwell.data_ptr()
