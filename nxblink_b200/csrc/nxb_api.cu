@@ -432,6 +432,8 @@ tolpar_kernel(const __grid_constant__ NxbSweepParams p) {
     tc.p = &p; tc.E = ml.E; tc.P = ml.P; tc.K = ml.K;
     tc.cls.off = ml.off_cls; tc.qm.off = ml.off_qm; tc.slot.off = ml.off_slot;
     tc.erec.off = ml.off_edgerec; tc.grec.off = ml.off_grec; tc.etab.off = ml.off_etab; tc.pcdf.off = ml.off_pcdf;
+    tc.lvl_off.off = ml.off_lvl_off; tc.lvl_node.off = ml.off_lvl_node; tc.ch_off.off = ml.off_ch_off; tc.ch_node.off = ml.off_ch_node;
+    tc.dep_off.off = ml.off_dep_off; tc.dep_edge.off = ml.off_dep_edge; tc.lslot.off = ml.off_lslot;
     tc.s_off_on = c.s_off_on; tc.s_root_misc = c.s_root_misc; tc.s_root_on_cls = c.s_root_on_cls;
     tc.k0 = c.k0; tc.k1 = c.k1;
     TpGroup<WPU> g;
@@ -1032,6 +1034,12 @@ static void build_blink_layout(const NxbModelLayout& ml, bool msg_f64, int capP,
     wl->off_tmpa = wl->off_newtol;                   // scratch of build_poff, dead before newtol is zeroed
     wl->off_nrec = take(16 * E, 16);
     wl->bytes = align_up(o, 16);
+    // Experiment knob: unit stride with a chosen residue mod 128 bytes (the lanes of a warp belong to
+    // two units; measured: no effect on the bank-conflict replays, 19.35-19.42 ms for every residue).
+    int residue = -1;
+    if (const char* ev = getenv("NXB_BLINK_STRIDE_MOD")) residue = atoi(ev);
+    if (residue >= 0) while (wl->bytes % 128 != residue % 128) wl->bytes += 16;
+    if (getenv("NXB_DEBUG_LAYOUT")) fprintf(stderr, "blink unit layout: %d bytes (payload %d)\n", wl->bytes, o);
 }
 
 // One unit of tolpar_kernel: the trajectory, the per-edge records, the event pool (time, key,
@@ -1046,7 +1054,7 @@ static void build_tol_layout(const NxbModelLayout& ml, bool msg_f64, int capP, i
     tl->capP = capP; tl->capB = capB; tl->capQ = capQ; tl->capL = capL;
     tl->off_q = take((msg_f64 ? 32 : 16) * std::max(capQ, capL), 16);
     tl->off_nrec = take(16 * E, 16);
-    tl->off_acc = take((msg_f64 ? 32 : 16) * K * ml.nslots, 16);
+    tl->off_acc = take((msg_f64 ? 32 : 16) * K * std::max(ml.nslots, ml.nslots_lvl), 16);
     tl->off_T = take(8 * capL, 8);
     tl->off_ptm = take(8 * capP, 8);
     tl->off_btm = take(8 * capB, 8);

@@ -86,6 +86,17 @@ struct NxbModelLayout {
     double tp_lam;          // length of one track on the axis: sum_e 2 max(on,off) rate_e len_e
     double tp_W;            // slice width = K * tp_lam / NXB_TP_NSLICE
     unsigned tp_thr[4];     // thinning thresholds [own][fg state] as u32 (accept iff word < thr)
+    // level-parallel tree passes of tol_par.cuh: internal nodes by height (children before parents),
+    // their children, message slots (a slot is live from a node's level to its parent's), and
+    // edges by depth of the child node (parents before children)
+    int n_levels, n_depths, nslots_lvl;
+    int off_lvl_off;        // u16 [n_levels + 1]  offsets into lvl_node, heights 1 .. n_levels
+    int off_lvl_node;       // u16 [internal nodes]
+    int off_ch_off;         // u16 [N + 1]
+    int off_ch_node;        // u16 [E]   children of every node (edge into child c is c - 1)
+    int off_lslot;          // i16 [N]   message slot of an internal node in the level-ordered pass, -1 for leaves
+    int off_dep_off;        // u16 [n_depths + 1] offsets into dep_edge, depths 1 .. n_depths
+    int off_dep_edge;       // u16 [E]
 };
 
 #define NXB_TP_NSLICE 64

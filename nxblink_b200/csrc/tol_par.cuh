@@ -87,6 +87,8 @@ struct TpCtx {
     SPtr<const NxbGenRec> grec;
     SPtr<const unsigned> pcdf;
     SPtr<const unsigned short> etab;
+    SPtr<const unsigned short> lvl_off, lvl_node, ch_off, ch_node, dep_off, dep_edge;
+    SPtr<const short> lslot;
     SPtr<unsigned long long> s_off_on, s_root_misc, s_root_on_cls;
     unsigned k0, k1;
 };
@@ -575,6 +577,7 @@ NXB_DEV int tolpar_update(const TpCtx& c, TpUnit<MSG>& u, const TpGroup<WPU>& g,
                 int dh = 0;
                 if (islast) dh = fmb ? (lane - (31 - __clz(fmb))) : (int)TPK_AUX_MAX;
                 u.key[r] = (key & ((1u << TPK_AUX_SHIFT) - 1u) & ~TPK_LAST) | (islast ? TPK_LAST : 0u) | ((unsigned)dh << TPK_AUX_SHIFT);
+                if (islast) atomicOr(&u.hasev[(int)(key & TPK_EDGE_MASK)], 1u << ((key >> TPK_TRACK_SHIFT) & 31u));
             }
             carry.x = __shfl_sync(0xffffffffu, m.x, 0); carry.y = __shfl_sync(0xffffffffu, m.y, 0);
             carry.z = __shfl_sync(0xffffffffu, m.z, 0); carry.w = __shfl_sync(0xffffffffu, m.w, 0);
@@ -583,30 +586,35 @@ NXB_DEV int tolpar_update(const TpCtx& c, TpUnit<MSG>& u, const TpGroup<WPU>& g,
     g.sync();
     tm.tick(TPT_SCAN);
 
-    // ================================================================== U: up the tree, lane = track
-    if (g.w == 0) {
-        const int k = lane;
-        const bool trk = k < K;
-        unsigned xroot = 0u;
-        if (trk) {
-            const int tlo = u.toff[k];
-            int cur = u.toff[k + 1] - 1;
-            unsigned inited = 0u;
-            for (int e = E - 1; e >= 0; --e) {
+    // ================================================================== U: up the tree, level by level
+    // lane = (internal node of the level, track): the messages of the node's children (one 2x2
+    // mat-vec per non-empty bucket) are multiplied into the node's accumulator.  Levels are the
+    // heights of the nodes, so every child is done before its parent.
+    for (int h = 0; h < ml.n_levels; ++h) {
+        const int n0 = (int)c.lvl_off[h], nn = (int)c.lvl_off[h + 1] - n0;
+        for (int task = li; task < nn * K; task += G) {
+            const int vi = task / K, k = task - vi * K;
+            const int v = (int)c.lvl_node[n0 + vi];
+            const int tlo = u.toff[k], thi = u.toff[k + 1];
+            AccRec<MSG> n; n.u0 = (MSG)1; n.u1 = (MSG)1; n.pen = 0.0;
+            for (int ci = (int)c.ch_off[v]; ci < (int)c.ch_off[v + 1]; ++ci) {
+                const int cn = (int)c.ch_node[ci], e = cn - 1;
                 const NxbEdgeRec er = c.erec[e];
                 const uint4 nr = u.nrec[e];
                 MSG u0 = 1, u1 = 1;
                 double pen = 0.0;
-                if (er.sb_slot >= 0 && ((inited >> er.sb_slot) & 1u)) {
-                    const AccRec<MSG> a = u.acc[er.sb_slot * K + k];
-                    u0 = a.u0; u1 = a.u1; pen = a.pen;
-                }
+                const int cs = (int)c.lslot[cn];
+                if (cs >= 0) { const AccRec<MSG> a = u.acc[cs * K + k]; u0 = a.u0; u1 = a.u1; pen = a.pen; }
                 if (!((nr.x >> k) & 1u)) u1 = 0;
                 if (!((nr.y >> k) & 1u)) u0 = 0;
                 const int ip0 = (int)(nr.w & 0xffffu), ip1 = (int)(nr.w >> 16);
-                unsigned ckey = 0u;
-                bool has = false;
-                if (cur >= tlo) { ckey = u.key[cur]; has = (int)(ckey & TPK_EDGE_MASK) == e; }
+                const bool has = ((u.hasev[e] >> k) & 1u) != 0u;
+                int cur = -1;
+                if (has) {          // last event of the bucket (k, e): events of a track are sorted by edge
+                    int lo = tlo, hi = thi;
+                    while (lo < hi) { const int m = (lo + hi) >> 1; if ((int)(u.key[m] & TPK_EDGE_MASK) <= e) lo = m + 1; else hi = m; }
+                    cur = lo - 1;
+                }
                 const double t_lo = has ? u.T[cur] : er.tma;
                 double pen_b; bool own_b;
                 if (ip0 == ip1) {
@@ -627,6 +635,7 @@ NXB_DEV int tolpar_update(const TpCtx& c, TpUnit<MSG>& u, const TpGroup<WPU>& g,
                     if (!(mx > (MSG)0)) { bad |= 1; mx = 1; }
                     const MSG rs = M::pow2_rescale(mx);
                     const MSG l0 = u0 * rs, l1 = u1 * rs;
+                    const unsigned ckey = u.key[cur];
                     // (the last event of a bucket carries the distance to its first one, if the block of
                     // the suffix scan saw it)
                     int head = cur - (int)(ckey >> TPK_AUX_SHIFT);
@@ -638,24 +647,26 @@ NXB_DEV int tolpar_update(const TpCtx& c, TpUnit<MSG>& u, const TpGroup<WPU>& g,
                     u0 = qh.x * l0 + qh.y * l1;
                     u1 = qh.z * l0 + qh.w * l1;
                     u.q[head] = TpT<MSG>::make(l0, l1, (MSG)0, (MSG)0);      // message at the bucket's last event
-                    cur = head - 1;
                 }
-                // fold into the parent's accumulator
-                const int ai = er.sa_slot * K + k;
-                AccRec<MSG> n; n.u0 = u0; n.u1 = u1; n.pen = pen;
-                if ((inited >> er.sa_slot) & 1u) { const AccRec<MSG> a = u.acc[ai]; n.u0 *= a.u0; n.u1 *= a.u1; n.pen += a.pen; }
-                MSG m2 = n.u0 > n.u1 ? n.u0 : n.u1;
-                if (!(m2 > (MSG)0)) { bad |= 1; m2 = 1; }
-                const MSG r2 = M::pow2_rescale(m2);
-                n.u0 *= r2; n.u1 *= r2;
-                nxb_acc_pad(n);
-                u.acc[ai] = n;
-                inited |= 1u << er.sa_slot;
-                if (er.sb_slot >= 0) inited &= ~(1u << er.sb_slot);
+                n.u0 *= u0; n.u1 *= u1; n.pen += pen;
             }
-            // root draw (prior: toymodel.py:17-27 get_blink_distn)
+            MSG m2 = n.u0 > n.u1 ? n.u0 : n.u1;
+            if (!(m2 > (MSG)0)) { bad |= 1; m2 = 1; }
+            const MSG r2 = M::pow2_rescale(m2);
+            n.u0 *= r2; n.u1 *= r2;
+            nxb_acc_pad(n);
+            u.acc[(int)c.lslot[v] * K + k] = n;
+        }
+        g.sync();
+    }
+    // root draw (prior: toymodel.py:17-27 get_blink_distn), lane = track
+    if (g.w == 0) {
+        const int k = lane;
+        const bool trk = k < K;
+        unsigned xroot = 0u;
+        if (trk) {
             MSG a0 = 1, a1 = 1; double apen = 0.0;
-            if (inited & (1u << c.slot[0])) { const AccRec<MSG> a = u.acc[c.slot[0] * K + k]; a0 = a.u0; a1 = a.u1; apen = a.pen; }
+            if ((int)c.lslot[0] >= 0) { const AccRec<MSG> a = u.acc[(int)c.lslot[0] * K + k]; a0 = a.u0; a1 = a.u1; apen = a.pen; }
             double w1 = (double)a1 * (a0 != (MSG)0 ? fmax(exp(-apen), 2.2250738585072014e-308) : 1.0) * ml.p_on;
             double w0 = (double)a0 * ml.p_off;
             if (!(((unsigned)u.x[8] >> k) & 1u)) w1 = 0.0;
@@ -731,7 +742,6 @@ NXB_DEV int tolpar_update(const TpCtx& c, TpUnit<MSG>& u, const TpGroup<WPU>& g,
                 if (key & TPK_LAST) {
                     const int e = (int)(key & TPK_EDGE_MASK);
                     const unsigned bit = 1u << ((key >> TPK_TRACK_SHIFT) & 31u);
-                    atomicOr(&u.hasev[e], bit);
                     if (gm & 1u) atomicOr(&u.f0[e], bit);
                     if (gm & 2u) atomicOr(&u.f1[e], bit);
                 }
@@ -744,14 +754,17 @@ NXB_DEV int tolpar_update(const TpCtx& c, TpUnit<MSG>& u, const TpGroup<WPU>& g,
     tm.tick(TPT_MAPS);
 
     // ================================================================== D: node states, all tracks at once
-    if (li == 0) {
-        for (int e = 0; e < E; ++e) {
+    // lane = edge of one depth level (parents before children); bit-parallel over the tracks
+    for (int dl = 0; dl < ml.n_depths; ++dl) {
+        const int e0 = (int)c.dep_off[dl], ne = (int)c.dep_off[dl + 1] - e0;
+        for (int i = li; i < ne; i += G) {
+            const int e = (int)c.dep_edge[e0 + i];
             const unsigned xa = u.newtol[c.erec[e].va];
             const unsigned hv = u.hasev[e];
             u.newtol[e + 1] = (xa & ~hv) | (hv & ((xa & u.f1[e]) | (~xa & u.f0[e])));
         }
+        g.sync();
     }
-    g.sync();
     tm.tick(TPT_DOWN);
 
     // ================================================================== W: survivors

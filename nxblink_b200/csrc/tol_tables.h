@@ -137,6 +137,57 @@ static inline int nxb_build_tol_tables(const nxb_model_desc* d, NxbModelLayout& 
         for (int i = 0; i < 4; ++i)
             ml.tp_thr[i] = (unsigned)fmin(ml.acc_blk[i] * 4294967296.0, 4294967295.0);
     }
+    // ---- level tables of the level-parallel tree passes (tol_par.cuh) ----
+    {
+        std::vector<int> height(N, 0), depth(N, 0), nchild(N, 0);
+        for (int v = N - 1; v >= 1; --v) height[d->parent[v]] = std::max(height[d->parent[v]], height[v] + 1);
+        for (int v = 1; v < N; ++v) { depth[v] = depth[d->parent[v]] + 1; nchild[d->parent[v]]++; }
+        const int H = height[0], D = *std::max_element(depth.begin(), depth.end());
+        std::vector<unsigned short> lvl_off(H + 1, 0), lvl_node, ch_off(N + 1, 0), ch_node(E, 0), dep_off(D + 1, 0), dep_edge;
+        for (int h = 1; h <= H; ++h) {
+            lvl_off[h - 1] = (unsigned short)lvl_node.size();
+            for (int v = 0; v < N; ++v) if (height[v] == h) lvl_node.push_back((unsigned short)v);
+        }
+        lvl_off[H] = (unsigned short)lvl_node.size();
+        for (int v = 0; v < N; ++v) ch_off[v + 1] = (unsigned short)(ch_off[v] + nchild[v]);
+        {
+            std::vector<int> fill(N, 0);
+            for (int v = 1; v < N; ++v) { const int pa = d->parent[v]; ch_node[ch_off[pa] + fill[pa]++] = (unsigned short)v; }
+        }
+        for (int dd = 1; dd <= D; ++dd) {
+            dep_off[dd - 1] = (unsigned short)dep_edge.size();
+            for (int v = 1; v < N; ++v) if (depth[v] == dd) dep_edge.push_back((unsigned short)(v - 1));
+        }
+        dep_off[D] = (unsigned short)dep_edge.size();
+        // message slots in level order: taken at the node's level, released after the parent's level
+        std::vector<short> lslot(N, -1);
+        {
+            std::vector<int> free_slots;
+            int next = 0;
+            for (int h = 1; h <= H; ++h) {
+                for (int i = lvl_off[h - 1]; i < lvl_off[h]; ++i) {
+                    const int v = lvl_node[i];
+                    if (!free_slots.empty()) { lslot[v] = (short)free_slots.back(); free_slots.pop_back(); }
+                    else lslot[v] = (short)next++;
+                }
+                // the children of this level's nodes are not needed again
+                for (int i = lvl_off[h - 1]; i < lvl_off[h]; ++i) {
+                    const int v = lvl_node[i];
+                    for (int j = ch_off[v]; j < ch_off[v + 1]; ++j)
+                        if (lslot[ch_node[j]] >= 0) free_slots.push_back(lslot[ch_node[j]]);
+                }
+            }
+            ml.nslots_lvl = std::max(next, 1);
+        }
+        ml.n_levels = H; ml.n_depths = D;
+        ml.off_lvl_off = put(lvl_off.data(), 2 * (H + 1), 2);
+        ml.off_lvl_node = put(lvl_node.data(), 2 * (int)std::max<size_t>(lvl_node.size(), 1), 2);
+        ml.off_ch_off = put(ch_off.data(), 2 * (N + 1), 2);
+        ml.off_ch_node = put(ch_node.data(), 2 * std::max(E, 1), 2);
+        ml.off_lslot = put(lslot.data(), 2 * N, 2);
+        ml.off_dep_off = put(dep_off.data(), 2 * (D + 1), 2);
+        ml.off_dep_edge = put(dep_edge.data(), 2 * std::max(E, 1), 2);
+    }
     blob.resize(align_up((int)blob.size(), 16));
     ml.blink_bytes = (int)blob.size();
     return 0;
