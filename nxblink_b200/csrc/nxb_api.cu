@@ -903,6 +903,7 @@ struct nxb_handle {
     bool need_reconfig = false;                    // the model blob changed size: tiers must be rebuilt
     double cap_boost = 1.0;                        // doubled when a unit outgrows its slab or the largest tier
     double cap_means[2] = {0.0, 0.0};              // expected primary / blink events per unit the capacities were sized for
+    int discard_pool = 1;                          // NXB_DISCARD_POOL
     int blink_ctas = 1;                            // co-resident blink_kernel CTAs per SM (NXB_BLINK_CTAS)
     int smem_per_sm = 0;
     bool sync_sweeps = false;                      // NXB_SYNC_SWEEPS=1: the host-synchronised split path (one wait per sweep)
@@ -1478,7 +1479,7 @@ static int configure_capacities(nxb_handle* h, const CapCfg& cfg) {
             }
             int o = 0;
             h->g_off_msg = o; o += (h->msg_f64 ? 8 : 4) * (h->gcapF + 1) * NXB_PPAD;
-            o = align_up(o, 16);
+            o = align_up(o, 128);         // (whole 128-byte lines per track region: discard.global.L2)
             h->g_off_ctm = o; o += (h->msg_f64 ? 32 : 16) * h->gcapC * K;      // one region per track, 16 B (f32) / 32 B (f64) records
             h->gscratch_stride = align_up(o, 256);
             if (h->d_gscratch) { cudaFree(h->d_gscratch); h->d_gscratch = nullptr; }
@@ -1556,6 +1557,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     h->num_sms = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
     h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    if (const char* ev = getenv("NXB_DISCARD_POOL")) h->discard_pool = atoi(ev) != 0;
     if (const char* ev = getenv("NXB_BLINK_CTAS")) h->blink_ctas = std::max(1, std::min(4, atoi(ev)));
     CUDA_TRY_C(cudaStreamCreate(&h->own_stream));
     h->stream = h->own_stream;
@@ -1788,6 +1790,7 @@ static void fill_params(nxb_handle* h, NxbSweepParams& p, int kind, const Tier& 
     p.perf = h->profile ? h->d_perf : nullptr;
     p.gscratch = h->d_gscratch; p.gscratch_stride = h->gscratch_stride;
     p.g_off_msg = h->g_off_msg; p.g_off_ctm = h->g_off_ctm; p.gcapF = h->gcapF; p.gcapC = h->gcapC;
+    p.discard_pool = h->discard_pool;
     p.dbg_unit = -1; p.dbg_sweep = 0;
     if (const char* ev = getenv("NXB_DBG_UNIT")) { p.dbg_unit = atoll(ev); p.dbg_sweep = getenv("NXB_DBG_SWEEP") ? atoi(getenv("NXB_DBG_SWEEP")) : 0; }
 }

@@ -809,6 +809,14 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         obcode[dst + q] = (unsigned)(ce & CE_EDGE) | ((unsigned)lane << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);
     }
     __syncwarp();
+    // The pool records of this sweep are dead now.  They live in the L2-resident scratch; tell L2
+    // that their lines need no write-back (discard.global.L2), or every sweep writes ~3 KB per
+    // unit of dead records to HBM when the lines are evicted.
+    if (lane < K && p.discard_pool) {
+        const char* b = (const char*)cev_own;
+        for (int off = 0; off < n_live * (int)sizeof(LiveEv<MSG>); off += 128)
+            asm volatile("discard.global.L2 [%0], 128;" :: "l"(b + off) : "memory");
+    }
     tick(c, T_BW);
     if (spill && !SPLIT) { c.nB = -total; return RC_DEFER; }
     c.nB = total;
