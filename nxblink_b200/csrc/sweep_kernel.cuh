@@ -489,13 +489,20 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
     // downward pass) flags the chunks that have received a factor, so that the first child
     // assigns instead of multiplying and an untouched chunk reads as all ones -- no
     // initialisation pass over the L2 scratch and no read of never-written messages.
-    for (int j = lane; j <= F; j += 32) cstate[j] = 0;
-    __syncwarp();
     const SPtr<const unsigned short> ell_info = {c.ell_info};
     const SPtr<const MSG> ell_q = {c.ell_q};
     const SPtr<const MSG> qdt = {(unsigned)p.ml.off_qdt};
     const int W = p.ml.ell_w;
     const bool two = P > 32;
+    // A parent's message is the raw product of its children's factors (each <= 1) until the parent
+    // is pushed up itself: a chunk with very many child chunks can underflow to all zeros in f32 on
+    // feasible data.  The pass is therefore run again, `careful`, when it meets an all-zero
+    // message: then every product is rescaled by a power of two as it is folded (zeros stay
+    // exact).  Only a second failure is an infeasible unit (raoteh.py:178-180).
+    bool careful = false;
+p3_again:
+    for (int j = lane; j <= F; j += 32) cstate[j] = 0;
+    __syncwarp();
     for (int j = F - 1; j >= 0; --j) {
         const int ci = j + 1, pi_ = par[ci];
         const unsigned fm = fmask[j];
@@ -508,7 +515,10 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
             // One feasible state o in the child chunk (it holds an observed leaf): the message is
             // one-hot, so P . L is column o of the uniformized matrix -- a lookup, not a mat-vec.
             const int o = __ffsll((long long)allow) - 1;
-            if (cinit && !((MSG)mc[o] > (MSG)0)) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
+            if (cinit && !((MSG)mc[o] > (MSG)0)) {
+                if (!careful) { careful = true; __syncwarp(); goto p3_again; }
+                fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR;
+            }
             MSG qo = 0;
             if (lane < W) {
                 const unsigned info = ell_info[lane * NXB_PPAD + o];
@@ -522,6 +532,11 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
                 const MSG c1 = (lane + 32 == o) ? (MSG)1 - inv * qo : inv * qdt[o * NXB_PPAD + lane + 32];
                 mp[lane + 32] = pinit ? mp[lane + 32] * c1 : c1;
             }
+            if (__builtin_expect(careful, 0)) {
+                MSG n0 = mp[lane], n1 = two ? mp[lane + 32] : (MSG)0, mx = n0 > n1 ? n0 : n1;
+                for (int d = 16; d > 0; d >>= 1) { const MSG y = __shfl_xor_sync(FULL, mx, d); mx = y > mx ? y : mx; }
+                if (mx > (MSG)0) { const MSG r = TolMath<MSG>::pow2_rescale(mx); mp[lane] = n0 * r; if (two) mp[lane + 32] = n1 * r; }
+            }
             if (lane == 0) cstate[pi_] = 1;
             __syncwarp();
             continue;
@@ -532,7 +547,10 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
         MSG mx = v0 > v1 ? v0 : v1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { MSG y = __shfl_xor_sync(FULL, mx, o); mx = y > mx ? y : mx; }
-        if (!(mx > (MSG)0)) { fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR; }
+        if (!(mx > (MSG)0)) {
+            if (!careful) { careful = true; __syncwarp(); goto p3_again; }
+            fail(c, NXB_ERR_INFEASIBLE, j); return RC_ERROR;
+        }
         const MSG sc = (MSG)1 / mx;
         v0 *= sc; v1 *= sc;
         mc[lane] = v0;                   // kept for the backward pass
@@ -564,8 +582,20 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
                 mp[lane + 32] = pinit ? mp[lane + 32] * f1 : f1;
             }
         }
+        if (__builtin_expect(careful, 0)) {
+            MSG n0 = mp[lane], n1 = two ? mp[lane + 32] : (MSG)0, mx2 = n0 > n1 ? n0 : n1;
+            for (int d = 16; d > 0; d >>= 1) { const MSG y = __shfl_xor_sync(FULL, mx2, d); mx2 = y > mx2 ? y : mx2; }
+            if (mx2 > (MSG)0) { const MSG r = TolMath<MSG>::pow2_rescale(mx2); mp[lane] = n0 * r; if (two) mp[lane + 32] = n1 * r; }
+        }
         if (lane == 0) cstate[pi_] = 1;
         __syncwarp();
+    }
+    if (!careful && cstate[0] != 0) {
+        // the root chunk is never pushed up: look at its raw product here (before the lockstep barrier)
+        const unsigned long long allow0 = callow[0];
+        const bool pos = (lane < P && ((allow0 >> lane) & 1ull) && msg[lane] > (MSG)0) ||
+                         (lane + 32 < P && ((allow0 >> (lane + 32)) & 1ull) && msg[lane + 32] > (MSG)0);
+        if (!__any_sync(FULL, pos)) { careful = true; goto p3_again; }
     }
     tick(c, T_P3);
     phase_sync(c);

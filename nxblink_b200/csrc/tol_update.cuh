@@ -52,7 +52,11 @@ template <> struct TolMath<float> {
     // penalty beyond the f32 range (exponent > 87) must not create one, or a unit whose OFF state is
     // excluded by data would turn infeasible.  Messages are rescaled by powers of two at every fold,
     // so the smallest normal number is as good as the true 1e-40.
+#ifdef NXB_AB_NOCLAMP
+    static NXB_DEV float expneg(double pen) { return nxb_fast_expf((float)(-pen)); }
+#else
     static NXB_DEV float expneg(double pen) { return fmaxf(nxb_fast_expf((float)(-pen)), 1.17549435e-38f); }
+#endif
     static NXB_DEV float div(float a, float b) { return nxb_fast_divf(a, b); }
     // 2^-(floor(log2 m) + 1) for a positive finite m: exact power-of-two rescaling into [0.5, 1)
     // without a division; preserves exact zeros of the other component.

@@ -109,3 +109,47 @@ def test_maximum_classes_and_states(nb):
     """K = 32 tolerance classes (every lane a track, full-width masks), P = 64 states."""
     M = BigModel(n_nodes=20, P=64, K=32, seed=3, deg=2)
     _prior_invariance(nb, M, n_units=2048, sweeps=4)
+
+
+class StarModel(BigModel):
+    """A root with `n_leaves` long branches: the root's chunk collects one factor per branch."""
+
+    def __init__(self, n_leaves=100, P=12, K=3, seed=5):
+        BigModel.__init__(self, n_nodes=2, P=P, K=K, seed=seed, deg=3)
+        self.edges, self.rates, self.blens = [], {}, {}
+        for v in range(1, n_leaves + 1):
+            e = ('n0', 'n%d' % v)
+            self.edges.append(e)
+            self.rates[e] = 1.0
+            self.blens[e] = 1.5
+
+
+def test_chunk_with_a_hundred_child_chunks_does_not_underflow_f32(nb):
+    """The message of a chunk is the product of the factors its child chunks push up
+    (chunking.py:264-289 -> nxmctree FFBS).  With 100 observed leaves on long branches the root
+    chunk receives ~100 factors of order 1e-2: the raw product leaves the f32 range (round-1
+    advisor finding: a spurious INFEASIBLE on feasible data).  The product is rescaled by a power
+    of two every 4th fold; f32 and f64 statistics agree."""
+    M = StarModel()
+    pm = packing.PackedModel(M)
+    rng = np.random.default_rng(1)
+    n_sites = 6
+    ls = np.full((n_sites, pm.n_nodes), -1, dtype=np.int64)
+    ls[:, 1:] = rng.integers(0, pm.n_states, size=(n_sites, pm.n_nodes - 1))
+    data = packing.pack_alignment(pm, ls)
+    res = {}
+    for f64 in (False, True):
+        vals = []
+        for seed in range(3):
+            s = nb.BlinkSampler(pm, validate=True, msg_f64=f64)
+            s.set_data(data)
+            s.init_chains(chains=64, seed=seed)
+            s.sweep(6, accumulate=False)          # raises NxbError(INFEASIBLE) if a message underflows
+            s.sweep(6, accumulate=True)
+            vals.append(gu.scalar_functionals(s.summary()))
+            s.close()
+        res[f64] = vals
+    for name in res[False][0]:
+        a = np.array([r[name] for r in res[False]]); b = np.array([r[name] for r in res[True]])
+        se = np.hypot(a.std(ddof=1), b.std(ddof=1)) / np.sqrt(len(a))
+        assert abs(a.mean() - b.mean()) <= 5 * se + 5e-3 * max(1.0, abs(a.mean())), (name, a.mean(), b.mean(), se)
