@@ -356,11 +356,7 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
                         active = true;
                         c.unit = u; c.unit32 = (unsigned)(p.unit_offset + u);
                         c.nP = hdr.n_pri; c.nB = hdr.n_blk; c.sweep = hdr.sweeps_done;
-#ifdef NXB_AB_NOPAD
-                        accum = hdr.sweeps_done >= p.accum_from;
-#else
                         accum = hdr.sweeps_done >= p.accum_from && hdr.pad == 0u;     // (pad: already booked, see sweep_kernel)
-#endif
                         const long long site = u / p.chains;
                         g_tt = p.tol_true_ok + site * N;
                         g_tf = p.tol_false_ok + site * N;

@@ -833,7 +833,7 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         obcode = (unsigned*)(slab + p.so_bcode);
     }
     for (int q = 0; q < n_mine; ++q) {
-        const LiveEv<MSG> sv = cev_own[n_live - 1 - q];      // first survivor (rootmost, earliest) on top
+        const LiveEv<MSG> sv = nxb_ev_load(cev_own + (n_live - 1 - q));      // first survivor (rootmost, earliest) on top
         const unsigned ce = sv.e;
         obtm[dst + q] = sv.t;
         obcode[dst + q] = (unsigned)(ce & CE_EDGE) | ((unsigned)lane << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);

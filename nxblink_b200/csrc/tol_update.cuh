@@ -43,6 +43,28 @@ template <> struct __align__(16) AccRec<float> { double pen; float u0, u1; };
 template <> struct __align__(16) AccRec<double> { double pen; double u0, u1; double pad; };
 NXB_DEV void nxb_acc_pad(AccRec<float>&) {}
 NXB_DEV void nxb_acc_pad(AccRec<double>& n) { n.pad = 0.0; }
+// pool records live in L2 (global scratch): access them with the cache-global operators, which do
+// not allocate in the small L1 that is left beside 212 KB of shared memory
+#if defined(__CUDACC__)
+NXB_DEV LiveEv<float> nxb_ev_load(const LiveEv<float>* p) {
+    const int4 v = __ldcg(reinterpret_cast<const int4*>(p));
+    LiveEv<float> e;
+    e.t = __hiloint2double(v.y, v.x); e.q = __int_as_float(v.z);
+    e.e = (unsigned short)(v.w & 0xffff); e.pad = (unsigned short)((unsigned)v.w >> 16);
+    return e;
+}
+NXB_DEV void nxb_ev_store(LiveEv<float>* p, const LiveEv<float>& e) {
+    int4 v;
+    v.x = __double2loint(e.t); v.y = __double2hiint(e.t); v.z = __float_as_int(e.q);
+    v.w = (int)((unsigned)e.e | ((unsigned)e.pad << 16));
+    __stcg(reinterpret_cast<int4*>(p), v);
+}
+NXB_DEV LiveEv<double> nxb_ev_load(const LiveEv<double>* p) { return *p; }
+NXB_DEV void nxb_ev_store(LiveEv<double>* p, const LiveEv<double>& e) { *p = e; }
+#else
+template <typename MSG> NXB_DEV LiveEv<MSG> nxb_ev_load(const LiveEv<MSG>* p) { return *p; }
+template <typename MSG> NXB_DEV void nxb_ev_store(LiveEv<MSG>* p, const LiveEv<MSG>& e) { *p = e; }
+#endif
 NXB_DEV void nxb_ev_pad(LiveEv<float>&) {}
 NXB_DEV void nxb_ev_pad(LiveEv<double>& e) { e.pad2 = 0u; e.pad3 = 0.0; }
 
@@ -52,11 +74,7 @@ template <> struct TolMath<float> {
     // penalty beyond the f32 range (exponent > 87) must not create one, or a unit whose OFF state is
     // excluded by data would turn infeasible.  Messages are rescaled by powers of two at every fold,
     // so the smallest normal number is as good as the true 1e-40.
-#ifdef NXB_AB_NOCLAMP
-    static NXB_DEV float expneg(double pen) { return nxb_fast_expf((float)(-pen)); }
-#else
     static NXB_DEV float expneg(double pen) { return fmaxf(nxb_fast_expf((float)(-pen)), 1.17549435e-38f); }
-#endif
     static NXB_DEV float div(float a, float b) { return nxb_fast_divf(a, b); }
     // 2^-(floor(log2 m) + 1) for a positive finite m: exact power-of-two rescaling into [0.5, 1)
     // without a division; preserves exact zeros of the other component.
@@ -305,7 +323,7 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
                             ev.q = (l0 == (MSG)0) ? (MSG)1 : (q < (MSG)1 ? q : (MSG)1);
                             ev.e = (unsigned short)e; ev.pad = 0;
                             nxb_ev_pad(ev);
-                            cev[cnt] = ev;
+                            nxb_ev_store(cev + cnt, ev);
                         } else bad = 2;
                         ++cnt;
                         // uniformized 2x2 matrix of this context (poisson.py:92-96)
@@ -370,7 +388,7 @@ NXB_DEV void tol_down(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPLIT
         LiveEv<MSG> pf;
         pf.t = NXB_INF; pf.q = 0; pf.e = 0xffffu; pf.pad = 0;
         nxb_ev_pad(pf);
-        if (ir >= 0) pf = cev[ir];
+        if (ir >= 0) pf = nxb_ev_load(cev + ir);
         while (TOL_ANY(e < E)) {
             if (e < E) {
                 if (fresh) {
@@ -393,7 +411,7 @@ NXB_DEV void tol_down(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPLIT
                     const MSG l1 = pf.q, l0 = (MSG)1 - pf.q;
                     --ir;
                     // (the record at ir is in registers before a survivor may overwrite it: wtop >= ir)
-                    if (ir >= 0) pf = cev[ir];
+                    if (ir >= 0) pf = nxb_ev_load(cev + ir);
                     else { pf.t = NXB_INF; pf.e = 0xffffu; }
                     const bool own = (c.cls[s] == k);
                     const MSG p1 = own ? (x ? (MSG)1 : (MSG)0.5) : (x ? a_off1_f : a_on_f);
@@ -405,7 +423,7 @@ NXB_DEV void tol_down(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPLIT
                         LiveEv<MSG> sv;
                         sv.t = tc; sv.q = 0; sv.e = (unsigned short)(e | (xn ? CE_NEW1 : 0u)); sv.pad = 0;
                         nxb_ev_pad(sv);
-                        cev[wtop] = sv;
+                        nxb_ev_store(cev + wtop, sv);
                         --wtop;
                         if (xn) ++n_on; else ++n_off;
                         x = xn;
