@@ -12,8 +12,6 @@ its statistics are an independent statistical cross-check of the CTBN sampler at
 """
 from __future__ import division, print_function
 
-from itertools import product
-
 import numpy as np
 
 from .dense import CompoundProcess
@@ -26,65 +24,96 @@ __all__ = ['State', 'gen_states', 'get_Q', 'state_is_consistent', 'gen_successor
 
 
 class State(object):
-    """compoundb.py:23-41: a primary state plus the list of tolerance states."""
+    """The reference's compound state (compoundb.py:23-41: a primary state and one 0/1 state per
+    tolerance class), kept here in packed form: the tolerance states are the bits of ``mask``.
+    Same public surface -- ``pri``, ``tol`` (a list), ``copy()``, ``tolist()``, ordering and
+    hashing by ``[pri] + tol`` -- so it can stand in wherever the reference's objects are used."""
+    __slots__ = ('pri', 'mask', 'ntol')
 
     def __init__(self, pri, tol):
-        self.pri = pri
-        self.tol = list(tol)
+        bits = [1 if x else 0 for x in tol]
+        self.pri, self.ntol = pri, len(bits)
+        self.mask = sum(bit << k for k, bit in enumerate(bits))
+
+    @classmethod
+    def packed(cls, pri, mask, ntol):
+        s = cls.__new__(cls)
+        s.pri, s.mask, s.ntol = pri, mask, ntol
+        return s
+
+    @property
+    def tol(self):
+        return [(self.mask >> k) & 1 for k in range(self.ntol)]
+
+    def flipped(self, k):
+        """The state with tolerance class k switched."""
+        return State.packed(self.pri, self.mask ^ (1 << k), self.ntol)
 
     def copy(self):
-        return State(self.pri, self.tol)
+        return State.packed(self.pri, self.mask, self.ntol)
 
     def tolist(self):
-        return [self.pri] + list(self.tol)
+        return [self.pri] + self.tol
+
+    def _key(self):
+        return (self.pri, tuple(self.tol))
 
     def __lt__(self, other):
-        return self.tolist() < other.tolist()
-
-    def __hash__(self):
-        return hash(tuple(self.tolist()))
+        return self._key() < other._key()
 
     def __eq__(self, other):
-        return self.tolist() == other.tolist()
+        return isinstance(other, State) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
 
     def __repr__(self):
         return 'State(%r, %r)' % (self.pri, self.tol)
 
 
 def state_is_consistent(pri_to_tol, s):
-    """compoundb.py:150-157: the tolerance class of the primary state must be on."""
-    return bool(s.tol[pri_to_tol[s.pri]])
+    """A compound state exists only with the class of its primary state switched on
+    (compoundb.py:150-157)."""
+    return (s.mask >> pri_to_tol[s.pri]) & 1 == 1
+
+
+def _n_classes(pri_to_tol):
+    classes = set(pri_to_tol.values())
+    if classes != set(range(len(classes))):
+        raise Exception('tolerance classes must be numbered 0..ntol-1')
+    return len(classes)
 
 
 def gen_states(pri_to_tol):
-    """compoundb.py:114-124; tolerance classes must be 0..ntol-1."""
-    ntol = len(set(pri_to_tol.values()))
-    if set(pri_to_tol.values()) != set(range(ntol)):
-        raise Exception('tolerance classes must be numbered 0..ntol-1')
+    """Every consistent compound state (compoundb.py:114-124), tolerance bits counting up with
+    the LAST class fastest, as ``itertools.product((0, 1), repeat=ntol)`` orders them."""
+    ntol = _n_classes(pri_to_tol)
     for pri in pri_to_tol:
-        for tols in product((0, 1), repeat=ntol):
-            s = State(pri, tols)
-            if state_is_consistent(pri_to_tol, s):
-                yield s
+        own = 1 << pri_to_tol[pri]
+        for code in range(1 << ntol):
+            # bit k of `mask` is digit k of the product tuple = bit (ntol - 1 - k) of `code`
+            mask = sum(((code >> (ntol - 1 - k)) & 1) << k for k in range(ntol))
+            if mask & own:
+                yield State.packed(pri, mask, ntol)
 
 
 def gen_successors(Q_pri, on_rate, off_rate, pri_to_tol, s):
-    """compoundb.py:160-193: (state, rate) pairs reachable in one step."""
-    for pri in Q_pri[s.pri]:
-        sb = State(pri, s.tol)
-        if state_is_consistent(pri_to_tol, sb):
-            w = Q_pri[s.pri][pri]
-            yield sb, (w['weight'] if isinstance(w, dict) else w)
-    rates = [on_rate, off_rate]
-    for tol_class, tol_state in enumerate(s.tol):
-        sb = s.copy()
-        sb.tol[tol_class] = 1 - tol_state
-        if state_is_consistent(pri_to_tol, sb):
-            yield sb, rates[tol_state]
+    """One-step moves of the compound chain with their rates (compoundb.py:160-193): a primary
+    transition into a state whose class is on, or one tolerance class switching (never the class
+    of the current primary state off)."""
+    for pri, w in Q_pri[s.pri].items():
+        if (s.mask >> pri_to_tol[pri]) & 1:
+            yield State.packed(pri, s.mask, s.ntol), (w['weight'] if isinstance(w, dict) else w)
+    own = pri_to_tol[s.pri]
+    for k in range(s.ntol):
+        is_on = (s.mask >> k) & 1
+        if is_on and k == own:
+            continue
+        yield s.flipped(k), (off_rate if is_on else on_rate)
 
 
 def get_Q(Q_pri, on_rate, off_rate, pri_to_tol):
-    """compoundb.py:127-134: the compound rate matrix as a weighted digraph."""
+    """The compound rate matrix as a weighted digraph over ``State`` objects (compoundb.py:127-134)."""
     Q = WeightGraph()
     for a in gen_states(pri_to_tol):
         for b, rate in gen_successors(Q_pri, on_rate, off_rate, pri_to_tol, a):

@@ -171,3 +171,27 @@ def test_device_mstep_matches_the_host_objective_and_optimum(nb):
     big = (host.trans_total > 50) & (cf > 0.01)
     assert_allclose(new['edge_rates'][big], sci['edge_rates'][big], rtol=5e-2)
     s.close()
+
+
+def test_em_iteration_on_device_reduced_statistics(nb):
+    """The multi-GPU form of the EM iteration: the statistics are all-reduced on the device
+    (copies; a no-op sum in a single process) and the device M-step runs on the reduced buffers --
+    same result as on the sampler's own accumulators."""
+    torch = pytest.importorskip('torch')
+    from nxblink_b200 import distributed as nd
+    m = p53.p53_model()
+    pm = packing.PackedModel(m)
+    leaf = pm.node_index[m.name_to_leaf['Has']]
+    ls, tt, tf = p53.synthetic_alignment(pm, 32, seed=4, reference_leaf=leaf)
+    data = packing.pack_alignment(pm, ls, tt, tf)
+    prm = p53.jeff_params()
+    params = dict(kappa=prm['kappa'], omega=prm['omega'], A=prm['A'], C=prm['C'], G=prm['G'],
+            T=prm['T'], rate_on=1.5, rate_off=0.5, edge_rates=np.maximum(pm.rate[1:], 1e-6))
+    own = p53em.em_iteration(m, data, params, chains=4, nburnin=4, nsamples=4, seed=9)
+    red = p53em.em_iteration(m, data, params, chains=4, nburnin=4, nsamples=4, seed=9,
+            reduce_device_fn=nd.allreduce_device)
+    assert own['where'].startswith('device') and red['where'].startswith('device')
+    # (dwell sums are floating-point atomics: equal to ~1e-12, the optimiser amplifies that)
+    assert_allclose(red['neg_ll'], own['neg_ll'], rtol=1e-6)
+    for k in ('kappa', 'omega', 'rate_on', 'rate_off'):
+        assert_allclose(red[k], own[k], rtol=1e-4)
