@@ -72,7 +72,7 @@ typedef struct {
     int32_t capP, capB, capF, capC;
     int64_t deferred_units;      /* units that needed a higher capacity tier so far */
     int64_t kernel_launches;     /* sweep-kernel launches so far */
-    int64_t capacity_doublings;  /* times a unit outgrew its HBM slab and every capacity was doubled (see nxb_sweep) */
+    int64_t capacity_doublings;  /* times a unit outgrew its HBM slab and the slab capacities were doubled (see nxb_sweep) */
 } nxb_stats;
 
 int nxb_device_count(void);
@@ -110,8 +110,8 @@ int nxb_init_chains(nxb_handle* h, int32_t chains, uint64_t seed, int64_t unit_o
  * the sufficient statistics of every sweep are added to the device summary
  * (nxblink/summary.py:190-243 Summary.on_sample).  The launches of up to 32 sweeps are enqueued
  * back to back; status and timings are collected once per such chunk.  A unit whose trajectory
- * outgrows its HBM slab does not end the call: every capacity is doubled, the states move to the
- * larger slabs and the unit is run again from where it stood, its already booked statistics
+ * outgrows its HBM slab does not end the call: the HBM-side capacities are doubled, the states move to
+ * the larger slabs and the unit is run again from where it stood, its already booked statistics
  * skipped -- results are identical to those of a handle that was large enough from the start. */
 int nxb_sweep(nxb_handle* h, int32_t n_sweeps, int32_t accumulate);
 

@@ -901,7 +901,7 @@ struct nxb_handle {
     unsigned long long* d_defer_total = nullptr;   // units listed for a higher tier during the current chunk
     unsigned reached = 0;                          // after NXB_ERR_STATE_CAP: the sweep count the other units have reached
     bool need_reconfig = false;                    // the model blob changed size: tiers must be rebuilt
-    double cap_boost = 1.0;                        // doubled when a unit outgrows its slab or the largest tier
+    double cap_boost = 1.0;                        // doubled when a unit outgrows its slab (slab, pool and message-scratch capacities)
     double cap_means[2] = {0.0, 0.0};              // expected primary / blink events per unit the capacities were sized for
     int discard_pool = 1;                          // NXB_DISCARD_POOL
     int blink_ctas = 1;                            // co-resident blink_kernel CTAs per SM (NXB_BLINK_CTAS)
@@ -1356,7 +1356,7 @@ __global__ void reslab_kernel(const ReslabArgs a) {
 }
 
 // Capacity tiers (shared memory), slab layout and global scratch from the expected event counts
-// of the current model; `h->cap_boost` scales every capacity (doubled when a unit outgrows its
+// of the current model; `h->cap_boost` scales the HBM-side capacities (doubled when a unit outgrows its
 // slab or the largest tier).  Called by nxb_create, by nxb_update_model when the new rates need
 // more room than the handle has, and by the sweep when a unit hits a capacity: existing unit
 // states are moved to the new slab layout (reslab_kernel), so chains continue.
@@ -1369,7 +1369,8 @@ static int configure_capacities(nxb_handle* h, const CapCfg& cfg) {
     const long long old_stride = h->stride;
     // ---- capacity tiers ----
     {
-        const double scale = ((cfg.cap_scale > 0.0) ? cfg.cap_scale : 1.0) * h->cap_boost;
+        const double scale = (cfg.cap_scale > 0.0) ? cfg.cap_scale : 1.0;
+        const double boost = h->cap_boost;      // HBM-side capacities only: the shared-memory tiers keep their sizes (and occupancy)
         const double on = cfg.rate_on, off = cfg.rate_off;
         const double mean_blk = K * sum_rt * 2.0 * on * off / (on + off);
         const double mean_pri = sum_rt;
@@ -1384,8 +1385,8 @@ static int configure_capacities(nxb_handle* h, const CapCfg& cfg) {
         int capF = cap(mean_pri + 0.75 * cand_pri + (double)cfg.diameter * 0, 4.0, 8.0);
         int capR = cap(mean_pri + cand_pri, 4.0, 8.0) + capP;
         int capC = cap(mean_blk + cand_blk, 4.0, 16.0);
-        h->gcapP = std::max(h->gcapP, std::min(65535, align_up(4 * capP + 32, 8)));      // (slabs never shrink)
-        h->gcapB = std::max(h->gcapB, std::min(65535, align_up(4 * capB + 64, 8)));
+        h->gcapP = std::max(h->gcapP, std::min(65535, align_up((int)(boost * (4 * capP + 32)), 8)));      // (slabs never shrink)
+        h->gcapB = std::max(h->gcapB, std::min(65535, align_up((int)(boost * (4 * capB + 64)), 8)));
         h->tiers.clear(); h->init_tiers.clear();
         const int stats_bytes = align_up(8 * (ml.stats_words + 16), 16);   // + lockstep batch slots
         const int fixed = ml.bytes + stats_bytes;
@@ -1471,11 +1472,11 @@ static int configure_capacities(nxb_handle* h, const CapCfg& cfg) {
             for (auto& t : h->tiers) max_w = std::max(max_w, t.warps);
             for (auto& t : h->init_tiers) max_w = std::max(max_w, t.warps);
             max_w = std::max(max_w, h->tiers[0].blink_units * h->blink_ctas);
-            h->gcapF = std::max(8 * capF, E * cfg.diameter + 8);
+            h->gcapF = std::max((int)(boost * 8 * capF), E * cfg.diameter + 8);
             // live events per track and sweep: retained + accepted candidates
             {
                 const double per_track = (mean_blk + cand_blk) / K;
-                h->gcapC = std::min(32760, align_up((int)(4.0 * per_track + 10.0 * sqrt(per_track + 1.0) + 64.0), 8));
+                h->gcapC = std::min(32760, align_up((int)(boost * (4.0 * per_track + 10.0 * sqrt(per_track + 1.0) + 64.0)), 8));
             }
             int o = 0;
             h->g_off_msg = o; o += (h->msg_f64 ? 8 : 4) * (h->gcapF + 1) * NXB_PPAD;
@@ -2071,7 +2072,7 @@ static int sweep_to(nxb_handle* h, unsigned target, unsigned accum_from) {
     return rc;
 }
 
-// A unit outgrew its HBM slab (NXB_ERR_STATE_CAP): double every capacity, move the unit states to
+// A unit outgrew its HBM slab (NXB_ERR_STATE_CAP): double the HBM-side capacities, move the unit states to
 // the larger slabs, and run the units that were left behind up to the sweep count the others have
 // reached.  Their random streams depend only on (seed, unit, sweep), and the statistics that the
 // failed attempt had already booked are skipped (NxbUnitHeader::pad), so the result is what slabs
