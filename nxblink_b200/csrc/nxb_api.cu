@@ -86,6 +86,22 @@ __device__ __forceinline__ void cta_epilogue(Ctx& c, const NxbSweepParams& p, in
     }
 }
 
+// L2 prefetch of the live part of one unit's slab, 16 lines by the first 16 lanes of a warp:
+// header + node states (3 lines), primary events (2), blink times (7), blink codes (4).  The
+// persistent kernels issue it one full wave of work ahead, so that whichever CTA takes that unit
+// later finds its slab in L2 instead of HBM (the event counts are not known yet: expected sizes).
+__device__ __forceinline__ void prefetch_unit_slab(const NxbSweepParams& p, long long u, int lane) {
+    if (lane >= 16 || u >= p.n_units) return;
+    const unsigned char* slab = p.state + u * p.state_stride;
+    const unsigned char* a;
+    if (lane < 3) a = slab + 128 * lane;
+    else if (lane == 3) a = slab + p.so_ptm;
+    else if (lane == 4) a = slab + p.so_pcode;
+    else if (lane < 12) a = slab + p.so_btm + 128 * (lane - 5);
+    else a = slab + p.so_bcode + 128 * (lane - 12);
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+}
+
 // PRIMARY_ONLY: the kernel runs the primary update of one sweep and leaves the tolerance update
 // to blink_kernel (the two alternate, one launch each per sweep); otherwise both are fused and a
 // launch runs every unit up to p.target_sweeps.
@@ -155,6 +171,8 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             if ((long long)widx >= n_work) break;
         }
         bool has = (long long)widx < n_work;
+        if (p.prefetch_wave && !p.unit_list)
+            prefetch_unit_slab(p, (long long)widx + (long long)gridDim.x * (blockDim.x >> 5), lane);
         long long u = 0;
         unsigned char* slab = nullptr;
         NxbUnitHeader hdr;
@@ -337,6 +355,8 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
         const long long w0 = (long long)s_batch[0] * U;
         __syncthreads();
         if (w0 >= n_work) break;
+        if (p.prefetch_wave && !p.unit_list)
+            for (int ui = warp; ui < U; ui += W) prefetch_unit_slab(p, w0 + (long long)gridDim.x * U + ui, lane);
         // ---- load + set up the units of the batch ----
         for (int ui = warp; ui < U; ui += W) {
             bind(ui);
@@ -904,6 +924,7 @@ struct nxb_handle {
     double cap_boost = 1.0;                        // doubled when a unit outgrows its slab (slab, pool and message-scratch capacities)
     double cap_means[2] = {0.0, 0.0};              // expected primary / blink events per unit the capacities were sized for
     int discard_pool = 1;                          // NXB_DISCARD_POOL
+    int prefetch_wave = 1;                         // NXB_PREFETCH: L2 prefetch of the unit slabs one wave of work ahead
     int blink_ctas = 1;                            // co-resident blink_kernel CTAs per SM (NXB_BLINK_CTAS)
     int smem_per_sm = 0;
     bool sync_sweeps = false;                      // NXB_SYNC_SWEEPS=1: the host-synchronised split path (one wait per sweep)
@@ -1559,6 +1580,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
     h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     if (const char* ev = getenv("NXB_DISCARD_POOL")) h->discard_pool = atoi(ev) != 0;
+    if (const char* ev = getenv("NXB_PREFETCH")) h->prefetch_wave = atoi(ev) != 0;
     if (const char* ev = getenv("NXB_BLINK_CTAS")) h->blink_ctas = std::max(1, std::min(4, atoi(ev)));
     CUDA_TRY_C(cudaStreamCreate(&h->own_stream));
     h->stream = h->own_stream;
@@ -1792,6 +1814,7 @@ static void fill_params(nxb_handle* h, NxbSweepParams& p, int kind, const Tier& 
     p.gscratch = h->d_gscratch; p.gscratch_stride = h->gscratch_stride;
     p.g_off_msg = h->g_off_msg; p.g_off_ctm = h->g_off_ctm; p.gcapF = h->gcapF; p.gcapC = h->gcapC;
     p.discard_pool = h->discard_pool;
+    p.prefetch_wave = h->prefetch_wave;
     p.dbg_unit = -1; p.dbg_sweep = 0;
     if (const char* ev = getenv("NXB_DBG_UNIT")) { p.dbg_unit = atoll(ev); p.dbg_sweep = getenv("NXB_DBG_SWEEP") ? atoi(getenv("NXB_DBG_SWEEP")) : 0; }
 }

@@ -221,6 +221,7 @@ struct NxbSweepParams {
     long long gscratch_stride;
     int g_off_msg, g_off_ctm;          // global scratch: chunk messages, event pool
     int gcapF, gcapC;
+    int prefetch_wave;                  // 1: the persistent kernels prefetch the unit slabs one wave of work ahead into L2
     int discard_pool;                   // 1: dead pool records are discarded from L2 instead of written back (NXB_DISCARD_POOL=0 switches it off)
     long long dbg_unit;                 // development: dump the event list of this unit (tolpar_kernel), -1: none
     int dbg_sweep;
