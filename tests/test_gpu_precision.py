@@ -5,16 +5,16 @@ default path: exact posterior at toy size, prior invariance at the p53 shape, an
 f64 statistics within Monte Carlo error at the p53 shape.
 
 Tolerances are Monte Carlo tolerances (5 standard errors from independent seeds, plus the
-additive floor written next to each assert); nothing compared here is deterministic."""
+additive floor written next to each assert; the exact-posterior gates are those of
+test_gpu_toy_exact.py: 32 seeds, 5 SE + 2e-4); nothing compared here is deterministic."""
 import os
 
 import numpy as np
 import pytest
 
 import golden_util as gu
-from oracle.dense_oracle import DensePosterior
 from nxblink_b200 import toymodel, toydata, p53, packing
-from test_gpu_toy_exact import _flatten, _flatten_exact, MODELS, DATA
+from test_gpu_toy_exact import exact_posterior_gate, MODELS, DATA
 
 pytestmark = pytest.mark.gpu
 
@@ -36,36 +36,13 @@ class _env(object):
             os.environ['NXB_TOLPAR'] = self.old
 
 
-def _exact_grid(nb, M, D, nseeds=8, **kw):
-    exact, runs = None, []
-    for seed in range(nseeds):
-        s = nb.BlinkSampler(M, validate=True, **kw)
-        s.set_data([D])
-        s.init_chains(chains=1024, seed=3000 + seed)
-        s.sweep(40, accumulate=False)
-        s.sweep(40, accumulate=True)
-        sm = s.summary()
-        assert sm.nsamples == 1024 * 40
-        if exact is None:
-            exact = _flatten_exact(DensePosterior(M, D).expected_summary(), s.pm)
-        runs.append(_flatten(sm, s.pm))
-        s.close()
-    worst = (0.0, None)
-    for key, ex in exact.items():
-        vals = np.array([r[key] for r in runs])
-        se = vals.std(ddof=1) / np.sqrt(nseeds)
-        z = abs(vals.mean() - ex) / (5 * se + 2e-3)          # floor: burn-in residue of 40 sweeps
-        if z > worst[0]:
-            worst = (z, (key, vals.mean(), ex, se))
-    return worst
-
-
 @pytest.mark.parametrize('D', DATA, ids=lambda d: d.__name__)
 @pytest.mark.parametrize('M', MODELS, ids=lambda m: m.__name__)
 def test_f64_messages_match_exact_posterior(nb, M, D):
     with _env(False):
-        worst = _exact_grid(nb, M, D, msg_f64=True)
+        worst, rms = exact_posterior_gate(nb, M, D, msg_f64=True)
     assert worst[0] <= 1.0, worst
+    assert rms < 1.5
 
 
 @pytest.mark.parametrize('f64', [False, True], ids=['f32', 'f64'])
@@ -74,8 +51,9 @@ def test_f64_messages_match_exact_posterior(nb, M, D):
     ids=['B-C', 'A-A', 'C-B', 'C-D'])
 def test_event_parallel_kernel_matches_exact_posterior(nb, M, D, f64):
     with _env(True):
-        worst = _exact_grid(nb, M, D, msg_f64=f64)
+        worst, rms = exact_posterior_gate(nb, M, D, msg_f64=f64)
     assert worst[0] <= 1.0, worst
+    assert rms < 1.5
 
 
 def _edge_matrix(sm):

@@ -4,9 +4,14 @@ restating compound.py / denseutil.py / toymodel-analytic.py), for the reference'
 full smoke grid (test_smoke.py:19-30: 3 models x 4 data levels).
 
 Every statistic that nxblink.summary.Summary accumulates is tested individually
-with a z-test whose standard error comes from independent seeds.  Tolerance:
-|mean - exact| <= 5 * SE + 2e-3 (Monte Carlo error; there is no FP tolerance to
-state because nothing here is deterministic)."""
+with a z-test whose standard error comes from 32 independent seeds.  Tolerance:
+|mean - exact| <= 5 * SE + 2e-4 (Monte Carlo error only; the additive term is there
+for statistics whose standard error is ~0, not as slack: typical SE is 1e-4..1e-3;
+there is no FP tolerance to state because nothing here is deterministic).  The
+chains run 100 burn-in sweeps from the reference-style initial trajectories
+(raoteh.py:337-361); the grids WITHOUT data mix slowly from there (a 1e-3 residue
+after 100 sweeps), so they start from exact prior draws instead (device forward
+sampler, fwdsample.py:67-262) and the sweep has to keep them on the prior."""
 import numpy as np
 import pytest
 
@@ -54,17 +59,24 @@ def _flatten_exact(ex, pm):
     return out
 
 
-@pytest.mark.parametrize('D', DATA, ids=lambda d: d.__name__)
-@pytest.mark.parametrize('M', MODELS, ids=lambda m: m.__name__)
-def test_summary_statistics_match_exact_posterior(nb, M, D):
+NSEEDS = 32
+
+
+def exact_posterior_gate(nb, M, D, nseeds=NSEEDS, **kw):
+    """Runs `nseeds` independent batches of 1024 chains x 40 accumulated sweeps and returns
+    (worst, rms z): worst = max over the statistics of |mean - exact| / (5 SE + 2e-4)."""
     exact = None
     runs = []
-    nseeds = 8
     for seed in range(nseeds):
-        s = nb.BlinkSampler(M, validate=True)
-        s.set_data([D])
-        s.init_chains(chains=1024, seed=1000 + seed)
-        s.sweep(40, accumulate=False)
+        s = nb.BlinkSampler(M, validate=(seed < 4), **kw)  # (every invariant after every phase, 4 of the runs)
+        if D is toydata.DataA:
+            s.forward_sample(1024, seed=1000 + seed)       # exact draws from the prior = the posterior without data
+            s.reset_summary()
+            s.sweep(20, accumulate=False)
+        else:
+            s.set_data([D])
+            s.init_chains(chains=1024, seed=1000 + seed)
+            s.sweep(100, accumulate=False)
         s.sweep(40, accumulate=True)
         sm = s.summary()
         assert sm.nsamples == 1024 * 40
@@ -73,13 +85,25 @@ def test_summary_statistics_match_exact_posterior(nb, M, D):
         runs.append(_flatten(sm, s.pm))
         s.close()
     worst = (0.0, None)
+    zs = []
     for key, ex in exact.items():
         vals = np.array([r[key] for r in runs])
         se = vals.std(ddof=1) / np.sqrt(nseeds)
-        z = abs(vals.mean() - ex) / (5 * se + 2e-3)
+        z = abs(vals.mean() - ex) / (5 * se + 2e-4)
+        if se > 0:
+            zs.append(abs(vals.mean() - ex) / se)
         if z > worst[0]:
             worst = (z, (key, vals.mean(), ex, se))
+    return worst, float(np.sqrt(np.mean(np.square(zs))))
+
+
+@pytest.mark.parametrize('D', DATA, ids=lambda d: d.__name__)
+@pytest.mark.parametrize('M', MODELS, ids=lambda m: m.__name__)
+def test_summary_statistics_match_exact_posterior(nb, M, D):
+    worst, rms = exact_posterior_gate(nb, M, D)
     assert worst[0] <= 1.0, worst
+    # unbiased estimates: the z-scores of the ~150 statistics have unit scale
+    assert rms < 1.5
 
 
 def test_reference_compatible_root_xon_count(nb):
