@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 def test_forward_statistics_match_exact_prior(nb):
     M = toymodel.BlinkModelB
     runs = []
-    for seed in range(6):
+    for seed in range(24):
         s = nb.BlinkSampler(M)
         node_pri, node_tol = s.forward_sample(40000, seed=seed)
         assert node_pri.shape == (40000, 6)
@@ -35,7 +35,7 @@ def test_forward_statistics_match_exact_prior(nb):
     for key, ex in exact.items():
         vals = np.array([r[key] for r in runs])
         se = vals.std(ddof=1) / np.sqrt(len(runs))
-        z = abs(vals.mean() - ex) / (5 * se + 2e-3)
+        z = abs(vals.mean() - ex) / (5 * se + 2e-4)          # (24 seeds; the floor is for statistics with SE ~ 0)
         if z > worst[0]:
             worst = (z, (key, vals.mean(), ex, se))
     assert worst[0] <= 1.0, worst
