@@ -5,7 +5,7 @@ split into contiguous blocks, one per rank, with NO data-path collective.  The
 single exchange step is the reduction of the sufficient statistics (the role the
 single ``Summary`` object plays across sites in
 examples/p53/run-stochastic.py:172-195): one all-reduce(sum) of the u64 count
-buffer and one of the f64 dwell buffer, in place on the device buffers
+buffer and one of the f64 dwell buffer, on device copies of the buffers
 (NCCL over NVLink; ``gloo`` on host buffers for the CPU tests).
 
 Random streams are keyed by GLOBAL unit index, so integer statistics are
