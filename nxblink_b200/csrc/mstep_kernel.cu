@@ -259,6 +259,10 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mstep_kernel(const MsArgs a) {
     }
     for (int i = tid; i < n; i += MS_THREADS) sh.x[i] = a.x[i];
     __syncthreads();
+    if (!(sh.scal[2] > 0.0)) {              // no sample accumulated: nothing to maximise
+        if (tid == 0) { a.out[0] = 0.0; a.out[1] = 0.0; a.out[2] = 0.0; a.out[3] = -1.0; a.out[4] = 0.0; }
+        return;
+    }
     int evals = 1, iters = 0, status = 0, hist = 0, head = 0;
     double f;
     if (a.eval_only) {
@@ -472,6 +476,7 @@ extern "C" int nxb_mstep(int device, const nxb_mstep_desc* d, const nxb_summary_
     MTRY(cudaMemcpy(out.data(), dx, 8 * (size_t)(8 + 2 * n), cudaMemcpyDeviceToHost));
     memcpy(x, out.data(), 8 * (size_t)n);
     out.erase(out.begin(), out.begin() + n);
+    if (out[3] < 0.0) { g_ms_err = "the statistics hold no samples (accumulate sweeps before the M-step)"; return NXB_ERR_BAD_ARG; }
     *f_out = out[0];
     if (grad_out) for (int i = 0; i < n; ++i) grad_out[i] = out[8 + i];
     if (info) { info[0] = (int)out[1]; info[1] = (int)out[2]; info[2] = (int)out[3]; }

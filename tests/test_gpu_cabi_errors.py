@@ -92,3 +92,39 @@ def test_infeasible_data_is_reported_with_the_unit(nb):
         s.init_chains(chains=3, seed=1)
     assert e.value.code == 1 and 'unit' in str(e.value)        # NXB_ERR_INFEASIBLE
     s.close()
+
+
+def test_mstep_without_samples_is_refused(nb):
+    """nxb_mstep on empty statistics (no accumulated sweep) raises instead of dividing by zero."""
+    from nxblink_b200 import p53, packing, p53em
+    import numpy as np
+    m = p53.p53_model()
+    pm = packing.PackedModel(m)
+    s = nb.BlinkSampler(pm)
+    dm = p53em.DeviceMStep(s, m.genetic_code)
+    with pytest.raises(Exception) as ei:
+        dm.minimize(np.zeros(8 + pm.n_nodes - 1))
+    assert 'no samples' in str(ei.value)
+    s.close()
+
+
+def test_new_site_count_drops_the_old_chains(nb):
+    """nxb_set_data with another number of sites: the chains belong to the old sites, so a sweep
+    without a new nxb_init_chains is refused (round-1 advisor finding: it used to read past the new
+    data buffers); init_chains right after forward_sample (no caller data) is refused with a message."""
+    M = toymodel.BlinkModelB
+    s = nb.BlinkSampler(M)
+    s.set_data([toydata.DataC] * 4)
+    s.init_chains(chains=8, seed=1)
+    s.sweep(2, accumulate=True)
+    s.set_data([toydata.DataC] * 2)
+    with pytest.raises(Exception) as ei:
+        s.sweep(1, accumulate=True)
+    assert 'init_chains' in str(ei.value)
+    s.init_chains(chains=8, seed=1)
+    s.sweep(1, accumulate=False)                 # usable again
+    s.forward_sample(64, seed=2)
+    with pytest.raises(Exception) as ei:
+        s.init_chains(chains=2, seed=3)
+    assert 'set_data' in str(ei.value)
+    s.close()
