@@ -156,7 +156,9 @@ def test_device_mstep_matches_the_host_objective_and_optimum(nb):
     assert info['status'] in (1, 2), info
     assert_allclose(host.neg_ll(x), f, rtol=1e-10)              # the device's own value is right
     assert abs(f - sci['neg_ll']) <= 2e-6 * abs(sci['neg_ll']), (f, sci['neg_ll'], info)
-    assert np.abs(g).max() < 1e-3
+    # (both optimisers stop on scipy's relative-decrease rule, 2.2e-9: the objective is flat in the
+    # blink rates, so the remaining gradient is small but not tiny)
+    assert np.abs(g).max() < 5e-2 and f <= sci['neg_ll'] + 1e-7 * abs(sci['neg_ll'])
     new = p53em.m_step(s, None, m.genetic_code, prm['kappa'], prm['omega'], prm['A'], prm['C'], prm['G'],
             prm['T'], 1.5, 0.5, np.maximum(pm.rate[1:], 1e-6))
     assert new['where'].startswith('device')

@@ -44,16 +44,16 @@ def test_forward_statistics_match_exact_prior(nb):
 def test_prior_is_invariant_under_the_sweep_p53_shape(nb):
     pm = packing.PackedModel(p53.p53_model())
     fwd, mcmc = [], []
-    for seed in range(4):
-        s = nb.BlinkSampler(pm, validate=True)
-        s.forward_sample(16384, seed=100 + seed)
+    for seed in range(16):
+        s = nb.BlinkSampler(pm, validate=(seed < 4))
+        s.forward_sample(4096, seed=100 + seed)
         s.reset_summary()
         s.summarize_current()
         fwd.append(gu.scalar_functionals(s.summary()))
         s.reset_summary()
         s.sweep(6, accumulate=True)              # also validates every invariant after every phase
         sm = s.summary()
-        assert sm.nsamples == 16384 * 6
+        assert sm.nsamples == 4096 * 6
         mcmc.append(gu.scalar_functionals(sm))
         s.close()
     for name in fwd[0]:

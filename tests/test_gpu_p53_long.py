@@ -41,15 +41,15 @@ def test_per_edge_statistics_against_long_reference_run(nb, fname, f64):
     data = packing.pack_alignment(pm, np.array([rec['leaf_states']]),
             np.array([rec['tol_true_ok']], dtype=np.uint32), np.array([rec['tol_false_ok']], dtype=np.uint32))
     mats, roots = [], []
-    nseeds = 4
+    nseeds = 16
     for seed in range(nseeds):
-        s = nb.BlinkSampler(pm, validate=True, msg_f64=f64)
+        s = nb.BlinkSampler(pm, validate=(seed < 2), msg_f64=f64)
         s.set_data(data)
-        s.init_chains(chains=4096, seed=900 + seed)
+        s.init_chains(chains=1024, seed=900 + seed)
         s.sweep(50, accumulate=False)
         s.sweep(25, accumulate=True)
         sm = s.summary()
-        assert sm.nsamples == 4096 * 25
+        assert sm.nsamples == 1024 * 25
         mats.append(_edge_matrix(sm))
         roots.append((sm.root_off_count / float(sm.nsamples), sm.root_xon_count / float(sm.nsamples)))
         s.close()
