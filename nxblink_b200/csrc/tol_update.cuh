@@ -217,12 +217,11 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
     NxbXo xo = L.xo;
     int bad = 0, cnt = 0;
     {
-        // thinning acceptance as integer thresholds: accept iff u32 <= thr (an acceptance
-        // probability of exactly 1 becomes 1 - 2^-32)
-        const unsigned thr_o0 = (unsigned)fmin(ml.acc_blk[0] * 4294967296.0, 4294967295.0);
-        const unsigned thr_o1 = (unsigned)fmin(ml.acc_blk[1] * 4294967296.0, 4294967295.0);
-        const unsigned thr_w0 = (unsigned)fmin(ml.acc_blk[2] * 4294967296.0, 4294967295.0);
-        const unsigned thr_w1 = (unsigned)fmin(ml.acc_blk[3] * 4294967296.0, 4294967295.0);
+        // Candidate rate = omega - (rate out of the OLD state), poisson.py:176-199: piecewise constant
+        // along the old trajectory, 0 in own-class segments (inert events, tol_tables.h).  The
+        // arrivals are exponential gaps at the rate of the current piece, restarted where the
+        // piece changes (a retained event, a primary event that changes the own flag): no thinning.
+        const float gf_off = (float)(1.0 / ml.acc_blk[0]), gf_on = (float)(1.0 / ml.acc_blk[1]);
         const MSG a_on = (MSG)ml.a_on, a_off = (MSG)ml.a_off;
         int e = trk ? E - 1 : -1;
         int io = ohi - 1;              // cursor into the retained events (descending)
@@ -264,16 +263,16 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
                     tcand = draw_gap ? tcur : -NXB_INF;
                     fresh = false;
                 }
+                const bool own = (c.cls[s] == k);
                 if (draw_gap) {
-                    tcand -= tol_gap<MSG>(xo, gsc, k + 1);
-                    if (!(tcand > tma)) tcand = -NXB_INF;
+                    tcand -= tol_gap<MSG>(xo, gsc * (xold ? gf_on : gf_off), k + 1);
+                    if (own || !(tcand > tma)) tcand = -NXB_INF;
                 }
                 const double tp = (ip >= ip0) ? u.ptm[ip] : -NXB_INF;
                 const bool haso = (io >= olo) && (u.bedge(io) == (unsigned)e);
                 const double to = haso ? u.btm[io] : -NXB_INF;
                 const double tf = dmax2(to, tcand);
                 const double tnext = dmax2(dmax2(tp, tf), tma);
-                const bool own = (c.cls[s] == k);
                 // chunking.py:67-79: own class forces ON; ON pays the rate into class k
                 pen += c.qm[s * K + k] * rate * (tcur - tnext);
                 if (own) u0 = 0;
@@ -295,15 +294,18 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
                     fresh = true;
                 } else if (tf > tp) {
                     bool live = true;
-                    if (to > tcand) { xold ^= 1u; --io; }
-                    else {
-                        const unsigned thr = own ? (xold ? thr_w1 : thr_w0) : (xold ? thr_o1 : thr_o0);
+                    if (to > tcand) {
+                        // the old trajectory changes state here: new piece, new candidate rate
+                        // (a retained event on an edge without events -- only an initial trajectory
+                        // from outside can hold one -- leaves the candidate slot empty)
+                        xold ^= 1u; --io;
+                        tcand = gsc > 0.f ? tnext : -NXB_INF;
+                    } else {
                         // (a candidate that ties with a retained event is dropped: probability ~2^-50)
-                        live = (nxb_xo_next(xo) < thr) && (tcand != to);
-                        // next arrival of the dominating process (rootward): drawn by the next step;
-                        // until then the candidate slot is empty
-                        gap_due = true;
+                        live = (tcand != to);
                     }
+                    // next arrival (rootward): drawn by the next step, from this point on
+                    gap_due = gsc > 0.f;
                     if (live) {
                         // (messages are scale-free: with OFF impossible the factor is a pure rescaling
                         // and is dropped, so that a long own-class segment cannot underflow ON to 0)
@@ -336,6 +338,7 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
                 } else {
                     s = (int)((u.pcode[ip] >> 16) & 0xffu);     // rootward: the state before the event
                     --ip;
+                    if ((c.cls[s] == k) != own) { tcand = tnext; gap_due = gsc > 0.f; }   // the own flag changes: new piece
                 }
             }
         }
