@@ -30,6 +30,7 @@ NXB_DEV int nxb_float_as_int(float x) { return __float_as_int(x); }
 NXB_DEV float nxb_int_as_float(int x) { return __int_as_float(x); }
 NXB_DEV long long nxb_double_as_ll(double x) { return __double_as_longlong(x); }
 NXB_DEV double nxb_ll_as_double(long long x) { return __longlong_as_double(x); }
+NXB_DEV int nxb_clzll(unsigned long long x) { return __clzll((long long)x); }
 NXB_DEV void nxb_atomic_or_shared(unsigned* a, unsigned v) { atomicOr(a, v); }
 NXB_DEV void nxb_atomic_add_shared(unsigned* a, unsigned v) { atomicAdd(a, v); }
 NXB_DEV void nxb_atomic_add_f64(double* a, double v) { atomicAdd(a, v); }
@@ -62,6 +63,7 @@ NXB_DEV int nxb_float_as_int(float x) { int i; memcpy(&i, &x, 4); return i; }
 NXB_DEV float nxb_int_as_float(int i) { float x; memcpy(&x, &i, 4); return x; }
 NXB_DEV long long nxb_double_as_ll(double x) { long long i; memcpy(&i, &x, 8); return i; }
 NXB_DEV double nxb_ll_as_double(long long i) { double x; memcpy(&x, &i, 8); return x; }
+NXB_DEV int nxb_clzll(unsigned long long x) { return x ? __builtin_clzll(x) : 64; }
 NXB_DEV void nxb_atomic_or_shared(unsigned* a, unsigned v) { *a |= v; }
 NXB_DEV void nxb_atomic_add_shared(unsigned* a, unsigned v) { *a += v; }
 NXB_DEV void nxb_atomic_add_f64(double* a, double v) { *a += v; }

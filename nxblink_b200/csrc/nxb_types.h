@@ -64,6 +64,7 @@ struct NxbModelLayout {
     int off_cls;        // u8     [P]
     int off_pi;         // f64    [P]
     int off_qm;         // f64    [P*K] dense Q_meta (model.py:93-106)
+    int off_ancmask;    // u64    [N]   edges on the path root -> node (bit e = edge e; only used when E <= 64)
     int off_clsmask;    // u64    [K]   states belonging to class k
     int ell_w;          // padded row width of the ELL copy of Q (max out-degree)
     int off_ell_info;   // u16    [ell_w*64] column | class << 8, transposed: [w][row]

@@ -813,7 +813,64 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
     const int n_mine = packed & 0xffff, n_live = packed >> 16;
     int total;
     int dst = warp_excl_scan(n_mine, lane, total);
-    for (int v = lane; v < N; v += 32) c.node_tol[v] = newtol_own[v];
+    if (tol_event_driven(c.E)) {
+        // The event-driven downward pass (tol_down_ev) sampled the node states only below the edges
+        // on which a track has live events.  hasev[e] = those tracks, from the evm words the lanes
+        // left in their dead accumulator records; an event-free edge hands the upper node's state
+        // down, so every node takes, per track, the bits of its nearest ancestor that has them
+        // (lane = node, at most depth steps); then the OFF dwell of the tracks that are OFF
+        // throughout an event-free edge (summary.py:123-131), lane = edge.  (tol_fill_scalar is the
+        // scalar statement of the same, checked by the host simulation.)
+        const int E = c.E, P = c.P;
+        const unsigned ALLK = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
+        const SPtr<unsigned> hasev = {c.wbase + wl.off_nrec};          // (the per-edge records of the upward walk are dead)
+        const SPtr<const AccRec<MSG> > acc = {c.wbase + wl.off_acc};
+        const SPtr<const NxbEdgeRec> erec = {(unsigned)p.ml.off_edgerec};
+        __syncwarp();
+        unsigned long long evm_k = 0ull;
+        if (lane < K) evm_k = *reinterpret_cast<const unsigned long long*>(&acc[lane]);
+        for (int e = 0; e < E; ++e) {
+            const unsigned h = __ballot_sync(FULL, (unsigned)(evm_k >> e) & 1u);
+            if (lane == (e & 31)) hasev[e] = h;
+        }
+        __syncwarp();
+        for (int v = lane; v < N; v += 32) {
+            unsigned need = (v == 0) ? 0u : (ALLK & ~hasev[v - 1]);
+            unsigned bits = newtol_own[v] & ~need;
+            int cur = v;
+            while (need) {
+                cur = erec[cur - 1].va;
+                const unsigned known = (cur == 0) ? ALLK : hasev[cur - 1];
+                bits |= newtol_own[cur] & need & known;
+                need &= ~known;
+            }
+            c.node_tol[v] = bits;
+        }
+        __syncwarp();
+        if (accumulate) {
+            const NxbSummaryLayout& sl = p.sl;
+            for (int e = lane; e < E; e += 32) {
+                const unsigned offm = ~c.node_tol[e + 1] & ~hasev[e] & ALLK;
+                if (!offm) continue;
+                const NxbEdgeRec er = erec[e];
+                double t = er.tma;
+                int s = c.node_pri[er.va];
+                const int i1 = c.poff[e + 1];
+                for (int i = c.poff[e]; i <= i1; ++i) {
+                    const bool last = i == i1;
+                    const double te = last ? er.tmb : c.ptm[i];
+                    const double dt = te - t;
+                    if (dt > 0.0) {
+                        double* const cell = p.dwell + (sl.d_off + (e * P + s) * K);
+                        for (unsigned m = offm; m; m &= m - 1u) atomicAdd(cell + (__ffs(m) - 1), dt);
+                    }
+                    if (!last) { s = (int)((c.pcode[i] >> 24) & 0xffu); t = te; }
+                }
+            }
+        }
+    } else {
+        for (int v = lane; v < N; v += 32) c.node_tol[v] = newtol_own[v];
+    }
     if (accumulate && lane == 0) {
         int on = __popc(newtol_own[0]);
         atomicAdd(&c.s_root_misc[0], (unsigned long long)on);

@@ -13,7 +13,7 @@
 
 // Fills the tolerance-update fields of `ml` (nslots, a_on/a_off, acc_blk, p_on/p_off and the off_*
 // of the tables below) and appends to `blob`:
-//   NxbEdgeRec[E], slot int[N], cls u8[P], qm f64[P*K]
+//   NxbEdgeRec[E], slot int[N], cls u8[P], qm f64[P*K], ancmask u64[N]
 // ml.N/E/P/K must be set.  Returns 0, or 1 with a message.
 static inline int nxb_build_tol_tables(const nxb_model_desc* d, NxbModelLayout& ml,
                                        std::vector<unsigned char>& blob, std::string& err, int pcdf_cap = 0) {
@@ -87,6 +87,15 @@ static inline int nxb_build_tol_tables(const nxb_model_desc* d, NxbModelLayout& 
         for (int i = d->q_ptr[s]; i < d->q_ptr[s + 1]; ++i)
             qm[(size_t)s * K + d->state_class[d->q_col[i]]] += d->q_val[i];
     ml.off_qm = put(qm.data(), 8 * P * K, 8);
+    // Edges on the path from the root to every node, as a bit mask (event-driven downward pass of
+    // tol_update.cuh: the nearest ancestor edge on which a track has a live event is the highest
+    // set bit of (edges with events) & ancmask, because parents are numbered before children).
+    {
+        std::vector<unsigned long long> anc(N, 0ull);
+        for (int v = 1; v < N; ++v)
+            anc[v] = anc[d->parent[v]] | ((v - 1 < 64) ? (1ull << (v - 1)) : 0ull);
+        ml.off_ancmask = put(anc.data(), 8 * N, 8);
+    }
     // ---- candidate generator of the event-parallel update (tol_par.cuh) ----
     {
         std::vector<NxbGenRec> g(E);

@@ -161,6 +161,7 @@ template <typename MSG> struct TolLane {
     bool trk, accum;
     int bad;                // 1: infeasible, 2: pool overflow
     int cnt;                // live events pushed by the upward pass
+    unsigned long long evm; // edges on which this track has a live event (bit e; E <= 64 only)
     LiveEv<MSG>* cev;       // this track's region of the pool
     NxbXo xo;               // per-track sequential stream: candidate gaps, thinning and backward-sampling decisions
 };
@@ -185,7 +186,7 @@ NXB_DEV void tol_begin(const TolCtx& c, TolLane<MSG>& L, TolUnit<MSG, SPLIT>& u,
     L.cev = (LiveEv<MSG>*)(ugb + p.g_off_ctm) + (size_t)L.k * p.gcapC;
     L.trk = has_job && u.uhdr[0] != 0;
     L.accum = L.trk && u.uhdr[6] != 0;
-    L.bad = 0; L.cnt = 0;
+    L.bad = 0; L.cnt = 0; L.evm = 0ull;
     NxbU4 r = nxb_philox_call((unsigned)u.uhdr[3], (unsigned)u.uhdr[5],
                               NXB_STREAM_BLK_FFBS | ((unsigned)L.k << 16), 0u, c.k0, c.k1);
     L.xo.s0 = r.x; L.xo.s1 = r.y; L.xo.s2 = r.z; L.xo.s3 = r.w | 1u;
@@ -216,6 +217,7 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
     const int olo = trk ? u.toff[k] : 0, ohi = trk ? u.toff[k + 1] : 0;
     NxbXo xo = L.xo;
     int bad = 0, cnt = 0;
+    unsigned long long evm = 0ull;
     {
         // Candidate rate = omega - (rate out of the OLD state), poisson.py:176-199: piecewise constant
         // along the old trajectory, 0 in own-class segments (inert events, tol_tables.h).  The
@@ -328,6 +330,7 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
                             nxb_ev_store(cev + cnt, ev);
                         } else bad = 2;
                         ++cnt;
+                        evm |= 1ull << (e & 63);
                         // uniformized 2x2 matrix of this context (poisson.py:92-96)
                         if (own) { u0 = (MSG)0.5 * l0 + (MSG)0.5 * l1; u1 = l1; }
                         else {
@@ -344,6 +347,7 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
         }
     }
     L.cnt = cnt;
+    L.evm = evm;
     // ---- root draw (prior: toymodel.py:17-27 get_blink_distn) ----
     unsigned x = 0u;
     if (trk) {
@@ -368,7 +372,7 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
 // and transition statistics are fused in (summary.py:123-131,234-243).
 // ---------------------------------------------------------------------------------------------
 template <typename MSG, bool SPLIT>
-NXB_DEV void tol_down(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPLIT>& u, unsigned x) {
+NXB_DEV void tol_down_walk(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPLIT>& u, unsigned x) {
     typedef TolMath<MSG> M;
     const NxbSweepParams& p = *c.p;
     const NxbModelLayout& ml = p.ml;
@@ -457,6 +461,166 @@ NXB_DEV void tol_down(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPLIT
         if (L.bad | bad) nxb_atomic_or_shared((unsigned*)&u.uhdr[4], (unsigned)(L.bad | bad));
     }
     L.xo = xo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// B2, event-driven form (trees with E <= 64; the walk above serves larger ones).  On an edge
+// without a live event the track keeps the state of the upper node, so the lane only visits the
+// edges on which it has live events (a third of the boundaries of the full walk at the p53 shape):
+// the state at the top of such an edge is the state below the nearest ancestor edge with events --
+// the highest set bit of evm & ancmask[va], already sampled because edges are taken in ascending
+// order -- or the root's.  What the walk did on the edges that are skipped here is done once per
+// unit, bit-parallel over the tracks, by tol_fill_* (node states below event-free edges, OFF dwell
+// of the tracks that are OFF throughout such an edge).  Same draws in the same order as the walk:
+// the sampled trajectory is identical.
+// ---------------------------------------------------------------------------------------------
+template <typename MSG, bool SPLIT>
+NXB_DEV void tol_down_ev(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPLIT>& u) {
+    typedef TolMath<MSG> M;
+    const NxbSweepParams& p = *c.p;
+    const NxbModelLayout& ml = p.ml;
+    const NxbSummaryLayout& sl = p.sl;
+    const int P = c.P, K = c.K, k = L.k;
+    const bool trk = L.trk, accum_u = L.accum;
+    const SPtr<const NxbEdgeRec> erec = {(unsigned)ml.off_edgerec};
+    const SPtr<const unsigned long long> ancm = {(unsigned)ml.off_ancmask};
+    LiveEv<MSG>* const cev = L.cev;
+    NxbXo xo = L.xo;
+    const int cnt = (L.bad & 2) ? 0 : L.cnt;
+    const unsigned long long evm = (L.bad & 2) ? 0ull : L.evm;
+    int bad = 0;
+    int wtop = cnt - 1;            // survivors overwrite consumed records, from the last one down
+    {
+        const MSG a_on_f = (MSG)ml.a_on, a_off1_f = (MSG)(1.0 - ml.a_off);
+        int ir = cnt - 1;              // read cursor (descending)
+        bool fresh = true;
+        bool act = trk && ir >= 0;
+        int e = 0, s = 0, ip = 0, ipe = 0, n_on = 0, n_off = 0;
+        unsigned x = 0u;
+        double tmb = 0.0, tcur = 0.0, offtime = 0.0;
+        LiveEv<MSG> pf;
+        pf.t = NXB_INF; pf.q = 0; pf.e = 0xffffu; pf.pad = 0;
+        nxb_ev_pad(pf);
+        if (ir >= 0) pf = nxb_ev_load(cev + ir);
+        while (TOL_ANY(act)) {
+            if (act) {
+                if (fresh) {
+                    e = (int)pf.e;
+                    const NxbEdgeRec er = erec[e];
+                    const int va = er.va;
+                    const unsigned long long m = evm & ancm[va];
+                    const int a = 64 - nxb_clzll(m);       // node below the nearest ancestor edge with events; 0: the root
+                    x = (u.newtol[a] >> k) & 1u;
+                    s = u.node_pri[va];
+                    ip = u.poff[e]; ipe = u.poff[e + 1];
+                    tcur = er.tma; tmb = er.tmb;
+                    offtime = 0.0; n_on = 0; n_off = 0;
+                    fresh = false;
+                }
+                const double tp = (ip < ipe) ? u.ptm[ip] : NXB_INF;
+                const double tc = ((int)pf.e == e) ? pf.t : NXB_INF;
+                const double tnext = dmin2(dmin2(tp, tc), tmb);
+                if (!x) offtime += tnext - tcur;
+                tcur = tnext;
+                if (tc < tp) {
+                    const MSG l1 = pf.q, l0 = (MSG)1 - pf.q;
+                    --ir;
+                    // (the record at ir is in registers before a survivor may overwrite it: wtop >= ir)
+                    if (ir >= 0) pf = nxb_ev_load(cev + ir);
+                    else { pf.t = NXB_INF; pf.e = 0xffffu; }
+                    const bool own = (c.cls[s] == k);
+                    const MSG p1 = own ? (x ? (MSG)1 : (MSG)0.5) : (x ? a_off1_f : a_on_f);
+                    const MSG w1 = p1 * l1, w0 = ((MSG)1 - p1) * l0;
+                    if (!(w0 + w1 > (MSG)0)) TOL_BAD(bad, 4);
+                    const MSG uu = M::uniform(xo);
+                    const unsigned xn = (uu * (w0 + w1) < w1) ? 1u : 0u;
+                    if (xn != x) {
+                        LiveEv<MSG> sv;
+                        sv.t = tc; sv.q = 0; sv.e = (unsigned short)(e | (xn ? CE_NEW1 : 0u)); sv.pad = 0;
+                        nxb_ev_pad(sv);
+                        nxb_ev_store(cev + wtop, sv);
+                        --wtop;
+                        if (xn) ++n_on; else ++n_off;
+                        x = xn;
+                    }
+                } else {
+                    // primary event or the bottom of the edge: close the OFF-time segment
+                    if (accum_u && offtime > 0.0)
+                        nxb_atomic_add_f64(p.dwell + (sl.d_off + (e * P + s) * K + k), offtime);
+                    offtime = 0.0;
+                    if (tp != NXB_INF) {
+                        s = (int)((u.pcode[ip] >> 24) & 0xffu);
+                        ++ip;
+                    } else {
+                        if (accum_u && n_on) nxb_atomic_add_shared((unsigned*)&c.s_off_on[e], (unsigned)n_on);
+                        if (accum_u && n_off) nxb_atomic_add_shared((unsigned*)&c.s_off_on[e] + 1, (unsigned)n_off);
+                        if (x) nxb_atomic_or_shared(&u.newtol[e + 1], 1u << k);
+                        fresh = true;
+                        act = ir >= 0;
+                    }
+                }
+            }
+        }
+    }
+    if (trk) {
+        u.uhdr[10 + k] = (cnt - 1 - wtop) | (cnt << 16);   // survivors of this track | live events
+        if (L.bad | bad) nxb_atomic_or_shared((unsigned*)&u.uhdr[4], (unsigned)(L.bad | bad));
+        // the track's accumulator records are dead: its slot-0 record carries evm to tol_fill_*
+        *reinterpret_cast<unsigned long long*>(&u.acc[k]) = evm;
+    }
+    L.xo = xo;
+}
+
+// (TOL_FORCE_WALK: test builds of the host simulation that keep the full walk, to compare with)
+NXB_DEV bool tol_event_driven(int E) {
+#if defined(TOL_FORCE_WALK)
+    (void)E; return false;
+#else
+    return E <= 64;
+#endif
+}
+
+template <typename MSG, bool SPLIT>
+NXB_DEV void tol_down(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPLIT>& u, unsigned x) {
+    if (tol_event_driven(c.E)) tol_down_ev<MSG, SPLIT>(c, L, u);
+    else tol_down_walk<MSG, SPLIT>(c, L, u, x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// What tol_down_ev leaves to do, for ONE unit after all of its tracks are done (E <= 64): scalar
+// form for the host simulation; blink_finish (sweep_kernel.cuh) does the same with a warp.
+//   hasev[e]   = tracks with a live event on edge e (from the evm words left in the accumulators)
+//   node_out[v] = sampled tolerance states of node v: its own bits where hasev[v-1] is set (or v
+//                is the root), else those of the nearest ancestor that has them
+//   OFF dwell of the tracks that are OFF throughout an event-free edge (summary.py:123-131)
+// ---------------------------------------------------------------------------------------------
+template <typename MSG, bool SPLIT>
+NXB_DEV void tol_fill_scalar(const TolCtx& c, const TolUnit<MSG, SPLIT>& u, bool accum, unsigned* node_out) {
+    const NxbSweepParams& p = *c.p;
+    const int E = c.E, P = c.P, K = c.K, N = E + 1;
+    const unsigned ALLK = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
+    const SPtr<const NxbEdgeRec> erec = {(unsigned)p.ml.off_edgerec};
+    node_out[0] = u.newtol[0];
+    for (int v = 1; v < N; ++v) {
+        const int e = v - 1;
+        unsigned h = 0u;
+        for (int k = 0; k < K; ++k)
+            h |= (unsigned)((*reinterpret_cast<const unsigned long long*>(&u.acc[k]) >> e) & 1ull) << k;
+        const int va = erec[e].va;
+        node_out[v] = (u.newtol[v] & h) | (node_out[va] & ~h & ALLK);
+        const unsigned offm = ~node_out[v] & ~h & ALLK;
+        if (!accum || !offm) continue;
+        double t = erec[e].tma;
+        int s = u.node_pri[va];
+        for (int i = u.poff[e]; i <= u.poff[e + 1]; ++i) {
+            const bool last = i == u.poff[e + 1];
+            const double te = last ? erec[e].tmb : u.ptm[i];
+            if (te - t > 0.0)
+                for (int k = 0; k < K; ++k)
+                    if ((offm >> k) & 1u) nxb_atomic_add_f64(p.dwell + (p.sl.d_off + (e * P + s) * K + k), te - t);
+            if (!last) { s = (int)((u.pcode[i] >> 24) & 0xffu); t = te; }
+        }
+    }
 }
 
 }  // namespace nxb

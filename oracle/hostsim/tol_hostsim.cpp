@@ -145,7 +145,15 @@ static int run(const nxb_model_desc* d, hs_unit* un, uint64_t seed, uint32_t uni
         }
     }
     un->n_blk = dst;
-    for (int v = 0; v < N; ++v) un->node_tol[v] = newtol[v];
+    if (tol_event_driven(E)) {
+        // the event-driven downward pass leaves the event-free edges to the per-unit fill-in
+        TolUnit<MSG, true> uu;
+        uu.bind(ub, wl);
+        std::vector<unsigned> filled(N, 0u);
+        tol_fill_scalar<MSG, true>(tc, uu, accumulate != 0, filled.data());
+        for (int v = 0; v < N; ++v) un->node_tol[v] = filled[v];
+    } else
+        for (int v = 0; v < N; ++v) un->node_tol[v] = newtol[v];
     if (accumulate) {
         const unsigned long long* st = (const unsigned long long*)(nxb_smem + ml.off_stats);
         for (int e = 0; e < E; ++e) { off_on[e] += st[e] & 0xffffffffull; on_off[e] += st[e] >> 32; }

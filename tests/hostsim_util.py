@@ -19,18 +19,19 @@ class HsUnit(C.Structure):
             ('tt', C.c_void_p), ('tf', C.c_void_p)]
 
 
-_hs = None
+SO_WALK = os.path.join(ROOT, 'oracle', '_ref', 'libtol_hostsim_walk.so')
+_hs = {}
 
 
-def load():
-    global _hs
-    if _hs is None:
-        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle', 'hostsim')])
-        lib = C.CDLL(SO)
+def load(walk=False):
+    """walk=True: the comparison build whose downward pass is the full walk (TOL_FORCE_WALK)."""
+    if walk not in _hs:
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle', 'hostsim'), 'all'])
+        lib = C.CDLL(SO_WALK if walk else SO)
         lib.hostsim_tol_update.argtypes = [C.POINTER(nlib.ModelDesc), C.POINTER(HsUnit), C.c_uint64,
                 C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        _hs = lib
-    return _hs
+        _hs[walk] = lib
+    return _hs[walk]
 
 
 def forward_primary_path(pm, rng):
@@ -61,8 +62,8 @@ def forward_primary_path(pm, rng):
 class HostTolChain(object):
     """Repeated tolerance updates of one unit with a FIXED primary trajectory."""
 
-    def __init__(self, pm, node_pri, pri_events, tt, tf, msg_f64=False, seed=1, cap=4096):
-        self.lib = load()
+    def __init__(self, pm, node_pri, pri_events, tt, tf, msg_f64=False, seed=1, cap=4096, walk=False):
+        self.lib = load(walk)
         self.pm = pm
         self.desc = pm.desc()
         N, E, P, K = pm.n_nodes, pm.n_nodes - 1, pm.n_states, pm.n_classes

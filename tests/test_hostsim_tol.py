@@ -135,3 +135,26 @@ def test_tolerance_update_p53_shape():
     pm = packing.PackedModel(p53.p53_model())
     zs = _run(pm, False, nsweep=8000, seed=4, nsub=8, min_rate=0.05, burn=1000)
     assert max(zs.values()) <= 5.5, zs
+
+
+@pytest.mark.parametrize('msg_f64', [False, True], ids=['f32', 'f64'])
+def test_event_driven_downward_pass_samples_the_same_trajectory_as_the_full_walk(msg_f64):
+    """tol_down_ev (visits only the edges with live events, the rest is filled in per unit) against
+    tol_down_walk (every edge of every track): same random draws in the same order, so node states,
+    blink events and integer statistics are IDENTICAL sweep after sweep; the OFF dwell sums agree to
+    rounding (the additions come in another order)."""
+    for pm, seed in ((packing.PackedModel(p53.p53_model()), 11), (packing.PackedModel(toymodel.BlinkModelC), 5)):
+        rng = np.random.default_rng(seed)
+        node_pri, ev = hu.forward_primary_path(pm, rng)
+        tt, tf = _leaf_constraints(pm, node_pri, rng, min_rate=0.05)
+        a = hu.HostTolChain(pm, node_pri, ev, tt, tf, msg_f64=msg_f64, seed=seed)
+        b = hu.HostTolChain(pm, node_pri, ev, tt, tf, msg_f64=msg_f64, seed=seed, walk=True)
+        for i in range(300):
+            a.sweep(True)
+            b.sweep(True)
+            assert np.array_equal(a.node_tol, b.node_tol), i
+            ea, eb = a.blink_events(), b.blink_events()
+            assert all(np.array_equal(x, y) for x, y in zip(ea, eb)), i
+        assert np.array_equal(a.off_on, b.off_on) and np.array_equal(a.on_off, b.on_off)
+        assert a.doff.sum() > 0
+        np.testing.assert_allclose(a.doff, b.doff, rtol=1e-11, atol=1e-12)
