@@ -15,6 +15,7 @@
 
 #define NXB_MAX_THREADS 640
 #define NXB_TP_THREADS 640         /* tolpar_kernel: up to 20 warps (10 units x 2 warps at the p53 shape) */
+#define NXB_BLINK_GROUP_WARPS 5   /* independent warp groups of blink_kernel: 160 lanes = 8 units x 20 tracks at the p53 shape */
 #define NXB_BLINK_THREADS 800      /* 25 warps at 72 registers: 40 units x 20 tracks per CTA at the p53 shape */
 
 namespace nxb {
@@ -322,7 +323,8 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
 // Units that are elsewhere are skipped (the primary launch listed them for the next tier);
 // units whose events do not fit the shared-memory capacities are listed here.
 // ---------------------------------------------------------------------------
-template <typename MSG>
+// (25 warps are 7 on one SM sub-partition: 7 x 32 x 72 registers is what its 16 K file holds)
+template <typename MSG, int GWT>
 __global__ void __launch_bounds__(NXB_BLINK_THREADS, 1)
 blink_kernel(const __grid_constant__ NxbSweepParams p) {
     const NxbModelLayout& ml = p.ml;
@@ -331,14 +333,27 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
     Ctx c;
     cta_prologue(c, p, tid, lane);
     c.bar_id = 1; c.bar_threads = 32; c.nbar = 0; c.sync_mask = 0u;     // phase_sync: no-op
-    c.wing = warp; c.gwbase = (unsigned)p.smem_warp0;
-    const int N = ml.N, K = ml.K, U = p.batch_units;
-    unsigned char* const gb0 = p.gscratch + (long long)blockIdx.x * U * p.gscratch_stride;
+    c.gwbase = (unsigned)p.smem_warp0;
+    const int N = ml.N, K = ml.K;
+    // Independent warp groups (p.blink_groups > 1): G groups of W / G warps, each with its own
+    // batches of p.batch_units / G units, its own part of the unit regions and of the event pool,
+    // and a named barrier instead of __syncthreads: a group waits for the slowest of ITS walks
+    // only, and its load / set-up / write-back overlap the walks of the other groups.
+    // (GWT: warps per group at compile time, 0 = the whole CTA is one group)
+    const int GW = GWT ? GWT : W, G = GWT ? W / GWT : 1, U = GWT ? p.batch_units / G : p.batch_units;
+    const int grp = warp / GW, wing = warp - grp * GW, gtid = tid - grp * GW * 32;
+    const unsigned ub0 = (unsigned)(p.smem_warp0 + grp * U * wl.bytes);
+    unsigned char* const gb0 = p.gscratch + ((long long)blockIdx.x * p.batch_units + (long long)grp * U) * p.gscratch_stride;
     c.ggbase = gb0;
+    c.wing = wing;
+    auto group_sync = [&]() {
+        if (GWT == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)(threadIdx.x >> 5) / GWT), "n"(GWT * 32) : "memory");
+    };
     const long long n_work = p.unit_list ? (long long)p.n_list : p.n_units;
     unsigned long long* s_batch = (unsigned long long*)(nxb_smem + ml.off_stats) + ml.stats_words;
     auto bind = [&](int ui) {
-        c.wbase = (unsigned)(p.smem_warp0 + ui * wl.bytes);
+        c.wbase = ub0 + (unsigned)(ui * wl.bytes);
         c.gbase = gb0 + (long long)ui * p.gscratch_stride;
         c.node_tol.off = c.wbase + wl.off_node_tol;
         c.node_pri.off = c.wbase + wl.off_node_pri;
@@ -350,15 +365,15 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
         c.tmpa.off = c.wbase + wl.off_tmpa;
     };
     while (true) {
-        if (tid == 0) s_batch[0] = atomicAdd(p.work_counter, 1ull);
-        __syncthreads();
-        const long long w0 = (long long)s_batch[0] * U;
-        __syncthreads();
+        if (gtid == 0) s_batch[grp] = atomicAdd(p.work_counter, 1ull);
+        group_sync();
+        const long long w0 = (long long)s_batch[grp] * U;
+        group_sync();
         if (w0 >= n_work) break;
         if (p.prefetch_wave && !p.unit_list)
-            for (int ui = warp; ui < U; ui += W) prefetch_unit_slab(p, w0 + (long long)gridDim.x * U + ui, lane);
+            for (int ui = wing; ui < U; ui += GW) prefetch_unit_slab(p, w0 + (long long)gridDim.x * p.batch_units + ui, lane);
         // ---- load + set up the units of the batch ----
-        for (int ui = warp; ui < U; ui += W) {
+        for (int ui = wing; ui < U; ui += GW) {
             bind(ui);
             const long long widx = w0 + ui;
             bool active = false, accum = false;
@@ -399,13 +414,13 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
             if (lane == 0) uhdr[7] = (int)c.unit;
             tick(c, T_B0);
         }
-        __syncthreads();
+        group_sync();
         // ---- one (unit, track) job per lane ----
-        blink_job<MSG, true>(c, tid, U * K, (unsigned)p.smem_warp0, gb0);
-        __syncthreads();
+        blink_job<MSG, true>(c, gtid, U * K, ub0, gb0);
+        group_sync();
         tick(c, T_BW);          // (waiting for the slowest lane of the CTA is booked here)
         // ---- write the units back ----
-        for (int ui = warp; ui < U; ui += W) {
+        for (int ui = wing; ui < U; ui += GW) {
             bind(ui);
             SPtr<int> uhdr = {c.wbase + wl.off_uhdr};
             if (!uhdr[0]) continue;
@@ -427,7 +442,7 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
             __syncwarp();
             tick(c, T_STORE);
         }
-        __syncthreads();
+        group_sync();
     }
     cta_epilogue(c, p, tid);
 }
@@ -862,7 +877,7 @@ struct Tier {
     size_t smem;
     // split mode (tier 0 only): shared-memory layout of one unit in blink_kernel
     NxbWarpLayout bwl;
-    int blink_warps = 0, blink_units = 0, blink_warp0 = 0;
+    int blink_warps = 0, blink_units = 0, blink_warp0 = 0, blink_groups = 1;
     size_t blink_smem = 0;
     // event-parallel tolerance update (every steady-state tier): one unit per group of tp_wpu warps
     NxbTolLayout tl;
@@ -926,6 +941,7 @@ struct nxb_handle {
     int discard_pool = 1;                          // NXB_DISCARD_POOL
     int prefetch_wave = 1;                         // NXB_PREFETCH: L2 prefetch of the unit slabs one wave of work ahead
     int blink_ctas = 1;                            // co-resident blink_kernel CTAs per SM (NXB_BLINK_CTAS)
+    int blink_groups = 1;                          // NXB_BLINK_GROUPS=0: blink_kernel CTAs as one group (default: groups of 5 warps when the shape allows)
     int smem_per_sm = 0;
     bool sync_sweeps = false;                      // NXB_SYNC_SWEEPS=1: the host-synchronised split path (one wait per sweep)
     std::vector<cudaEvent_t> evpool;
@@ -1454,6 +1470,10 @@ static int configure_capacities(nxb_handle* h, const CapCfg& cfg) {
                         tier.blink_units = bu;
                         tier.blink_warps = std::min(bw, (bu * K + 31) / 32);
                         tier.blink_smem = (size_t)bfixed + (size_t)bu * tier.bwl.bytes;
+                        // independent warp groups (NXB_BLINK_GROUPS): whole warps and whole units per group
+                        const int g = tier.blink_warps / NXB_BLINK_GROUP_WARPS;
+                        tier.blink_groups = (h->blink_groups != 0 && g > 1 && g <= 15 && tier.blink_warps % NXB_BLINK_GROUP_WARPS == 0 &&
+                                             bu % g == 0 && (bu / g) * K <= 32 * NXB_BLINK_GROUP_WARPS) ? g : 1;
                     }
                 }
                 if (pass == 0 && h->tolpar) {
@@ -1582,6 +1602,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     if (const char* ev = getenv("NXB_DISCARD_POOL")) h->discard_pool = atoi(ev) != 0;
     if (const char* ev = getenv("NXB_PREFETCH")) h->prefetch_wave = atoi(ev) != 0;
     if (const char* ev = getenv("NXB_BLINK_CTAS")) h->blink_ctas = std::max(1, std::min(4, atoi(ev)));
+    if (const char* ev = getenv("NXB_BLINK_GROUPS")) h->blink_groups = atoi(ev) != 0;
     CUDA_TRY_C(cudaStreamCreate(&h->own_stream));
     h->stream = h->own_stream;
     CUDA_TRY_C(cudaEventCreate(&h->ev0));
@@ -1645,8 +1666,11 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
             ? cudaFuncSetAttribute(sweep_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
             : cudaFuncSetAttribute(sweep_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
         if (e1 == cudaSuccess) e1 = h->msg_f64
-            ? cudaFuncSetAttribute(blink_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
-            : cudaFuncSetAttribute(blink_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+            ? cudaFuncSetAttribute(blink_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
+            : cudaFuncSetAttribute(blink_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+        if (e1 == cudaSuccess) e1 = h->msg_f64
+            ? cudaFuncSetAttribute(blink_kernel<double, NXB_BLINK_GROUP_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
+            : cudaFuncSetAttribute(blink_kernel<float, NXB_BLINK_GROUP_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
         if (e1 != cudaSuccess) { set_err(nullptr, NXB_ERR_CUDA, cudaGetErrorString(e1)); nxb_destroy(h); return NXB_ERR_CUDA; }
     }
     if (h->msg_f64) {
@@ -1808,6 +1832,7 @@ static void fill_params(nxb_handle* h, NxbSweepParams& p, int kind, const Tier& 
     p.validate = h->validate;
     p.validate_only = (kind == KIND_CHECK) ? 1 : 0;
     p.batch_units = tier.blink_units;
+    p.blink_groups = tier.blink_groups;
     p.counts = h->d_counts; p.dwell = h->d_dwell; p.status = h->d_status;
     p.work_counter = h->d_work;
     p.perf = h->profile ? h->d_perf : nullptr;
@@ -1834,8 +1859,14 @@ static cudaError_t enqueue_kernel(nxb_handle* h, int kind, const Tier& tier, con
         }
     } else if (kind == KIND_BLINK) {
         int grid = (int)std::min<long long>((long long)h->num_sms * h->blink_ctas, (n_work + tier.blink_units - 1) / tier.blink_units);
-        if (h->msg_f64) blink_kernel<double><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
-        else blink_kernel<float><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
+        const bool grouped = tier.blink_groups > 1;          // groups of NXB_BLINK_GROUP_WARPS warps
+        if (h->msg_f64) {
+            if (grouped) blink_kernel<double, NXB_BLINK_GROUP_WARPS><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
+            else blink_kernel<double, 0><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
+        } else {
+            if (grouped) blink_kernel<float, NXB_BLINK_GROUP_WARPS><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
+            else blink_kernel<float, 0><<<std::max(grid, 1), tier.blink_warps * 32, tier.blink_smem, h->stream>>>(p);
+        }
     } else {
         const int gw = std::max(p.group_warps, 1);
         const int launch_warps = tier.warps / gw * gw;       // whole groups only

@@ -22,10 +22,13 @@ namespace nxb {
 // arithmetic instead of rebuilding 64-bit generic pointers inside the hot loops.
 extern __shared__ __align__(16) unsigned char nxb_smem[];
 
-NXB_DEV float nxb_fast_expf(float x) { return __expf(x); }
-NXB_DEV float nxb_fast_log2f(float x) { return __log2f(x); }
+// single MUFU forms (flush-to-zero variants: no range fix-ups around the instruction).  Their
+// callers keep the arguments in range: the logarithm sees (2^-24, 1), the exponential is clamped
+// from below afterwards, the divisor is a normalised message sum in [0.5, 2).
+NXB_DEV float nxb_fast_expf(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f)); return y; }
+NXB_DEV float nxb_fast_log2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 NXB_DEV float nxb_fast_exp2f(float x) { return exp2f(x); }
-NXB_DEV float nxb_fast_divf(float a, float b) { return __fdividef(a, b); }
+NXB_DEV float nxb_fast_divf(float a, float b) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return a * r; }
 NXB_DEV int nxb_float_as_int(float x) { return __float_as_int(x); }
 NXB_DEV float nxb_int_as_float(int x) { return __int_as_float(x); }
 NXB_DEV long long nxb_double_as_ll(double x) { return __double_as_longlong(x); }

@@ -76,6 +76,8 @@ struct NxbModelLayout {
     double inv_omega_pri;   // 1 / (2 * Rmax(all classes on))
     double acc_blk[4];      // thinning acceptance [own][fg state]
     double a_on, a_off;     // off-diagonal entries of the uniformized 2x2 blink matrix
+    float gf_off, gf_on;    // 1 / acc_blk[0], 1 / acc_blk[1]: mean-gap factors of the candidate process (old state OFF / ON)
+    float a_on_f, a_off_f, a_off1_f, pad_f;   // f32 copies of a_on, a_off, 1 - a_off (no conversions in the f32 walks)
     double p_on, p_off;     // blink prior at the root
     // event-parallel tolerance update (tol_par.cuh): the dominating Poisson process of all K
     // tracks laid out on one axis (track-major, edges in index order, rate-length units)
@@ -211,6 +213,7 @@ struct NxbSweepParams {
     int validate;                       // 1: check trajectory invariants after every phase
     int validate_only;                  // primary-only kernel: load, check, do nothing else
     int batch_units;                    // blink_kernel: units per CTA batch
+    int blink_groups;                   // blink_kernel: independent warp groups per CTA (each takes batch_units / groups units)
     unsigned long long* counts;
     double* dwell;
     int* status;                        // [4]: code, unit, detail, detail

@@ -62,6 +62,8 @@ static inline int nxb_build_tol_tables(const nxb_model_desc* d, NxbModelLayout& 
     // and saves 1/K of the live events (5 % at K = 20; a third at the toy models' K = 3).
     ml.acc_blk[2] = 0.0;                                  // own class, OFF (infeasible state)
     ml.acc_blk[3] = 0.0;                                  // own class, ON: inert events, dropped
+    ml.gf_off = (float)(1.0 / ml.acc_blk[0]); ml.gf_on = (float)(1.0 / ml.acc_blk[1]);
+    ml.a_on_f = (float)ml.a_on; ml.a_off_f = (float)ml.a_off; ml.a_off1_f = (float)(1.0 - ml.a_off); ml.pad_f = 0.f;
     ml.p_on = d->rate_on / (d->rate_on + d->rate_off);
     ml.p_off = d->rate_off / (d->rate_on + d->rate_off);
 

@@ -70,6 +70,9 @@ NXB_DEV void nxb_ev_pad(LiveEv<double>& e) { e.pad2 = 0u; e.pad3 = 0.0; }
 
 template <typename MSG> struct TolMath;
 template <> struct TolMath<float> {
+    static NXB_DEV float a_on(const NxbModelLayout& ml) { return ml.a_on_f; }
+    static NXB_DEV float a_off(const NxbModelLayout& ml) { return ml.a_off_f; }
+    static NXB_DEV float a_off1(const NxbModelLayout& ml) { return ml.a_off1_f; }
     // exp(-pen), never exactly 0: zeros in a message are HARD constraints (data, own class); a
     // penalty beyond the f32 range (exponent > 87) must not create one, or a unit whose OFF state is
     // excluded by data would turn infeasible.  Messages are rescaled by powers of two at every fold,
@@ -84,6 +87,9 @@ template <> struct TolMath<float> {
     static NXB_DEV float uniform(NxbXo& xo) { return (float)(nxb_xo_next(xo) >> 8) * (1.0f / 16777216.0f); }
 };
 template <> struct TolMath<double> {
+    static NXB_DEV double a_on(const NxbModelLayout& ml) { return ml.a_on; }
+    static NXB_DEV double a_off(const NxbModelLayout& ml) { return ml.a_off; }
+    static NXB_DEV double a_off1(const NxbModelLayout& ml) { return 1.0 - ml.a_off; }
     static NXB_DEV double expneg(double pen) { return fmax(exp(-pen), 2.2250738585072014e-308); }
     static NXB_DEV double div(double a, double b) { return a / b; }
     static NXB_DEV double pow2_rescale(double m) {
@@ -223,8 +229,8 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
         // along the old trajectory, 0 in own-class segments (inert events, tol_tables.h).  The
         // arrivals are exponential gaps at the rate of the current piece, restarted where the
         // piece changes (a retained event, a primary event that changes the own flag): no thinning.
-        const float gf_off = (float)(1.0 / ml.acc_blk[0]), gf_on = (float)(1.0 / ml.acc_blk[1]);
-        const MSG a_on = (MSG)ml.a_on, a_off = (MSG)ml.a_off;
+        const float gf_off = ml.gf_off, gf_on = ml.gf_on;
+        const MSG a_on = M::a_on(ml), a_off = M::a_off(ml);
         int e = trk ? E - 1 : -1;
         int io = ohi - 1;              // cursor into the retained events (descending)
         unsigned inited = 0u;          // live accumulator slots of this lane
@@ -386,7 +392,7 @@ NXB_DEV void tol_down_walk(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, 
     int bad = 0;
     int wtop = cnt - 1;            // survivors overwrite consumed records, from the last one down
     {
-        const MSG a_on_f = (MSG)ml.a_on, a_off1_f = (MSG)(1.0 - ml.a_off);
+        const MSG a_on_f = M::a_on(ml), a_off1_f = M::a_off1(ml);
         int e = trk ? 0 : E;
         int ir = cnt - 1;              // read cursor (descending)
         bool fresh = true;
@@ -491,7 +497,7 @@ NXB_DEV void tol_down_ev(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SP
     int bad = 0;
     int wtop = cnt - 1;            // survivors overwrite consumed records, from the last one down
     {
-        const MSG a_on_f = (MSG)ml.a_on, a_off1_f = (MSG)(1.0 - ml.a_off);
+        const MSG a_on_f = M::a_on(ml), a_off1_f = M::a_off1(ml);
         int ir = cnt - 1;              // read cursor (descending)
         bool fresh = true;
         bool act = trk && ir >= 0;
