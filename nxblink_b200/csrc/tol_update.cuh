@@ -331,7 +331,9 @@ NXB_DEV unsigned tol_up(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SPL
                             ev.t = tnext;
                             const MSG q = M::div(l1, l0 + l1);
                             ev.q = (l0 == (MSG)0) ? (MSG)1 : (q < (MSG)1 ? q : (MSG)1);
-                            ev.e = (unsigned short)e; ev.pad = 0;
+                            // pad = 1: first record of this edge, i.e. the LAST live event the downward pass
+                            // meets on it (it then closes the edge in the same step)
+                            ev.e = (unsigned short)e; ev.pad = (unsigned short)(((evm >> (e & 63)) & 1ull) ? 0u : 1u);
                             nxb_ev_pad(ev);
                             nxb_ev_store(cev + cnt, ev);
                         } else bad = 2;
@@ -523,13 +525,15 @@ NXB_DEV void tol_down_ev(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SP
                     offtime = 0.0; n_on = 0; n_off = 0;
                     fresh = false;
                 }
-                const double tp = (ip < ipe) ? u.ptm[ip] : NXB_INF;
+                double tp = (ip < ipe) ? u.ptm[ip] : NXB_INF;
                 const double tc = ((int)pf.e == e) ? pf.t : NXB_INF;
                 const double tnext = dmin2(dmin2(tp, tc), tmb);
                 if (!x) offtime += tnext - tcur;
                 tcur = tnext;
+                bool close = true;             // a primary event or the bottom of the edge ends an OFF-time segment
                 if (tc < tp) {
                     const MSG l1 = pf.q, l0 = (MSG)1 - pf.q;
+                    const bool last_here = pf.pad != 0;
                     --ir;
                     // (the record at ir is in registers before a survivor may overwrite it: wtop >= ir)
                     if (ir >= 0) pf = nxb_ev_load(cev + ir);
@@ -549,8 +553,12 @@ NXB_DEV void tol_down_ev(const TolCtx& c, TolLane<MSG>& L, const TolUnit<MSG, SP
                         if (xn) ++n_on; else ++n_off;
                         x = xn;
                     }
-                } else {
-                    // primary event or the bottom of the edge: close the OFF-time segment
+                    // nothing else on this edge (no further live event, no primary event): its bottom
+                    // is reached in the same step
+                    close = last_here && ip >= ipe;
+                    if (close && !x) offtime += tmb - tc;
+                }
+                if (close) {
                     if (accum_u && offtime > 0.0)
                         nxb_atomic_add_f64(p.dwell + (sl.d_off + (e * P + s) * K + k), offtime);
                     offtime = 0.0;
