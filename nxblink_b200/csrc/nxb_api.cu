@@ -418,7 +418,7 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
         // ---- one (unit, track) job per lane ----
         blink_job<MSG, true>(c, gtid, U * K, ub0, gb0);
         group_sync();
-        tick(c, T_BW);          // (waiting for the slowest lane of the CTA is booked here)
+        tick(c, T_BW);          // (waiting for the slowest lane of the group is booked here)
         // ---- write the units back ----
         for (int ui = wing; ui < U; ui += GW) {
             bind(ui);
@@ -428,11 +428,11 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
             c.unit = (long long)uhdr[7];
             const bool accum = uhdr[6] != 0;
             unsigned char* slab = p.state + c.unit * p.state_stride;
+            NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;     // (issued early: needed after blink_finish)
             int rc = blink_finish<MSG, true>(c, accum);          // new blink list written to the slab
             tick(c, T_BW);
             if (rc == RC_STATECAP) { if (lane == 0) ((NxbUnitHeader*)slab)->pad = 1u; continue; }
             if (rc == RC_ERROR) continue;
-            NxbUnitHeader hdr = *(const NxbUnitHeader*)slab;
             hdr.phase = NXB_PHASE_PRIMARY; hdr.sweeps_done++; hdr.pad = hdr.pad > 0u ? hdr.pad - 1u : 0u;
             hdr.n_blk = (uint16_t)c.nB;
             __syncwarp();

@@ -826,12 +826,15 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         const SPtr<unsigned> hasev = {c.wbase + wl.off_nrec};          // (the per-edge records of the upward walk are dead)
         const SPtr<const AccRec<MSG> > acc = {c.wbase + wl.off_acc};
         const SPtr<const NxbEdgeRec> erec = {(unsigned)p.ml.off_edgerec};
+        for (int e = lane; e < E; e += 32) hasev[e] = 0u;
         __syncwarp();
-        unsigned long long evm_k = 0ull;
-        if (lane < K) evm_k = *reinterpret_cast<const unsigned long long*>(&acc[lane]);
-        for (int e = 0; e < E; ++e) {
-            const unsigned h = __ballot_sync(FULL, (unsigned)(evm_k >> e) & 1u);
-            if (lane == (e & 31)) hasev[e] = h;
+        if (lane < K) {
+            unsigned long long m = *reinterpret_cast<const unsigned long long*>(&acc[lane]);
+            while (m) {
+                const int e = __ffsll((long long)m) - 1;
+                m &= m - 1ull;
+                atomicOr(&hasev[e], 1u << lane);
+            }
         }
         __syncwarp();
         for (int v = lane; v < N; v += 32) {
@@ -889,11 +892,19 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
         obtm = (double*)(slab + p.so_btm);
         obcode = (unsigned*)(slab + p.so_bcode);
     }
-    for (int q = 0; q < n_mine; ++q) {
-        const LiveEv<MSG> sv = nxb_ev_load(cev_own + (n_live - 1 - q));      // first survivor (rootmost, earliest) on top
-        const unsigned ce = sv.e;
-        obtm[dst + q] = sv.t;
-        obcode[dst + q] = (unsigned)(ce & CE_EDGE) | ((unsigned)lane << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);
+    // (two pool records in flight per lane: the copy is bound by the L2 latency of its loads)
+    for (int q0 = 0; q0 < n_mine; q0 += 2) {
+        LiveEv<MSG> sv[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (q0 + j < n_mine) sv[j] = nxb_ev_load(cev_own + (n_live - 1 - (q0 + j)));      // first survivor (rootmost, earliest) on top
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (q0 + j < n_mine) {
+                const unsigned ce = sv[j].e;
+                obtm[dst + q0 + j] = sv[j].t;
+                obcode[dst + q0 + j] = (unsigned)(ce & CE_EDGE) | ((unsigned)lane << 16) | ((ce & CE_NEW1) ? (1u << 31) : 0u);
+            }
     }
     __syncwarp();
     // The pool records of this sweep are dead now.  They live in the L2-resident scratch; tell L2
