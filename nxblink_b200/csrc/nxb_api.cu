@@ -14,6 +14,7 @@
 #include "tol_tables.h"
 
 #define NXB_MAX_THREADS 640
+#define NXB_LEAN_THREADS 768       /* LEAN primary-only kernel with f32 messages: 24 warps at 80 registers */
 #define NXB_TP_THREADS 640         /* tolpar_kernel: up to 20 warps (10 units x 2 warps at the p53 shape) */
 #define NXB_BLINK_GROUP_WARPS 5   /* independent warp groups of blink_kernel: 160 lanes = 8 units x 20 tracks at the p53 shape */
 #define NXB_BLINK_THREADS 800      /* 25 warps at 72 registers: 40 units x 20 tracks per CTA at the p53 shape */
@@ -111,7 +112,7 @@ __device__ __forceinline__ void prefetch_unit_slab(const NxbSweepParams& p, long
 // so `init` is a compile-time false there; both cut the code the hot kernel carries (11.7 k -> 8.5 k
 // SASS instructions, 96 -> 88 registers).
 template <typename MSG, bool PRIMARY_ONLY, bool LEAN>
-__global__ void __launch_bounds__(NXB_MAX_THREADS, 1)
+__global__ void __launch_bounds__((LEAN && sizeof(MSG) == 4) ? NXB_LEAN_THREADS : NXB_MAX_THREADS, 1)
 sweep_kernel(const __grid_constant__ NxbSweepParams p) {
     const bool p_init = !PRIMARY_ONLY && p.init;
     const bool p_validate = !LEAN && p.validate;
@@ -208,7 +209,8 @@ sweep_kernel(const __grid_constant__ NxbSweepParams p) {
             const unsigned long long* g_pri = p.pri_ok + site * N;
             const unsigned* g_tt = p.tol_true_ok + site * N;
             const unsigned* g_tf = p.tol_false_ok + site * N;
-            for (int v = lane; v < N; v += 32) { d_pri[v] = g_pri[v]; d_tt[v] = g_tt[v]; d_tf[v] = g_tf[v]; }
+            if (LEAN) { for (int v = lane; v < N; v += 32) d_pri[v] = g_pri[v]; }      // (the lean layout has no tolerance data)
+            else for (int v = lane; v < N; v += 32) { d_pri[v] = g_pri[v]; d_tt[v] = g_tt[v]; d_tf[v] = g_tf[v]; }
             c.nP = hdr.n_pri; c.nB = hdr.n_blk;
             if (hdr.phase != NXB_PHASE_INIT) {
                 const unsigned* g_tol = (const unsigned*)(slab + p.so_tol);
@@ -884,6 +886,10 @@ struct Tier {
     // split mode (tier 0 only): shared-memory layout of one unit in blink_kernel
     NxbWarpLayout bwl;
     int blink_warps = 0, blink_units = 0, blink_warp0 = 0, blink_groups = 1;
+    // tier 0: leaner layout and warp count of the LEAN primary-only kernel (asynchronous split path)
+    NxbWarpLayout pwl;
+    int pwarps = 0;
+    size_t psmem = 0;
     size_t blink_smem = 0;
     // event-parallel tolerance update (every steady-state tier): one unit per group of tp_wpu warps
     NxbTolLayout tl;
@@ -990,8 +996,11 @@ struct DevFree {
     ~DevFree() { for (void* q : ptrs) cudaFree(q); }
 };
 
+// lean: the layout of the LEAN primary-only kernel -- no tolerance data, no unit header, no
+// tolerance-update scratch, and the arrays of the FFBS passes (staging row, 1/(2 Rmax), uniforms)
+// alias the candidate arrays of P1, which are dead once the foreground events have been compacted.
 static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, int capB,
-                              int capR, int capF, int capC, NxbWarpLayout* wl) {
+                              int capR, int capF, int capC, NxbWarpLayout* wl, bool lean = false) {
     const int N = ml.N, E = ml.E, K = ml.K;
     int o = 0;
     auto take = [&](int bytes, int al) { o = align_up(o, al); int r = o; o += bytes; return r; };
@@ -1003,20 +1012,21 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     wl->off_btm = take(8 * capB, 8);
     wl->off_bcode = take(4 * capB, 4);
     wl->off_dpri = take(8 * N, 8);
-    wl->off_dtt = take(4 * N, 4);
-    wl->off_dtf = take(4 * N, 4);
+    wl->off_dtt = lean ? wl->off_dpri : take(4 * N, 4);
+    wl->off_dtf = lean ? wl->off_dpri : take(4 * N, 4);
     wl->off_boff = take(4 * (E + 1), 4);
     wl->off_poff = take(4 * (E + 1), 4);
     wl->off_tmpa = take(4 * (E + 1), 4);
     wl->off_tmpb = take(4 * (E + 1), 4);
     wl->off_tmpc = take(4 * (E + 1), 4);
-    wl->off_uhdr = take(4 * (10 + 32), 4);
+    wl->off_uhdr = lean ? 0 : take(4 * (10 + 32), 4);
     const int scratch0 = align_up(o, 16);
     // primary-phase scratch
     o = scratch0;
     wl->off_bord = take(2 * capB, 2);
     wl->off_rtm = take(8 * capR, 8);
     wl->off_rmask = take(4 * capR, 4);
+    const int cand_end = o;
     wl->off_ftm = take(8 * capF, 8);
     wl->off_fmask = take(4 * capF, 4);
     wl->off_fedge = take(2 * capF, 2);
@@ -1026,9 +1036,21 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     wl->off_toland = take(4 * (capF + 1), 4);
     wl->off_callow = take(8 * (capF + 1), 8);
     wl->off_cstate = take(capF + 1, 1);
-    wl->off_msg = take((msg_f64 ? 8 : 4) * NXB_PPAD, 16);     // one staging row; the messages are global
-    wl->off_finv = take((msg_f64 ? 8 : 4) * capF, 8);
-    wl->off_fu = take(8 * (capF + 1), 8);
+    {
+        const int msz = msg_f64 ? 8 : 4;
+        const int need = align_up(msz * NXB_PPAD, 8) + align_up(msz * capF, 8) + 8 * (capF + 1);
+        const int a0 = align_up(wl->off_rtm, 16);
+        if (lean && a0 + need <= cand_end) {
+            int oo = a0;
+            wl->off_msg = oo; oo += align_up(msz * NXB_PPAD, 8);
+            wl->off_finv = oo; oo += align_up(msz * capF, 8);
+            wl->off_fu = oo;
+        } else {
+            wl->off_msg = take(msz * NXB_PPAD, 16);     // one staging row; the messages are global
+            wl->off_finv = take(msz * capF, 8);
+            wl->off_fu = take(8 * (capF + 1), 8);
+        }
+    }
     const int end_pri = o;
     // blink-phase scratch (aliases the primary-phase scratch)
     o = scratch0;
@@ -1039,7 +1061,7 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     // validate_unit needs bord while the persistent state is live; it is only called
     // between phases, when either scratch is dead.
     const int end_blk = o;
-    wl->bytes = align_up(std::max(end_pri, end_blk), 16);
+    wl->bytes = align_up(lean ? end_pri : std::max(end_pri, end_blk), 16);
 }
 
 // Warps per lockstep group.  Several small groups per CTA drift out of phase, so the walks of
@@ -1458,6 +1480,16 @@ static int configure_capacities(nxb_handle* h, const CapCfg& cfg) {
                             t, pass, fixed, tier.wl.bytes, tier.wl.capP, tier.wl.capB, cR, cF, w, tier.warps);
                 tier.smem = (size_t)fixed + (size_t)tier.warps * tier.wl.bytes;
                 if (pass == 0 && t == 0) {
+                    build_warp_layout(ml, h->msg_f64, tier.wl.capP, tier.wl.capB, cR, cF, cC, &tier.pwl, true);
+                    {
+                        // f32 messages: 80 registers per thread leave room for 24 warps (6 per SM sub-partition)
+                        const int cap_w = (cfg.max_warps > 0) ? max_warps : (h->msg_f64 ? NXB_MAX_THREADS / 32 : NXB_LEAN_THREADS / 32);
+                        tier.pwarps = std::min((h->max_smem - fixed) / tier.pwl.bytes, cap_w);
+                        if (getenv("NXB_LEAN_WARPS")) tier.pwarps = std::min(tier.pwarps, std::max(1, atoi(getenv("NXB_LEAN_WARPS"))));
+                        tier.psmem = (size_t)fixed + (size_t)tier.pwarps * tier.pwl.bytes;
+                        if (getenv("NXB_DEBUG_LAYOUT"))
+                            fprintf(stderr, "lean primary layout: %d bytes per warp, %d warps\n", tier.pwl.bytes, tier.pwarps);
+                    }
                     build_blink_layout(ml, h->msg_f64, tier.wl.capP, tier.wl.capB, &tier.bwl);
                     const int bfixed = ml.blink_bytes + stats_bytes;      // model prefix + statistic partials
                     tier.blink_warp0 = bfixed;
@@ -1519,7 +1551,7 @@ static int configure_capacities(nxb_handle* h, const CapCfg& cfg) {
         // global scratch per warp slot: chunk messages + candidate pool
         {
             int max_w = 1;
-            for (auto& t : h->tiers) max_w = std::max(max_w, t.warps);
+            for (auto& t : h->tiers) max_w = std::max(max_w, std::max(t.warps, t.pwarps));
             for (auto& t : h->init_tiers) max_w = std::max(max_w, t.warps);
             max_w = std::max(max_w, h->tiers[0].blink_units * h->blink_ctas);
             h->gcapF = std::max((int)(boost * 8 * capF), E * cfg.diameter + 8);
@@ -1812,14 +1844,14 @@ static const char* status_text(int code) {
     }
 }
 
-enum { KIND_FUSED = 0, KIND_PRIMARY = 1, KIND_BLINK = 2, KIND_CHECK = 3 };
+enum { KIND_FUSED = 0, KIND_PRIMARY = 1, KIND_BLINK = 2, KIND_CHECK = 3, KIND_PRIMARY_LEAN = 4 };   // (LEAN: tier 0, pwl / pwarps)
 
 // Kernel parameters of one launch over `list` (or every unit).
 static void fill_params(nxb_handle* h, NxbSweepParams& p, int kind, const Tier& tier, int group_warps,
                         const int* list, int n_list, int* out, unsigned begin, unsigned target,
                         unsigned accum_from, int init) {
     memset(&p, 0, sizeof(p));
-    p.ml = h->ml; p.wl = (kind == KIND_BLINK) ? tier.bwl : tier.wl; p.sl = h->sl;
+    p.ml = h->ml; p.wl = (kind == KIND_BLINK) ? tier.bwl : (kind == KIND_PRIMARY_LEAN ? tier.pwl : tier.wl); p.sl = h->sl;
     p.smem_warp0 = tier.smem_warp0;
     const bool tolpar = kind == KIND_BLINK && h->tolpar && tier.tp_units > 0;
     if (kind == KIND_BLINK) {       // only the tolerance tables of the model are staged
@@ -1881,7 +1913,9 @@ static cudaError_t enqueue_kernel(nxb_handle* h, int kind, const Tier& tier, con
         }
     } else {
         const int gw = std::max(p.group_warps, 1);
-        const int launch_warps = tier.warps / gw * gw;       // whole groups only
+        const bool lean_layout = kind == KIND_PRIMARY_LEAN;
+        const int launch_warps = (lean_layout ? tier.pwarps : tier.warps) / gw * gw;       // whole groups only
+        const size_t smem = lean_layout ? tier.psmem : tier.smem;
         int grid = (int)std::min<long long>(h->num_sms, (n_work + launch_warps - 1) / launch_warps);
         grid = std::max(grid, 1);
         if (kind == KIND_FUSED) {
@@ -1890,11 +1924,11 @@ static cudaError_t enqueue_kernel(nxb_handle* h, int kind, const Tier& tier, con
         } else {
             const bool lean = !p.validate && !p.validate_only;
             if (h->msg_f64) {
-                if (lean) sweep_kernel<double, true, true><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
-                else sweep_kernel<double, true, false><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
+                if (lean) sweep_kernel<double, true, true><<<grid, launch_warps * 32, smem, h->stream>>>(p);
+                else sweep_kernel<double, true, false><<<grid, launch_warps * 32, smem, h->stream>>>(p);
             } else {
-                if (lean) sweep_kernel<float, true, true><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
-                else sweep_kernel<float, true, false><<<grid, launch_warps * 32, tier.smem, h->stream>>>(p);
+                if (lean) sweep_kernel<float, true, true><<<grid, launch_warps * 32, smem, h->stream>>>(p);
+                else sweep_kernel<float, true, false><<<grid, launch_warps * 32, smem, h->stream>>>(p);
             }
         }
     }
@@ -2033,7 +2067,11 @@ static int run_split(nxb_handle* h, unsigned target, unsigned accum_from) {
 static int run_split_async(nxb_handle* h, unsigned target, unsigned accum_from) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     const Tier& t0 = h->tiers[0];
-    const int gw = (h->lockstep < 0 && t0.warps >= 8) ? (t0.warps % 10 == 0 ? 10 : t0.warps / 2) : group_warps_for(h, t0.warps);
+    // primary-only launches: the LEAN kernel with its own layout and warp count.  Lockstep groups,
+    // measured at the p53 shape with 24 warps: 8 -> 8.98, 12 -> 9.11, 6 -> 9.95 ms per 4 sweeps of
+    // 131 072 units (20 warps: 10 -> 10.15)
+    const int pw = t0.pwarps;
+    const int gw = (h->lockstep < 0 && pw >= 8) ? (pw % 8 == 0 ? 8 : (pw % 10 == 0 ? 10 : pw / 2)) : group_warps_for(h, pw);
     const int nblind = (int)std::min<size_t>(2, h->tiers.size() - 1);
     if (h->evpool.empty()) {
         h->evpool.resize(4 * NXB_ASYNC_CHUNK);
@@ -2050,9 +2088,9 @@ static int run_split_async(nxb_handle* h, unsigned target, unsigned accum_from) 
             NxbSweepParams p;
             CUDA_TRY(h, cudaMemsetAsync(h->d_ctl, 0, 48, h->stream));
             CUDA_TRY(h, cudaEventRecord(h->evpool[4 * i + 0], h->stream));
-            fill_params(h, p, KIND_PRIMARY, t0, gw, nullptr, 0, lists[0], sw, sw + 1, accum_from, 0);
+            fill_params(h, p, KIND_PRIMARY_LEAN, t0, gw, nullptr, 0, lists[0], sw, sw + 1, accum_from, 0);
             p.work_counter = work + 0; p.defer_count = cnt + 0;
-            CUDA_TRY(h, enqueue_kernel(h, KIND_PRIMARY, t0, p, h->n_units));
+            CUDA_TRY(h, enqueue_kernel(h, KIND_PRIMARY_LEAN, t0, p, h->n_units));
             CUDA_TRY(h, cudaEventRecord(h->evpool[4 * i + 1], h->stream));
             fill_params(h, p, KIND_BLINK, t0, 1, nullptr, 0, lists[0], sw, sw + 1, accum_from, 0);
             p.work_counter = work + 1; p.defer_count = cnt + 0;
