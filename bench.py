@@ -414,10 +414,12 @@ def em_config(nb, torch, fp64_peak):
         t0 = time.perf_counter()
         r = f()
         return r, 1e3 * (time.perf_counter() - t0)
-    out = {}
+    PARTS = ('expm_48x61x61_ms', 'pruning_393_sites_ms', 'init_chains_ms', 'sweeps_20_ms', 'read_summary_ms', 'mstep_ms')
     s = nb.BlinkSampler(pm)
     s.set_data(data)
-    for rep in range(2):                       # the first repetition warms everything up
+    best = None
+    for rep in range(4):                       # the first repetition warms everything up; then the fastest of three
+        out = {}
         Pe, out['expm_48x61x61_ms'] = timed(lambda: dense.expm_batched(Q, t))
         _, out['pruning_393_sites_ms'] = timed(lambda: dense.pruning_loglik(pm.parent, Pe, pm.prior, data.pri_ok))
         _, out['init_chains_ms'] = timed(lambda: s.init_chains(chains=64, seed=rep))
@@ -434,10 +436,12 @@ def em_config(nb, torch, fp64_peak):
         out['mstep_where'] = res.get('where', 'host')
         if isinstance(res.get('result'), dict):
             out['mstep_kernel'] = res['result']
+        if rep >= 1 and (best is None or sum(v for k, v in out.items() if k in PARTS) < sum(v for k, v in best.items() if k in PARTS)):
+            best = dict(out)
+    out = best
     s.close()
     out['allreduce_ms'] = None         # one GPU; at N > 1 see `allreduce_ms_per_step` of the main figure
-    out['total_ms'] = sum(out[k] for k in ('expm_48x61x61_ms', 'pruning_393_sites_ms', 'init_chains_ms',
-        'sweeps_20_ms', 'read_summary_ms', 'mstep_ms'))
+    out['total_ms'] = sum(out[k] for k in PARTS)
     # dense kernels at bench size: kernel time from CUDA events inside the library call
     many = np.tile(t, 64)
     dense.expm_batched(Q, many)
@@ -463,7 +467,7 @@ def em_config(nb, torch, fp64_peak):
             'tflops': fl_prune / (k_prune * 1e-3) / 1e12, 'frac': fl_prune / (k_prune * 1e-3) / 1e12 / fp64_peak,
             'flops': '[64x64].[64x32] contraction per edge and tile of 32 sites'}}
     out['workload'] = ('EM iteration, p53-shaped codon blink model, 393 columns x 64 chains, 10 burn-in + 10 '
-            'sampling sweeps, wall ms of each host-API call (second repetition)')
+            'sampling sweeps, wall ms of each host-API call (the fastest of three repetitions after one warm-up)')
     return out
 
 
@@ -628,6 +632,8 @@ def run_gpu_arm(args, rank, local_rank, world):
                 'timing': 'torch CUDA events on the stream the kernels are launched on (nxb_set_stream), '
                     'max over ranks; kernels[] from the library\'s own events around each launch',
                 'warps_per_cta': st1['warps_per_cta'], 'ctas': st1['n_ctas'],
+                'kernels_note': 'warps_per_cta / smem_bytes_per_cta: the primary-only sweep_kernel; blink_kernel runs 25 warps '
+                    '(5 groups of 5 = 40 units x 20 tracks) per CTA at the p53 shape',
                 'smem_bytes_per_cta': st1['smem_bytes'],
                 'deferred_unit_launch_fraction': (st1['deferred_units'] - st0['deferred_units'])
                     / float(n_units * args.steps),

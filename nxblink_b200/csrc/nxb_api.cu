@@ -2421,7 +2421,11 @@ extern "C" int nxb_get_stats(nxb_handle* h, nxb_stats* o) {
     }
     o->data_bytes = h->n_sites * (int64_t)h->ml.N * 16;
     const Tier& t0 = h->tiers[0];
-    o->warps_per_cta = t0.warps; o->n_ctas = h->num_sms; o->smem_bytes = (int32_t)t0.smem;
+    // the kernel that a plain nxb_sweep launches for the primary update: the LEAN one with its own
+    // layout on the asynchronous split path, else the tier-0 kernel
+    const bool lean_path = h->split && !h->tolpar && !h->validate && !h->sync_sweeps && t0.blink_units > 0 && t0.pwarps > 0;
+    o->warps_per_cta = lean_path ? t0.pwarps : t0.warps; o->n_ctas = h->num_sms;
+    o->smem_bytes = (int32_t)(lean_path ? t0.psmem : t0.smem);
     o->n_tiers = (int32_t)h->tiers.size();
     o->capP = t0.wl.capP; o->capB = t0.wl.capB; o->capF = t0.wl.capF; o->capC = t0.wl.capC;
     o->deferred_units = h->deferred_total; o->kernel_launches = h->launches_total;

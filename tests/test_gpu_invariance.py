@@ -63,6 +63,25 @@ def test_capacity_tiers_and_geometry_do_not_change_results(nb):
         assert base[2]['n_pri_events'] == other[2]['n_pri_events']
 
 
+def test_warp_groups_and_lean_primary_kernel_do_not_change_results(nb, monkeypatch):
+    """blink_kernel as independent groups of 5 warps against one group per CTA (NXB_BLINK_GROUPS=0),
+    the LEAN primary-only kernel with 24 warps against 20 and 7 (NXB_LEAN_WARPS), all against the
+    validated path (non-LEAN kernel, one host wait per sweep): identical integer statistics."""
+    pm, data = _p53_inputs(40)
+    base = _run(nb, pm, data, chains=16, validate=True)
+    dflt = _run(nb, pm, data, chains=16)
+    monkeypatch.setenv('NXB_BLINK_GROUPS', '0')
+    one_group = _run(nb, pm, data, chains=16)
+    monkeypatch.delenv('NXB_BLINK_GROUPS')
+    monkeypatch.setenv('NXB_LEAN_WARPS', '20')
+    w20 = _run(nb, pm, data, chains=16)
+    monkeypatch.setenv('NXB_LEAN_WARPS', '7')
+    w7 = _run(nb, pm, data, chains=16)
+    for other in (dflt, one_group, w20, w7):
+        assert (base[0] == other[0]).all()
+        np.testing.assert_allclose(base[1], other[1], rtol=1e-11, atol=1e-9)
+
+
 def test_sharding_over_handles_is_invisible(nb):
     """Two handles with half the sites each (unit_offset = first global unit) give
     the same integer statistics as one handle with all sites."""
