@@ -68,7 +68,7 @@ typedef struct {
     int64_t n_pri_events;        /* retained primary events, all units */
     int64_t n_blk_events;        /* retained blink events, all units */
     int64_t data_bytes;          /* per-site constraint bytes held on the device */
-    int32_t warps_per_cta, n_ctas, smem_bytes, n_tiers;
+    int32_t warps_per_cta, n_ctas, smem_bytes, n_tiers;   /* warps / shared memory of the primary-update kernel that nxb_sweep launches */
     int32_t capP, capB, capF, capC;
     int64_t deferred_units;      /* units that needed a higher capacity tier so far */
     int64_t kernel_launches;     /* sweep-kernel launches so far */
