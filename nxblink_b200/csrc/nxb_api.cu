@@ -450,6 +450,8 @@ blink_kernel(const __grid_constant__ NxbSweepParams p) {
             __syncwarp();
             tick(c, T_STORE);
         }
+        // the bulk copies of this warp's units (blink_finish) have left shared memory and are complete
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         group_sync();
     }
     cta_epilogue(c, p, tid);
@@ -953,6 +955,7 @@ struct nxb_handle {
     int discard_pool = 1;                          // NXB_DISCARD_POOL
     int prefetch_wave = 1;                         // NXB_PREFETCH: L2 prefetch of the unit slabs one wave of work ahead
     int blink_ctas = 1;                            // co-resident blink_kernel CTAs per SM (NXB_BLINK_CTAS)
+    int bulk_store = 1;                            // NXB_BULK_STORE=0: blink_finish stores the new blink list directly instead of cp.async.bulk
     int blink_groups = 1;                          // NXB_BLINK_GROUPS=0: blink_kernel CTAs as one group (default: groups of 5 warps when the shape allows)
     int smem_per_sm = 0;
     bool sync_sweeps = false;                      // NXB_SYNC_SWEEPS=1: the host-synchronised split path (one wait per sweep)
@@ -1573,10 +1576,10 @@ static int configure_capacities(nxb_handle* h, const CapCfg& cfg) {
         int o = (int)sizeof(NxbUnitHeader);
         h->so_tol = o; o += 4 * N;
         h->so_pri = o; o += align_up(N, 4);
-        o = align_up(o, 8);
+        o = align_up(o, 16);           // (16-byte sections: bulk-async copies)
         h->so_ptm = o; o += 8 * h->gcapP;
         h->so_pcode = o; o += 4 * h->gcapP;
-        o = align_up(o, 8);
+        o = align_up(o, 16);
         h->so_btm = o; o += 8 * h->gcapB;
         h->so_bcode = o; o += 4 * h->gcapB;
         h->stride = align_up(o, 16);
@@ -1644,6 +1647,7 @@ extern "C" int nxb_create(const nxb_model_desc* d, int device, nxb_handle** out)
     if (const char* ev = getenv("NXB_PREFETCH")) h->prefetch_wave = atoi(ev) != 0;
     if (const char* ev = getenv("NXB_BLINK_CTAS")) h->blink_ctas = std::max(1, std::min(4, atoi(ev)));
     if (const char* ev = getenv("NXB_BLINK_GROUPS")) h->blink_groups = atoi(ev) != 0;
+    if (const char* ev = getenv("NXB_BULK_STORE")) h->bulk_store = atoi(ev) != 0;
     CUDA_TRY_C(cudaStreamCreate(&h->own_stream));
     h->stream = h->own_stream;
     CUDA_TRY_C(cudaEventCreate(&h->ev0));
@@ -1877,6 +1881,7 @@ static void fill_params(nxb_handle* h, NxbSweepParams& p, int kind, const Tier& 
     p.validate_only = (kind == KIND_CHECK) ? 1 : 0;
     p.batch_units = tier.blink_units;
     p.blink_groups = tier.blink_groups;
+    p.bulk_store = h->bulk_store;
     p.counts = h->d_counts; p.dwell = h->d_dwell; p.status = h->d_status;
     p.work_counter = h->d_work;
     p.perf = h->profile ? h->d_perf : nullptr;

@@ -214,6 +214,7 @@ struct NxbSweepParams {
     int validate_only;                  // primary-only kernel: load, check, do nothing else
     int batch_units;                    // blink_kernel: units per CTA batch
     int blink_groups;                   // blink_kernel: independent warp groups per CTA (each takes batch_units / groups units)
+    int bulk_store;                     // blink_kernel: new blink lists leave shared memory as bulk-async copies (cp.async.bulk)
     unsigned long long* counts;
     double* dwell;
     int* status;                        // [4]: code, unit, detail, detail

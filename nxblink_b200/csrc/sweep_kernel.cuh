@@ -883,14 +883,26 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
     }
     double* obtm = c.btm.ptr(); unsigned* obcode = c.bcode.ptr();
     const bool spill = SPLIT || total > wl.capB;
+    // SPLIT: the new list is assembled in shared memory -- times over the old ones, codes in the dead
+    // accumulator records -- and leaves as two bulk-async copies (cp.async.bulk, shared -> global) that
+    // run while the warp finishes its next unit; blink_kernel waits for them before the group's
+    // shared memory is reused.  Lists that do not fit are stored directly.
+    bool bulk = false;
+    if (SPLIT) {
+        const int acc_bytes = (int)sizeof(AccRec<MSG>) * K * p.ml.nslots;
+        bulk = p.bulk_store && total > 0 && total <= wl.capB && 4 * ((total + 3) & ~3) <= acc_bytes;
+    }
+    unsigned char* const slab_out = p.state + c.unit * p.state_stride;
     if (spill) {
         // The sweep is complete and its statistics are booked; only the shared-memory
         // arrays are too small.  Spill the new blink list straight to the HBM slab and
         // let the next capacity tier pick the unit up at the next sweep boundary.
         if (total > p.gcapB) { fail(c, NXB_ERR_STATE_CAP, total); return RC_STATECAP; }
-        unsigned char* slab = p.state + c.unit * p.state_stride;
-        obtm = (double*)(slab + p.so_btm);
-        obcode = (unsigned*)(slab + p.so_bcode);
+        if (bulk) obcode = sm_ptr<unsigned>(c.wbase + wl.off_acc);
+        else {
+            obtm = (double*)(slab_out + p.so_btm);
+            obcode = (unsigned*)(slab_out + p.so_bcode);
+        }
     }
     // (two pool records in flight per lane: the copy is bound by the L2 latency of its loads)
     for (int q0 = 0; q0 < n_mine; q0 += 2) {
@@ -907,6 +919,18 @@ __device__ __forceinline__ int blink_finish(Ctx& c, bool accumulate) {
             }
     }
     __syncwarp();
+    if (bulk && lane == 0) {
+        // generic-proxy writes to shared memory -> visible to the async proxy, then the two copies
+        const unsigned s_tm = (unsigned)__cvta_generic_to_shared(obtm);
+        const unsigned s_cd = (unsigned)__cvta_generic_to_shared(obcode);
+        const unsigned b_tm = (unsigned)((8 * total + 15) & ~15), b_cd = (unsigned)((4 * total + 15) & ~15);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(slab_out + p.so_btm), "r"(s_tm), "r"(b_tm) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(slab_out + p.so_bcode), "r"(s_cd), "r"(b_cd) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
     // The pool records of this sweep are dead now.  They live in the L2-resident scratch; tell L2
     // that their lines need no write-back (discard.global.L2), or every sweep writes ~3 KB per
     // unit of dead records to HBM when the lines are evicted.

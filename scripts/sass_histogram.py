@@ -16,7 +16,7 @@ for line in out.splitlines():
 KEYS = ('DMMA', 'HMMA', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'SYNCS', 'LDGSTS', 'LDS', 'STS', 'LDG', 'STG', 'ATOMS', 'ATOMG', 'RED', 'CCTL',
         'MUFU', 'DFMA', 'DMUL', 'DADD', 'FFMA', 'FMUL', 'FADD', 'IMAD', 'LOP3', 'SHFL', 'BAR', 'VOTE', 'BRA', 'BSSY', 'BSYNC', 'CALL')
 print('SASS mnemonic counts per kernel of', os.path.basename(lib), '(sm_100a)')
-print('(bulk-async / TMA mnemonics UTMALDG, UTMASTG, UBLKCP, SYNCS are listed to show their absence: see DESIGN.md section 4)')
+print('(bulk-async mnemonics: UBLKCP = cp.async.bulk, the shared -> global copies of the new blink lists in blink_kernel; UTMALDG / SYNCS = tensor-map loads / mbarrier, not used: see DESIGN.md section 4)')
 for k, h in hist.items():
     tot = sum(h.values())
     if tot < 200:
