@@ -14,7 +14,7 @@
 #include "tol_tables.h"
 
 #define NXB_MAX_THREADS 640
-#define NXB_LEAN_THREADS 768       /* LEAN primary-only kernel with f32 messages: 24 warps at 80 registers */
+#define NXB_LEAN_THREADS 896       /* LEAN primary-only kernel with f32 messages: 28 warps (7 per SM sub-partition) at 72 registers, no spills */
 #define NXB_TP_THREADS 640         /* tolpar_kernel: up to 20 warps (10 units x 2 warps at the p53 shape) */
 #define NXB_BLINK_GROUP_WARPS 5   /* independent warp groups of blink_kernel: 160 lanes = 8 units x 20 tracks at the p53 shape */
 #define NXB_BLINK_THREADS 800      /* 25 warps at 72 registers: 40 units x 20 tracks per CTA at the p53 shape */
@@ -890,7 +890,7 @@ struct Tier {
     int blink_warps = 0, blink_units = 0, blink_warp0 = 0, blink_groups = 1;
     // tier 0: leaner layout and warp count of the LEAN primary-only kernel (asynchronous split path)
     NxbWarpLayout pwl;
-    int pwarps = 0;
+    int pwarps = 0, pskip = 0, pwarp0 = 0;      // pskip: bytes of the model blob (the tolerance tables) the LEAN kernel does not stage
     size_t psmem = 0;
     size_t blink_smem = 0;
     // event-parallel tolerance update (every steady-state tier): one unit per group of tp_wpu warps
@@ -1030,29 +1030,32 @@ static void build_warp_layout(const NxbModelLayout& ml, bool msg_f64, int capP, 
     wl->off_rtm = take(8 * capR, 8);
     wl->off_rmask = take(4 * capR, 4);
     const int cand_end = o;
+    // lean: the FFBS arrays (first written in P3) and the pointer-jumping scratch of P2 live in the
+    // candidate arrays, which are dead once P1 has compacted the foreground events (primary_phase
+    // separates the last read from the first write with a __syncwarp / the lockstep barrier)
+    const int msz = msg_f64 ? 8 : 4;
+    const int ffbs_bytes = align_up(msz * NXB_PPAD, 8) + align_up(msz * capF, 8) + 8 * (capF + 1);
+    const int a0 = align_up(wl->off_rtm, 16);
+    const bool alias_ffbs = lean && a0 + ffbs_bytes <= cand_end;
+    const bool alias_jump = alias_ffbs && a0 + ffbs_bytes + 4 * N <= cand_end;
     wl->off_ftm = take(8 * capF, 8);
     wl->off_fmask = take(4 * capF, 4);
     wl->off_fedge = take(2 * capF, 2);
     wl->off_nchunk = take(4 * N, 4);
-    wl->off_jump = take(4 * N, 4);
+    wl->off_jump = alias_jump ? a0 + ffbs_bytes : take(4 * N, 4);
     wl->off_par = take(2 * (capF + 1), 2);
     wl->off_toland = take(4 * (capF + 1), 4);
     wl->off_callow = take(8 * (capF + 1), 8);
     wl->off_cstate = take(capF + 1, 1);
-    {
-        const int msz = msg_f64 ? 8 : 4;
-        const int need = align_up(msz * NXB_PPAD, 8) + align_up(msz * capF, 8) + 8 * (capF + 1);
-        const int a0 = align_up(wl->off_rtm, 16);
-        if (lean && a0 + need <= cand_end) {
-            int oo = a0;
-            wl->off_msg = oo; oo += align_up(msz * NXB_PPAD, 8);
-            wl->off_finv = oo; oo += align_up(msz * capF, 8);
-            wl->off_fu = oo;
-        } else {
-            wl->off_msg = take(msz * NXB_PPAD, 16);     // one staging row; the messages are global
-            wl->off_finv = take(msz * capF, 8);
-            wl->off_fu = take(8 * (capF + 1), 8);
-        }
+    if (alias_ffbs) {
+        int oo = a0;
+        wl->off_msg = oo; oo += align_up(msz * NXB_PPAD, 8);
+        wl->off_finv = oo; oo += align_up(msz * capF, 8);
+        wl->off_fu = oo;
+    } else {
+        wl->off_msg = take(msz * NXB_PPAD, 16);     // one staging row; the messages are global
+        wl->off_finv = take(msz * capF, 8);
+        wl->off_fu = take(8 * (capF + 1), 8);
     }
     const int end_pri = o;
     // blink-phase scratch (aliases the primary-phase scratch)
@@ -1487,11 +1490,14 @@ static int configure_capacities(nxb_handle* h, const CapCfg& cfg) {
                     {
                         // f32 messages: 80 registers per thread leave room for 24 warps (6 per SM sub-partition)
                         const int cap_w = (cfg.max_warps > 0) ? max_warps : (h->msg_f64 ? NXB_MAX_THREADS / 32 : NXB_LEAN_THREADS / 32);
-                        tier.pwarps = std::min((h->max_smem - fixed) / tier.pwl.bytes, cap_w);
+                        // the primary update reads none of the tolerance tables (the prefix of the blob)
+                        tier.pskip = ml.blink_bytes;
+                        tier.pwarp0 = fixed - tier.pskip;
+                        tier.pwarps = std::min((h->max_smem - tier.pwarp0) / tier.pwl.bytes, cap_w);
                         if (getenv("NXB_LEAN_WARPS")) tier.pwarps = std::min(tier.pwarps, std::max(1, atoi(getenv("NXB_LEAN_WARPS"))));
-                        tier.psmem = (size_t)fixed + (size_t)tier.pwarps * tier.pwl.bytes;
+                        tier.psmem = (size_t)tier.pwarp0 + (size_t)tier.pwarps * tier.pwl.bytes;
                         if (getenv("NXB_DEBUG_LAYOUT"))
-                            fprintf(stderr, "lean primary layout: %d bytes per warp, %d warps\n", tier.pwl.bytes, tier.pwarps);
+                            fprintf(stderr, "lean primary layout: fixed %d, %d bytes per warp, %d warps\n", tier.pwarp0, tier.pwl.bytes, tier.pwarps);
                     }
                     build_blink_layout(ml, h->msg_f64, tier.wl.capP, tier.wl.capB, &tier.bwl);
                     const int bfixed = ml.blink_bytes + stats_bytes;      // model prefix + statistic partials
@@ -1864,6 +1870,20 @@ static void fill_params(nxb_handle* h, NxbSweepParams& p, int kind, const Tier& 
         p.tl = tier.tl;
     }
     p.blob = h->d_blob; p.rmax_tab = h->d_rmax;
+    if (kind == KIND_PRIMARY_LEAN && tier.pskip > 0) {
+        // stage blob[pskip:] at shared offset 0: every table of the primary update moves down by
+        // pskip; the tolerance tables (never touched by this kernel) get an offset that faults
+        const int skip = tier.pskip;
+        NxbModelLayout& m = p.ml;
+        int* const moved[] = {&m.off_stats, &m.off_eperm, &m.off_parent, &m.off_tma, &m.off_len, &m.off_rate,
+            &m.off_lam_pri, &m.off_p0_pri, &m.off_lam_blk, &m.off_p0_blk, &m.off_gsc_blk, &m.off_qval, &m.off_qinfo,
+            &m.off_qptr, &m.off_pi, &m.off_clsmask, &m.off_ell_info, &m.off_ell_q, &m.off_qdt};
+        for (int* q : moved) *q -= skip;
+        m.bytes -= skip;
+        m.off_slot = m.off_edgerec = m.off_cls = m.off_qm = m.off_ancmask = 0x7ffffff0;
+        p.blob = h->d_blob + skip;
+        p.smem_warp0 = tier.pwarp0;
+    }
     p.pri_ok = h->d_pri_ok; p.tol_true_ok = h->d_tt; p.tol_false_ok = h->d_tf;
     p.state = h->d_state; p.state_stride = h->stride;
     p.gcapP = h->gcapP; p.gcapB = h->gcapB;
@@ -2077,6 +2097,7 @@ static int run_split_async(nxb_handle* h, unsigned target, unsigned accum_from) 
     // 131 072 units (20 warps: 10 -> 10.15)
     const int pw = t0.pwarps;
     const int gw = (h->lockstep < 0 && pw >= 8) ? (pw % 8 == 0 ? 8 : (pw % 10 == 0 ? 10 : pw / 2)) : group_warps_for(h, pw);
+    // (28 warps at 72 registers: 14 -> 8.84, 7 -> 9.38, 28 -> 9.47, 4 -> 11.9; 24 warps of the same build in groups of 8: 9.39)
     const int nblind = (int)std::min<size_t>(2, h->tiers.size() - 1);
     if (h->evpool.empty()) {
         h->evpool.resize(4 * NXB_ASYNC_CHUNK);

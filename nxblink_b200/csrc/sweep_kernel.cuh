@@ -405,6 +405,7 @@ __device__ __forceinline__ int primary_phase(Ctx& c, bool init, bool accumulate)
             fedge[dst + i] = (unsigned short)e;
         }
     }
+    __syncwarp();       // (the lean layout reuses the candidate arrays from here on: jump[], later the FFBS arrays)
     // ---- P2: chunk structure (chunking.py:158-261) --------------------------------
     // chunk 0 holds the root; foreground event j opens chunk j+1.
     for (int v = lane; v < N; v += 32) {
