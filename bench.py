@@ -4,23 +4,26 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
 A *step* is one full Gibbs sweep (primary track + all 20 tolerance tracks,
-statistics accumulated) of every (site, chain) unit resident on the GPU(s):
+statistics accumulated) of every (site, chain) unit, plus -- at N > 1 -- the NCCL
+all-reduce of the statistics, all inside the timed region and on one CUDA stream:
 BASELINE.json configs[2] -- the p53-shaped codon blink model (49-node tree, 61
 codon states, 20 tolerance classes), synthetic alignment, 15 625 sites x 64
-chains = 10^6 units per GPU.  One process per GPU; units are sharded by site with
-no data-path collective ("scaling": "weak": every GPU holds 10^6 units); the one
-NCCL all-reduce of the statistics happens after the timed region, as it would once
-per EM iteration.
+chains = 10^6 units IN TOTAL, the same global problem for every N (sites sharded
+over the ranks, no data-path collective: "scaling": "strong"; the weak-scaling
+figure, 10^6 units on every GPU, is reported beside it in `weak`).  One process
+per GPU.
 
 Printed JSON (one line, rank 0): see the contract in the task description.  In
 short: `value` = whole-job site-sweeps/s with everything resident in HBM, timed
 with CUDA events on the launching stream (max over ranks); `e2e` = the same metric
 through the public host-buffer API with the step's site data uploaded from pinned
 host memory and the statistics read back inside the timed region; `roofline` =
-algorithmic HBM bytes of the sweep kernel / its measured duration against the
+algorithmic HBM bytes of the dominant kernel / its measured duration against the
 measured copy bandwidth in MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle
 port (oracle/blink_oracle.py, a restatement of the reference's own Python path)
-timed on this box's host cores on a bounded sample.
+timed on this box's host cores on a bounded sample; `precision` = the same run
+with f64 FFBS messages; `statistics_hash` = hash of the all-reduced integer
+statistics (equal for every N); `configs` (N = 1) = BASELINE configs[1] and [4].
 
 `--impl reference` times that CPU path alone (the reference is pure Python whose
 FFBS lives in an un-vendored dependency, so oracle/_ref cannot exist; the oracle
